@@ -1,0 +1,394 @@
+// Device-side graph structure: destination CSR (+ implicit self-loops), source slot lists,
+// graph pointers, and the packed-store collate.  Integer work, HBM/latency bound.
+// Replaces PyG add_self_loops / scatter index handling / Batch.from_data_list
+// (reference gnnepcsaft/train/models.py:118-121,133; train/train.py:74-79).
+#include "common.cuh"
+
+static int g_sm_count = 0;
+int gnn_sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_sm_count = n;
+        else
+            g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+extern "C" const char* gnn_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case GNN_ERR_BAD_ARG: return "gnnepcsaft_b200: bad argument";
+        case GNN_ERR_TOO_LARGE: return "gnnepcsaft_b200: problem too large for this kernel";
+        case GNN_ERR_UNSUPPORTED: return "gnnepcsaft_b200: unsupported configuration";
+        case GNN_ERR_WORKSPACE: return "gnnepcsaft_b200: workspace too small";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "gnnepcsaft_b200: unknown error";
+    }
+}
+extern "C" int gnn_abi_version(void) { return 1; }
+extern "C" int gnn_device_info(int32_t* out_host) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, dev);
+    if (e != cudaSuccess) return (int)e;
+    out_host[0] = p.multiProcessorCount;
+    out_host[1] = p.major;
+    out_host[2] = p.minor;
+    return 0;
+}
+
+// ------------------------------------------------------------------ exclusive scan (int32)
+// 3-kernel scan: per-block scan of SCAN_ITEMS*SCAN_THREADS elements, scan of block totals by
+// one block, add-back.  In place.
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* smem_warp, int& block_total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(GNN_FULL_MASK, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) smem_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < (int)(blockDim.x >> 5)) ? smem_warp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(GNN_FULL_MASK, winc, o);
+            if (lane >= o) winc += n;
+        }
+        smem_warp[lane] = winc - w;       // exclusive warp offsets
+        if (lane == 31) smem_warp[32] = winc;
+    }
+    __syncthreads();
+    block_total = smem_warp[32];
+    int res = smem_warp[warp] + inc - v;
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tiles_kernel(int* data, int64_t n, int* block_sums) {
+    __shared__ int sw[33];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int local = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? data[base + k] : 0;
+        local += v[k];
+    }
+    int total;
+    int off = block_exclusive_scan(local, sw, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) data[base + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(int* block_sums, int nblocks) {
+    __shared__ int sw[33];
+    int carry = 0;
+    for (int start = 0; start < nblocks; start += SCAN_THREADS) {
+        int i = start + threadIdx.x;
+        int v = i < nblocks ? block_sums[i] : 0;
+        int total;
+        int off = block_exclusive_scan(v, sw, total);
+        if (i < nblocks) block_sums[i] = off + carry;
+        carry += total;
+    }
+}
+
+__global__ void scan_add_kernel(int* data, int64_t n, const int* block_sums) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) data[i] += block_sums[i / SCAN_TILE];
+}
+
+// exclusive scan of data[0..n) in place; block_sums needs ceil(n/SCAN_TILE) ints
+static int exclusive_scan_i32(int* data, int64_t n, int* block_sums, cudaStream_t st) {
+    if (n <= 0) return 0;
+    int64_t nblocks = gnn_ceil_div(n, SCAN_TILE);
+    if (nblocks > (1 << 30)) return GNN_ERR_TOO_LARGE;
+    scan_tiles_kernel<<<(unsigned)nblocks, SCAN_THREADS, 0, st>>>(data, n, block_sums);
+    if (nblocks > 1) {
+        scan_block_sums_kernel<<<1, SCAN_THREADS, 0, st>>>(block_sums, (int)nblocks);
+        scan_add_kernel<<<(unsigned)gnn_ceil_div(n, 256), 256, 0, st>>>(data, n, block_sums);
+    }
+    return gnn_launch_status();
+}
+
+// ------------------------------------------------------------------ CSR build
+__global__ void csr_init_counts_kernel(int* rowptr, int* srcptr, int* fill_in, int* fill_out,
+                                       int64_t n, int init) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) {
+        int v = i < n ? init : 0;
+        rowptr[i] = v;
+        srcptr[i] = v;
+    }
+    if (i < n) {
+        fill_in[i] = 0;
+        fill_out[i] = 0;
+    }
+}
+
+__global__ void csr_count_kernel(const int64_t* __restrict__ edge_index, int64_t n, int64_t e,
+                                 int* rowptr, int* srcptr, int* err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    int64_t s = edge_index[i], d = edge_index[e + i];
+    if (s < 0 || s >= n || d < 0 || d >= n) {
+        if (err) atomicExch(err, 1);
+        return;
+    }
+    atomicAdd(&rowptr[d], 1);
+    atomicAdd(&srcptr[s], 1);
+}
+
+__global__ void csr_fill_eid_kernel(const int64_t* __restrict__ edge_index, int64_t n, int64_t e,
+                                    int self_loops, const int* __restrict__ rowptr, int* fill_in,
+                                    int* col_eid) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = e + (self_loops ? n : 0);
+    if (i >= total) return;
+    int64_t d;
+    if (i < e) {
+        int64_t s = edge_index[i];
+        d = edge_index[e + i];
+        if (s < 0 || s >= n || d < 0 || d >= n) return;
+    } else {
+        d = i - e;
+    }
+    int pos = atomicAdd(&fill_in[d], 1);
+    col_eid[rowptr[d] + pos] = (int)i;
+}
+
+// ascending insertion sort of every segment (segments are tiny: in-degree of an atom)
+__global__ void sort_segments_kernel(const int* __restrict__ ptr, int64_t n, int* vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int b = ptr[i], e = ptr[i + 1];
+    for (int a = b + 1; a < e; ++a) {
+        int key = vals[a];
+        int j = a - 1;
+        while (j >= b && vals[j] > key) {
+            vals[j + 1] = vals[j];
+            --j;
+        }
+        vals[j + 1] = key;
+    }
+}
+
+__global__ void csr_finalize_kernel(const int64_t* __restrict__ edge_index,
+                                    const int64_t* __restrict__ edge_attr, int64_t n, int64_t e,
+                                    int64_t total, const int* __restrict__ col_eid, int* col_src,
+                                    uint8_t* col_code, const int* __restrict__ rowptr,
+                                    const int* __restrict__ srcptr, int* fill_out, int* src_slot, int* err) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= total || s >= rowptr[n]) return;   // fewer slots than edges only if edges were invalid
+    int eid = col_eid[s];
+    int src, code = 0;
+    if (eid < e) {
+        src = (int)edge_index[eid];
+        int64_t a0 = edge_attr[3 * (int64_t)eid], a1 = edge_attr[3 * (int64_t)eid + 1],
+                a2 = edge_attr[3 * (int64_t)eid + 2];
+        if (a0 < 0 || a0 >= 5 || a1 < 0 || a1 >= 6 || a2 < 0 || a2 >= 2) {
+            if (err) atomicExch(err, 2);
+            a0 = a1 = a2 = 0;
+        }
+        code = (int)(a0 * 12 + a1 * 2 + a2);
+    } else {
+        src = eid - (int)e;
+    }
+    col_src[s] = src;
+    col_code[s] = (uint8_t)code;
+    int pos = atomicAdd(&fill_out[src], 1);
+    src_slot[srcptr[src] + pos] = (int)s;
+}
+
+extern "C" int64_t gnn_build_csr_workspace_bytes(int64_t n, int64_t e) {
+    (void)e;
+    int64_t ints = 2 * (n + 1) + 2 * (gnn_ceil_div(n + 1, SCAN_TILE) + 1);
+    return gnn_align_up(ints * 4, 256);
+}
+
+extern "C" int gnn_build_csr(const int64_t* edge_index, const int64_t* edge_attr, int64_t n,
+                             int64_t e, int self_loops, int32_t* rowptr, int32_t* col_src,
+                             uint8_t* col_code, int32_t* col_eid, int32_t* srcptr,
+                             int32_t* src_slot, int32_t* err_flag, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+    if (n < 0 || e < 0) return GNN_ERR_BAD_ARG;
+    int64_t total = e + (self_loops ? n : 0);
+    if (n >= (1ll << 31) - 1 || total >= (1ll << 31) - 1) return GNN_ERR_TOO_LARGE;
+    if (workspace_bytes < gnn_build_csr_workspace_bytes(n, e)) return GNN_ERR_WORKSPACE;
+    cudaStream_t st = gnn_stream(stream);
+    int* ws = reinterpret_cast<int*>(workspace);
+    int* fill_in = ws;
+    int* fill_out = fill_in + (n + 1);
+    int* bs_in = fill_out + (n + 1);
+    int* bs_out = bs_in + gnn_ceil_div(n + 1, SCAN_TILE) + 1;
+    const int T = 256;
+    if (err_flag) cudaMemsetAsync(err_flag, 0, sizeof(int), st);
+    csr_init_counts_kernel<<<(unsigned)gnn_ceil_div(n + 1, T), T, 0, st>>>(rowptr, srcptr, fill_in, fill_out, n,
+                                                                             self_loops ? 1 : 0);
+    if (e > 0)
+        csr_count_kernel<<<(unsigned)gnn_ceil_div(e, T), T, 0, st>>>(edge_index, n, e, rowptr, srcptr, err_flag);
+    int rc = exclusive_scan_i32(rowptr, n + 1, bs_in, st);
+    if (rc) return rc;
+    rc = exclusive_scan_i32(srcptr, n + 1, bs_out, st);
+    if (rc) return rc;
+    if (total > 0) {
+        csr_fill_eid_kernel<<<(unsigned)gnn_ceil_div(total, T), T, 0, st>>>(edge_index, n, e, self_loops, rowptr,
+                                                                             fill_in, col_eid);
+        if (n > 0) sort_segments_kernel<<<(unsigned)gnn_ceil_div(n, T), T, 0, st>>>(rowptr, n, col_eid);
+        csr_finalize_kernel<<<(unsigned)gnn_ceil_div(total, T), T, 0, st>>>(
+            edge_index, edge_attr, n, e, total, col_eid, col_src, col_code, rowptr, srcptr, fill_out, src_slot,
+            err_flag);
+        if (n > 0) sort_segments_kernel<<<(unsigned)gnn_ceil_div(n, T), T, 0, st>>>(srcptr, n, src_slot);
+    }
+    return gnn_launch_status();
+}
+
+// ------------------------------------------------------------------ graph_ptr from batch
+__global__ void graph_count_kernel(const int64_t* __restrict__ batch, int64_t n, int64_t b,
+                                   int* node_graph, int* graph_ptr) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t g = batch[i];
+    if (g < 0) g = 0;
+    if (g >= b) g = b - 1;
+    node_graph[i] = (int)g;
+    // batch is sorted (PyG Batch): graph g starts where batch changes
+    if (i == 0 || batch[i - 1] != batch[i]) {
+        // every graph in (prev, g] that has no nodes also starts here
+        int64_t prev = i == 0 ? -1 : batch[i - 1];
+        if (prev < -1) prev = -1;
+        for (int64_t k = prev + 1; k <= g; ++k) graph_ptr[k] = (int)i;
+    }
+    if (i == n - 1)
+        for (int64_t k = g + 1; k <= b; ++k) graph_ptr[k] = (int)n;
+}
+__global__ void graph_ptr_empty_kernel(int* graph_ptr, int64_t b) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= b) graph_ptr[i] = 0;
+}
+
+extern "C" int64_t gnn_graph_ptr_workspace_bytes(int64_t) { return 256; }
+extern "C" int gnn_graph_ptr_from_batch(const int64_t* batch, int64_t n, int64_t b, int32_t* node_graph,
+                                        int32_t* graph_ptr, void*, int64_t, void* stream) {
+    if (n < 0 || b < 1 || n >= (1ll << 31)) return GNN_ERR_BAD_ARG;
+    cudaStream_t st = gnn_stream(stream);
+    if (n == 0) {
+        graph_ptr_empty_kernel<<<(unsigned)gnn_ceil_div(b + 1, 256), 256, 0, st>>>(graph_ptr, b);
+        return gnn_launch_status();
+    }
+    graph_count_kernel<<<(unsigned)gnn_ceil_div(n, 256), 256, 0, st>>>(batch, n, b, node_graph, graph_ptr);
+    return gnn_launch_status();
+}
+
+// ------------------------------------------------------------------ collate from a packed store
+// Offsets: counts -> exclusive scans (int64 outputs; the scan itself runs on int32 counts).
+__global__ void collate_counts_kernel(const int64_t* __restrict__ ids, int64_t nb,
+                                      const int64_t* __restrict__ node_slices,
+                                      const int64_t* __restrict__ edge_slices, int* ncnt, int* ecnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nb) return;
+    if (i == nb) {
+        ncnt[i] = 0;
+        ecnt[i] = 0;
+        return;
+    }
+    int64_t g = ids[i];
+    ncnt[i] = (int)(node_slices[g + 1] - node_slices[g]);
+    ecnt[i] = (int)(edge_slices[g + 1] - edge_slices[g]);
+}
+__global__ void widen_kernel(const int* __restrict__ a, const int* __restrict__ b, int64_t n, int64_t* oa,
+                             int64_t* ob) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        oa[i] = a[i];
+        ob[i] = b[i];
+    }
+}
+
+extern "C" int64_t gnn_collate_workspace_bytes(int64_t nb) {
+    int64_t ints = 2 * (nb + 1) + 2 * (gnn_ceil_div(nb + 1, SCAN_TILE) + 1);
+    return gnn_align_up(ints * 4, 256);
+}
+extern "C" int gnn_collate_offsets(const int64_t* ids, int64_t nb, const int64_t* node_slices,
+                                   const int64_t* edge_slices, int64_t* out_ptr, int64_t* out_eptr,
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
+    if (nb < 0) return GNN_ERR_BAD_ARG;
+    if (workspace_bytes < gnn_collate_workspace_bytes(nb)) return GNN_ERR_WORKSPACE;
+    cudaStream_t st = gnn_stream(stream);
+    int* ncnt = reinterpret_cast<int*>(workspace);
+    int* ecnt = ncnt + (nb + 1);
+    int* bs0 = ecnt + (nb + 1);
+    int* bs1 = bs0 + gnn_ceil_div(nb + 1, SCAN_TILE) + 1;
+    collate_counts_kernel<<<(unsigned)gnn_ceil_div(nb + 1, 256), 256, 0, st>>>(ids, nb, node_slices, edge_slices,
+                                                                                ncnt, ecnt);
+    int rc = exclusive_scan_i32(ncnt, nb + 1, bs0, st);
+    if (rc) return rc;
+    rc = exclusive_scan_i32(ecnt, nb + 1, bs1, st);
+    if (rc) return rc;
+    widen_kernel<<<(unsigned)gnn_ceil_div(nb + 1, 256), 256, 0, st>>>(ncnt, ecnt, nb + 1, out_ptr, out_eptr);
+    return gnn_launch_status();
+}
+
+// one warp per selected graph: copies its node rows / edge rows, adds the node offset to
+// edge_index and writes the batch vector.
+__global__ void collate_gather_kernel(const int64_t* __restrict__ ids, int64_t nb,
+                                      const int64_t* __restrict__ node_slices,
+                                      const int64_t* __restrict__ edge_slices,
+                                      const int64_t* __restrict__ sx, const int64_t* __restrict__ sei,
+                                      int64_t store_e, const int64_t* __restrict__ sea,
+                                      const int64_t* __restrict__ optr, const int64_t* __restrict__ oeptr,
+                                      int64_t tot_e, int64_t* x, int64_t* ei, int64_t* ea, int64_t* batch) {
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = w; b < nb; b += nwarps) {
+        int64_t g = ids[b];
+        int64_t n0 = node_slices[g], n1 = node_slices[g + 1];
+        int64_t e0 = edge_slices[g], e1 = edge_slices[g + 1];
+        int64_t on = optr[b], oe = oeptr[b];
+        int64_t nn = n1 - n0, ne = e1 - e0;
+        for (int64_t k = lane; k < nn * GNN_NUM_ATOM_FEATS; k += 32) x[on * GNN_NUM_ATOM_FEATS + k] = sx[n0 * GNN_NUM_ATOM_FEATS + k];
+        for (int64_t k = lane; k < nn; k += 32) batch[on + k] = b;
+        for (int64_t k = lane; k < ne * GNN_NUM_BOND_FEATS; k += 32) ea[oe * GNN_NUM_BOND_FEATS + k] = sea[e0 * GNN_NUM_BOND_FEATS + k];
+        for (int64_t k = lane; k < ne; k += 32) {
+            ei[oe + k] = sei[e0 + k] + on;
+            ei[tot_e + oe + k] = sei[store_e + e0 + k] + on;
+        }
+    }
+}
+
+extern "C" int gnn_collate_gather(const int64_t* ids, int64_t nb, const int64_t* node_slices,
+                                  const int64_t* edge_slices, const int64_t* store_x,
+                                  const int64_t* store_edge_index, int64_t store_num_edges,
+                                  const int64_t* store_edge_attr, const int64_t* out_ptr,
+                                  const int64_t* out_eptr, int64_t total_nodes, int64_t total_edges,
+                                  int64_t* x, int64_t* edge_index, int64_t* edge_attr, int64_t* batch,
+                                  void* stream) {
+    (void)total_nodes;
+    if (nb <= 0) return nb == 0 ? 0 : GNN_ERR_BAD_ARG;
+    cudaStream_t st = gnn_stream(stream);
+    int64_t blocks = gnn_ceil_div(nb, 8);
+    int64_t cap = (int64_t)gnn_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    collate_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(ids, nb, node_slices, edge_slices, store_x,
+                                                            store_edge_index, store_num_edges, store_edge_attr,
+                                                            out_ptr, out_eptr, total_edges, x, edge_index,
+                                                            edge_attr, batch);
+    return gnn_launch_status();
+}

@@ -1,0 +1,631 @@
+"""Drop-in `PNAPCSAFT` for the reference's gnnepcsaft/train/models.py:28-135, on sm_100a kernels.
+
+Same constructor (`hidden_dim, pna_params, mlp_params`), same `forward(data)` contract
+(`data.x [N,9] i64`, `data.edge_index [2,E] i64`, `data.edge_attr [E,3] i64`, `data.batch [N] i64`
+or None -> `float32 [B, num_para]`) and the same `state_dict()` keys, so
+reference checkpoints load with `strict=True`.  The submodules below only *hold* parameters
+under the reference's names; the arithmetic runs in the CUDA library behind the C ABI
+(include/gnnepcsaft_b200.h).  There is no CPU / PyG / torch_scatter fallback: CPU tensors raise.
+"""
+
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from .. import _lib
+from ..data.graph import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS, NUM_BOND_CODES
+
+TOWERS = 2  # reference models.py:76
+
+
+@dataclasses.dataclass
+class PnaconvsParams:
+    "Parameters for pna convolutions (reference models.py:28-37)."
+    propagation_depth: int
+    pre_layers: int
+    post_layers: int
+    deg: torch.Tensor
+    dropout: float = 0.0
+    skip_connections: bool = False
+    self_loops: bool = False
+
+
+@dataclasses.dataclass
+class ReadoutMLPParams:
+    "Parameters for the MLP layers (reference models.py:40-45)."
+    num_mlp_layers: int
+    num_para: int
+    dropout: float = 0.0
+
+
+# ----------------------------------------------------------------------------- parameter holders
+class _AtomEncoder(nn.Module):           # ogb AtomEncoder: atom_embedding_list.{k}.weight
+    def __init__(self, emb_dim):
+        super().__init__()
+        self.atom_embedding_list = nn.ModuleList()
+        for dim in ATOM_FEATURE_DIMS:
+            emb = nn.Embedding(dim, emb_dim)
+            nn.init.xavier_uniform_(emb.weight.data)
+            self.atom_embedding_list.append(emb)
+
+
+class _BondEncoder(nn.Module):           # ogb BondEncoder: bond_embedding_list.{k}.weight
+    def __init__(self, emb_dim):
+        super().__init__()
+        self.bond_embedding_list = nn.ModuleList()
+        for dim in BOND_FEATURE_DIMS:
+            emb = nn.Embedding(dim, emb_dim)
+            nn.init.xavier_uniform_(emb.weight.data)
+            self.bond_embedding_list.append(emb)
+
+
+class _DegreeScalerAggregation(nn.Module):   # PyG DegreeScalerAggregation buffers
+    def __init__(self, deg: torch.Tensor):
+        super().__init__()
+        deg = deg.to(torch.float)
+        num_nodes = int(deg.sum())
+        bins = torch.arange(deg.numel())
+        self.register_buffer("avg_deg_lin", torch.tensor([float((bins * deg).sum()) / num_nodes], dtype=torch.float))
+        self.register_buffer("avg_deg_log",
+                             torch.tensor([float(((bins + 1).log() * deg).sum()) / num_nodes], dtype=torch.float))
+
+
+class _PNAConv(nn.Module):               # PyG PNAConv parameter layout (towers=2, divide_input=False)
+    def __init__(self, hidden, deg, pre_layers, post_layers):
+        super().__init__()
+        f_in, f_out = hidden, hidden // TOWERS
+        self.aggr_module = _DegreeScalerAggregation(deg)
+        self.edge_encoder = nn.Linear(hidden, f_in)
+        self.pre_nns = nn.ModuleList()
+        self.post_nns = nn.ModuleList()
+        for _ in range(TOWERS):
+            mods = [nn.Linear(3 * f_in, f_in)]
+            for _ in range(pre_layers - 1):
+                mods += [nn.ReLU(), nn.Linear(f_in, f_in)]
+            self.pre_nns.append(nn.Sequential(*mods))
+            mods = [nn.Linear(13 * f_in, f_out)]
+            for _ in range(post_layers - 1):
+                mods += [nn.ReLU(), nn.Linear(f_out, f_out)]
+            self.post_nns.append(nn.Sequential(*mods))
+        self.lin = nn.Linear(hidden, hidden)
+
+
+class _BatchNorm(nn.Module):             # PyG BatchNorm: `.module` = BatchNorm1d
+    def __init__(self, channels):
+        super().__init__()
+        self.module = nn.BatchNorm1d(channels)
+
+
+# ----------------------------------------------------------------------------- helpers
+def _c(name, *args):
+    _lib.call(name, *args, _lib.stream_ptr())
+
+
+class _Workspace:
+    """Grow-only scratch buffers per device (BN partials, CSR scratch)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, key, nbytes, device):
+        t = self.buf.get((key, device))
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self.buf[(key, device)] = t
+        return t
+
+
+_WS = _Workspace()
+
+
+class GraphStructure:
+    """Device-side CSR / slot lists of one batch (gnn_build_csr, gnn_graph_ptr_from_batch)."""
+
+    def __init__(self, edge_index, edge_attr, batch, num_nodes, num_graphs, self_loops, ptr=None):
+        dev = edge_index.device
+        n, e = int(num_nodes), int(edge_index.shape[1])
+        ep = e + (n if self_loops else 0)
+        self.n, self.e, self.ep, self.b = n, e, ep, int(num_graphs)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.rowptr = torch.empty(n + 1, **i32)
+        self.srcptr = torch.empty(n + 1, **i32)
+        self.col_src = torch.empty(max(ep, 1), **i32)
+        self.col_eid = torch.empty(max(ep, 1), **i32)
+        self.src_slot = torch.empty(max(ep, 1), **i32)
+        self.col_code = torch.empty(max(ep, 1), dtype=torch.uint8, device=dev)
+        self.err = torch.zeros(1, **i32)
+        nbytes = _lib.query("gnn_build_csr_workspace_bytes", n, e)
+        ws = _WS.get("csr", nbytes, dev)
+        _c("gnn_build_csr", edge_index, edge_attr, n, e, 1 if self_loops else 0, self.rowptr, self.col_src,
+           self.col_code, self.col_eid, self.srcptr, self.src_slot, self.err, ws, ws.numel())
+        self.graph_ptr = torch.empty(self.b + 1, **i32)
+        if batch is None:
+            self.node_graph = None
+            self.graph_ptr.copy_(torch.tensor([0, n], dtype=torch.int32), non_blocking=False)
+        else:
+            self.node_graph = torch.empty(max(n, 1), **i32)
+            _c("gnn_graph_ptr_from_batch", batch, n, self.b, self.node_graph, self.graph_ptr, None, 0)
+
+    def check(self):
+        """Synchronising validity check (the reference would raise IndexError inside torch)."""
+        code = int(self.err.item())
+        if code:
+            raise IndexError("edge_index / edge_attr out of range" if code == 1 else "bond feature out of range")
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"gnnepcsaft_b200: {what} is on {t.device}; this implementation has no CPU path "
+            "(move the model and the batch to a CUDA device)")
+
+
+# ----------------------------------------------------------------------------- the model
+class PNAPCSAFT(nn.Module):
+    """Graph neural network to predict ePC-SAFT parameters (reference models.py:48-135)."""
+
+    def __init__(self, hidden_dim: int, pna_params: PnaconvsParams, mlp_params: ReadoutMLPParams):
+        super().__init__()
+        if hidden_dim % 4 != 0:
+            raise ValueError("hidden_dim must be divisible by 4 (towers=2, head uses H//2 and H//4)")
+        if hidden_dim % 8 != 0:
+            raise ValueError("gnnepcsaft_b200 kernels use 128-bit accesses: hidden_dim must be a multiple of 8")
+        self.hidden_dim = hidden_dim
+        self.pna_params = pna_params
+        self.mlp_params = mlp_params
+        self.convs = nn.ModuleList()
+        self.batch_norms = nn.ModuleList()
+        self.node_embed = _AtomEncoder(hidden_dim)
+        self.edge_embed = _BondEncoder(hidden_dim)
+        for _ in range(pna_params.propagation_depth):
+            self.convs.append(_PNAConv(hidden_dim, pna_params.deg, pna_params.pre_layers, pna_params.post_layers))
+            self.batch_norms.append(_BatchNorm(hidden_dim))
+        self.mlp = nn.Sequential()
+        for _ in range(mlp_params.num_mlp_layers):
+            self.mlp.append(nn.Linear(hidden_dim, hidden_dim))
+            self.mlp.append(nn.BatchNorm1d(hidden_dim))
+            self.mlp.append(nn.ReLU())
+            self.mlp.append(nn.Dropout(p=mlp_params.dropout))
+        self.mlp.append(nn.Sequential(
+            nn.Linear(hidden_dim, hidden_dim // 2), nn.BatchNorm1d(hidden_dim // 2), nn.ReLU(),
+            nn.Dropout(p=mlp_params.dropout),
+            nn.Linear(hidden_dim // 2, hidden_dim // 4), nn.BatchNorm1d(hidden_dim // 4), nn.ReLU(),
+            nn.Dropout(p=mlp_params.dropout),
+            nn.Linear(hidden_dim // 4, mlp_params.num_para)))
+        self._arena: Optional[torch.Tensor] = None
+        self._arena_offsets: List[int] = []
+        self._row_off = None
+
+    # ---- flat parameter arena -------------------------------------------------------------
+    def _param_list(self):
+        return list(self.parameters())
+
+    def _arena_valid(self) -> bool:
+        if self._arena is None:
+            return False
+        ps = self._param_list()
+        base = self._arena.data_ptr()
+        for p, off in ((ps[0], self._arena_offsets[0]), (ps[-1], self._arena_offsets[-1])):
+            if p.data_ptr() != base + 4 * off or p.device != self._arena.device:
+                return False
+        return True
+
+    def flatten_parameters(self) -> torch.Tensor:
+        """(Re)build the flat fp32 arena; every parameter becomes a view at a 16-byte aligned offset.
+
+        Layer l's conv parameters sit at a constant stride, the 9 atom tables / 3 bond tables are
+        contiguous; kernels rely on both.  Called lazily by forward after `.to()` / `.cuda()`.
+        """
+        ps = self._param_list()
+        for p in ps:
+            if p.dtype != torch.float32:
+                raise RuntimeError("gnnepcsaft_b200 kernels are fp32; float64 / half models are not supported "
+                                   "(the reference's `.to(torch.float64)` evaluation must stay on fp32 here)")
+        offsets, total = [], 0
+        for p in ps:
+            offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        arena = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
+        with torch.no_grad():
+            for p, off in zip(ps, offsets):
+                view = arena[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+        self._arena, self._arena_offsets = arena, offsets
+        self._row_off = None
+        return arena
+
+    def arena(self) -> torch.Tensor:
+        if not self._arena_valid():
+            self.flatten_parameters()
+        return self._arena
+
+    def _offset_of(self, p: torch.Tensor) -> int:
+        return (p.data_ptr() - self._arena.data_ptr()) // 4
+
+    def _consts(self, device):
+        if self._row_off is None or self._row_off.device != device:
+            off = [0]
+            for d in ATOM_FEATURE_DIMS[:-1]:
+                off.append(off[-1] + d)
+            self._row_off = torch.tensor(off, dtype=torch.int32, device=device)
+        return self._row_off
+
+    # ---- forward ----------------------------------------------------------------------------
+    def forward(self, data):
+        """Forward pass of the model (reference models.py:105-135)."""
+        x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, getattr(data, "batch", None)
+        _require_cuda(x, "data.x")
+        arena = self.arena()
+        _require_cuda(arena, "the model")
+        if batch is None:
+            num_graphs = 1
+        else:
+            num_graphs = getattr(data, "num_graphs", None)
+            if num_graphs is None:
+                ptr = getattr(data, "ptr", None)
+                num_graphs = int(ptr.numel()) - 1 if ptr is not None else int(batch.max()) + 1
+        params = self._param_list()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _PNAFunction.apply(self, x, edge_index, edge_attr, batch, int(num_graphs), *params)
+        out, _ = _forward_impl(self, x, edge_index, edge_attr, batch, int(num_graphs), save=False)
+        return out
+
+
+def _check_inputs(x, edge_index, edge_attr, batch):
+    for name, t in (("x", x), ("edge_index", edge_index), ("edge_attr", edge_attr)):
+        _require_cuda(t, f"data.{name}")
+        if t.dtype != torch.int64:
+            raise TypeError(f"data.{name} must be int64 (OGB integer features), got {t.dtype}")
+    if x.dim() != 2 or x.shape[1] != 9:
+        raise ValueError(f"data.x must be [N, 9], got {tuple(x.shape)}")
+    if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise ValueError(f"data.edge_index must be [2, E], got {tuple(edge_index.shape)}")
+    if edge_attr.shape[0] != edge_index.shape[1] or (edge_attr.numel() and edge_attr.shape[1] != 3):
+        raise ValueError(f"data.edge_attr must be [E, 3], got {tuple(edge_attr.shape)}")
+    if batch is not None and (batch.dtype != torch.int64 or batch.shape[0] != x.shape[0]):
+        raise ValueError("data.batch must be int64 [N]")
+
+
+class _Saved:
+    pass
+
+
+def _bn_forward(y, bn: nn.BatchNorm1d, training: bool, skip, relu: bool):
+    rows, ch = y.shape
+    dev = y.device
+    stats = torch.empty(2 * ch, dtype=torch.float32, device=dev)
+    use_batch = training or bn.running_mean is None
+    nbytes = _lib.query("gnn_bn_workspace_bytes", rows, ch)
+    ws = _WS.get("bn", nbytes, dev)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    _c("gnn_bn_stats", y, rows, ch, 1 if use_batch else 0, float(bn.eps), float(momentum), bn.running_mean,
+       bn.running_var, bn.num_batches_tracked if use_batch else None, stats, ws, ws.numel())
+    out = torch.empty_like(y)
+    _c("gnn_bn_act_fwd", y, stats, bn.weight, bn.bias, skip, rows, ch, 1 if relu else 0, out)
+    return out, stats, use_batch
+
+
+def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_graphs, save: bool, graph=None):
+    _check_inputs(x_idx, edge_index, edge_attr, batch)
+    pp, mp = model.pna_params, model.mlp_params
+    if model.training and (pp.dropout > 0.0 or mp.dropout > 0.0):
+        raise NotImplementedError("gnnepcsaft_b200: dropout > 0 in training mode is not implemented "
+                                  "(the reference configs use dropout_rate = 0.0)")
+    dev = x_idx.device
+    H = model.hidden_dim
+    F, Fo, T = H, H // TOWERS, TOWERS
+    C = T * F
+    L = pp.propagation_depth
+    x_idx = x_idx.contiguous()
+    edge_index = edge_index.contiguous()
+    edge_attr = edge_attr.contiguous()
+    if batch is not None:
+        batch = batch.contiguous()
+    n = int(x_idx.shape[0])
+    training = model.training
+    f32 = dict(dtype=torch.float32, device=dev)
+
+    g = graph if graph is not None else GraphStructure(edge_index, edge_attr, batch, n, num_graphs, pp.self_loops)
+    row_off = model._consts(dev)
+    sv = _Saved() if save else None
+
+    # AtomEncoder: the 9 tables are contiguous in the arena
+    atom_tab = model.node_embed.atom_embedding_list[0].weight
+    total_rows = sum(ATOM_FEATURE_DIMS)
+    x = torch.empty(n, H, **f32)
+    _c("gnn_atom_embed_fwd", x_idx, n, atom_tab, row_off, total_rows, H, x)
+
+    # bond-code tables of all layers in one launch
+    conv0 = model.convs[0] if L > 0 else None
+    enc = tab = None
+    layer_stride = tower_stride_pre = 0
+    if L > 0:
+        bond_tab = model.edge_embed.bond_embedding_list[0].weight
+        layer_stride = (model._offset_of(model.convs[1].edge_encoder.weight) -
+                        model._offset_of(conv0.edge_encoder.weight)) if L > 1 else 0
+        tower_stride_pre = model._offset_of(conv0.pre_nns[1][0].weight) - model._offset_of(conv0.pre_nns[0][0].weight)
+        enc = torch.empty(L, NUM_BOND_CODES, F, **f32)
+        tab = torch.empty(L, NUM_BOND_CODES, C, **f32)
+        _c("gnn_bond_table_fwd", bond_tab, conv0.edge_encoder.weight, conv0.edge_encoder.bias,
+           conv0.pre_nns[0][0].weight, tower_stride_pre, layer_stride, L, H, T, enc, tab)
+
+    layers = []
+    for l in range(L):
+        conv, bn = model.convs[l], model.batch_norms[l].module
+        rec = _Saved()
+        rec.x_in = x
+        # node projections  P = [Pdst_t0 | Pdst_t1 | Psrc_t0 | Psrc_t1]
+        P = torch.empty(n, 2 * C, **f32)
+        for t in range(T):
+            w = conv.pre_nns[t][0].weight
+            b = conv.pre_nns[t][0].bias
+            _c("gnn_linear_fwd", x, H, w, 3 * F, b, n, F, F, 0, P[:, t * F:], 2 * C)
+            _c("gnn_linear_fwd", x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
+        A = torch.empty(n, T * 4 * F, **f32)
+        rec.P = P
+        if pp.pre_layers == 1:
+            _c("gnn_pna_aggregate_fwd", P, tab[l], g.rowptr, g.col_src, g.col_code, n, T, F, A)
+        else:
+            hs = []
+            h = torch.empty(max(g.ep, 1), C, **f32)
+            _c("gnn_edge_hidden_fwd", P, tab[l], g.rowptr, g.col_src, g.col_code, n, C, 1, h)
+            hs.append(h)
+            for k in range(1, pp.pre_layers):
+                h2 = torch.empty(max(g.ep, 1), C, **f32)
+                last = k == pp.pre_layers - 1
+                for t in range(T):
+                    lin = conv.pre_nns[t][2 * k]
+                    _c("gnn_linear_fwd", h[:, t * F:], C, lin.weight, F, lin.bias, g.ep, F, F, 0 if last else 1,
+                       h2[:, t * F:], C)
+                hs.append(h2)
+                h = h2
+            rec.hs = hs
+            _c("gnn_pna_aggregate_msg_fwd", h, g.rowptr, n, T, F, A)
+        rec.A = A
+        scal = torch.empty(n, 2, **f32)
+        _c("gnn_pna_scalers", g.rowptr, conv.aggr_module.avg_deg_log, n, scal)
+        rec.scal = scal
+        # post_nns (virtual 13F concat) -> lin
+        tower_stride_post = model._offset_of(conv.post_nns[1][0].weight) - model._offset_of(conv.post_nns[0][0].weight)
+        bias_stride_post = model._offset_of(conv.post_nns[1][0].bias) - model._offset_of(conv.post_nns[0][0].bias)
+        rec.post_strides = (tower_stride_post, bias_stride_post)
+        O = torch.empty(n, H, **f32)
+        _c("gnn_pna_post_fwd", x, A, scal, conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias,
+           bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O)
+        os_ = [O]
+        for k in range(1, pp.post_layers):
+            O2 = torch.empty(n, H, **f32)
+            last = k == pp.post_layers - 1
+            for t in range(T):
+                lin = conv.post_nns[t][2 * k]
+                _c("gnn_linear_fwd", O[:, t * Fo:], H, lin.weight, Fo, lin.bias, n, Fo, Fo, 0 if last else 1,
+                   O2[:, t * Fo:], H)
+            os_.append(O2)
+            O = O2
+        rec.os = os_
+        y = torch.empty(n, H, **f32)
+        _c("gnn_linear_fwd", O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H)
+        rec.y = y
+        x, rec.stats, rec.bn_batch = _bn_forward(y, bn, training, rec.x_in if pp.skip_connections else None, True)
+        if save:
+            layers.append(rec)
+
+    # global_add_pool
+    pooled = torch.empty(num_graphs, H, **f32)
+    _c("gnn_segment_pool_fwd", x, g.graph_ptr, num_graphs, H, pooled)
+
+    # MLP head
+    head = []
+    hcur = pooled
+
+    def head_block(lin: nn.Linear, bn: Optional[nn.BatchNorm1d]):
+        nonlocal hcur
+        rec = _Saved()
+        rec.inp, rec.lin, rec.bn = hcur, lin, bn
+        z = torch.empty(hcur.shape[0], lin.out_features, **f32)
+        _c("gnn_linear_fwd", hcur, lin.in_features, lin.weight, lin.in_features, lin.bias, hcur.shape[0],
+           lin.out_features, lin.in_features, 0, z, lin.out_features)
+        rec.z = z
+        if bn is not None:
+            hcur, rec.stats, rec.bn_batch = _bn_forward(z, bn, training, None, True)
+        else:
+            hcur = z
+        head.append(rec)
+
+    for i in range(mp.num_mlp_layers):
+        head_block(model.mlp[4 * i], model.mlp[4 * i + 1])
+    tail = model.mlp[4 * mp.num_mlp_layers]
+    head_block(tail[0], tail[1])
+    head_block(tail[4], tail[5])
+    head_block(tail[8], None)
+    out = hcur
+
+    if save:
+        sv.g, sv.layers, sv.head, sv.enc, sv.tab = g, layers, head, enc, tab
+        sv.x_idx, sv.x_final, sv.n, sv.num_graphs = x_idx, x, n, num_graphs
+        sv.layer_stride, sv.tower_stride_pre = layer_stride, tower_stride_pre
+        sv.training = training
+    return out, sv
+
+
+def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.Tensor):
+    """Backward of `_forward_impl`; accumulates parameter gradients into `grad_arena` (same layout
+    as the parameter arena)."""
+    pp = model.pna_params
+    dev = dout.device
+    H = model.hidden_dim
+    F, Fo, T = H, H // TOWERS, TOWERS
+    C = T * F
+    L = pp.propagation_depth
+    n, g = sv.n, sv.g
+    f32 = dict(dtype=torch.float32, device=dev)
+    arena = model._arena
+
+    def gview(p: torch.Tensor) -> torch.Tensor:
+        off = model._offset_of(p)
+        return grad_arena[off:off + p.numel()].view(p.shape)
+
+    def bn_backward(dOut, rec_y, stats, bn, relu, use_batch):
+        rows, ch = rec_y.shape
+        nbytes = _lib.query("gnn_bn_workspace_bytes", rows, ch)
+        ws = _WS.get("bn", nbytes, dev)
+        dY = torch.empty_like(rec_y)
+        _c("gnn_bn_act_bwd", dOut, rec_y, stats, bn.weight, bn.bias, rows, ch, 1 if relu else 0,
+           1 if use_batch else 0, dY, gview(bn.weight), gview(bn.bias), ws, ws.numel())
+        return dY
+
+    # ---- head
+    d = dout.contiguous()
+    for rec in reversed(sv.head):
+        lin = rec.lin
+        if rec.bn is not None:
+            d = bn_backward(d, rec.z, rec.stats, rec.bn, True, rec.bn_batch)
+        rows = rec.inp.shape[0]
+        _c("gnn_linear_wgrad", d, lin.out_features, rec.inp, lin.in_features, rows, lin.out_features,
+           lin.in_features, gview(lin.weight), lin.in_features, gview(lin.bias))
+        dprev = torch.empty(rows, lin.in_features, **f32)
+        _c("gnn_linear_dgrad", d, lin.out_features, lin.weight, lin.in_features, rows, lin.out_features,
+           lin.in_features, 0, dprev, lin.in_features)
+        d = dprev
+    # ---- pool
+    dx = torch.empty(n, H, **f32)
+    _c("gnn_segment_pool_bwd", d, g.node_graph, n, H, 0, dx)
+
+    dtab = torch.zeros(L, NUM_BOND_CODES, C, **f32) if L > 0 else None
+    for l in reversed(range(L)):
+        conv, bn = model.convs[l], model.batch_norms[l].module
+        rec = sv.layers[l]
+        x_in = rec.x_in
+        dy = bn_backward(dx, rec.y, rec.stats, bn, True, rec.bn_batch)
+        if not pp.skip_connections:
+            dx = torch.zeros(n, H, **f32)        # else: dx (the skip gradient) keeps accumulating
+        # lin
+        O_last = rec.os[-1]
+        _c("gnn_linear_wgrad", dy, H, O_last, H, n, H, H, gview(conv.lin.weight), H, gview(conv.lin.bias))
+        dO = torch.empty(n, H, **f32)
+        _c("gnn_linear_dgrad", dy, H, conv.lin.weight, H, n, H, H, 0, dO, H)
+        # extra post layers
+        for k in reversed(range(1, pp.post_layers)):
+            O_in = rec.os[k - 1]
+            dprev = torch.empty(n, H, **f32)
+            for t in range(T):
+                lin = conv.post_nns[t][2 * k]
+                _c("gnn_linear_wgrad", dO[:, t * Fo:], H, O_in[:, t * Fo:], H, n, Fo, Fo, gview(lin.weight), Fo,
+                   gview(lin.bias))
+                _c("gnn_linear_dgrad", dO[:, t * Fo:], H, lin.weight, Fo, n, Fo, Fo, 0, dprev[:, t * Fo:], H)
+            _c("gnn_relu_bwd", dprev, O_in, n * H)
+            dO = dprev
+        ts_post, bs_post = rec.post_strides
+        w0, b0 = conv.post_nns[0][0].weight, conv.post_nns[0][0].bias
+        _c("gnn_pna_post_wgrad", dO, x_in, rec.A, rec.scal, n, F, Fo, T, gview(w0), ts_post, gview(b0), bs_post)
+        gA = torch.empty(n, T * 4 * F, **f32)
+        _c("gnn_pna_post_dgrad", dO, rec.scal, w0, ts_post, n, F, Fo, T, dx, gA)
+        # aggregation + message
+        dP = torch.empty(n, 2 * C, **f32)
+        if pp.pre_layers == 1:
+            dq = torch.empty(max(g.ep, 1), C, **f32)
+            _c("gnn_pna_aggregate_bwd", gA, rec.P, sv.tab[l], rec.A, g.rowptr, g.col_src, g.col_code, n, T, F, dP,
+               dq, dtab[l])
+        else:
+            hs = rec.hs
+            dm = torch.empty(max(g.ep, 1), C, **f32)
+            _c("gnn_pna_aggregate_msg_bwd", gA, hs[-1], rec.A, g.rowptr, n, T, F, dm)
+            for k in reversed(range(1, pp.pre_layers)):
+                h_in = hs[k - 1]
+                dprev = torch.empty(max(g.ep, 1), C, **f32)
+                for t in range(T):
+                    lin = conv.pre_nns[t][2 * k]
+                    _c("gnn_linear_wgrad", dm[:, t * F:], C, h_in[:, t * F:], C, g.ep, F, F, gview(lin.weight), F,
+                       gview(lin.bias))
+                    _c("gnn_linear_dgrad", dm[:, t * F:], C, lin.weight, F, g.ep, F, F, 0, dprev[:, t * F:], C)
+                _c("gnn_relu_bwd", dprev, h_in, g.ep * C)
+                dm = dprev
+            dq = dm
+            _c("gnn_edge_hidden_bwd", dq, g.rowptr, g.col_code, n, C, dP, dtab[l])
+        _c("gnn_scatter_src_bwd", dq, g.srcptr, g.src_slot, n, C, dP)
+        # projections
+        for t in range(T):
+            lin = conv.pre_nns[t][0]
+            gw = gview(lin.weight)
+            _c("gnn_linear_wgrad", dP[:, t * F:], 2 * C, x_in, H, n, F, F, gw, 3 * F, gview(lin.bias))
+            _c("gnn_linear_wgrad", dP[:, C + t * F:], 2 * C, x_in, H, n, F, F, gw[:, F:], 3 * F, None)
+            _c("gnn_linear_dgrad", dP[:, t * F:], 2 * C, lin.weight, 3 * F, n, F, F, 1, dx, H)
+            _c("gnn_linear_dgrad", dP[:, C + t * F:], 2 * C, lin.weight[:, F:], 3 * F, n, F, F, 1, dx, H)
+
+    # ---- encoders
+    atom_tab = model.node_embed.atom_embedding_list[0].weight
+    _c("gnn_atom_embed_bwd", sv.x_idx, n, dx, model._consts(dev), sum(ATOM_FEATURE_DIMS), H, gview(atom_tab))
+    if L > 0:
+        conv0 = model.convs[0]
+        denc = torch.empty(L, NUM_BOND_CODES, F, **f32)
+        _c("gnn_bond_table_bwd", dtab, model.edge_embed.bond_embedding_list[0].weight, conv0.edge_encoder.weight,
+           conv0.pre_nns[0][0].weight, sv.tower_stride_pre, sv.layer_stride, L, sv.enc, H, T, denc,
+           gview(model.edge_embed.bond_embedding_list[0].weight), gview(conv0.edge_encoder.weight),
+           gview(conv0.edge_encoder.bias), gview(conv0.pre_nns[0][0].weight))
+    del arena
+
+
+class _PNAFunction(torch.autograd.Function):
+    """One autograd node for the whole network: forward/backward are the CUDA kernel chains."""
+
+    @staticmethod
+    def forward(ctx, model, x_idx, edge_index, edge_attr, batch, num_graphs, *params):
+        out, sv = _forward_impl(model, x_idx, edge_index, edge_attr, batch, num_graphs, save=True)
+        ctx.model, ctx.sv = model, sv
+        ctx.n_params = len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        model, sv = ctx.model, ctx.sv
+        if not model._arena_valid():
+            raise RuntimeError("gnnepcsaft_b200: parameters were moved between forward and backward")
+        grad_arena = torch.zeros_like(model._arena)
+        _backward_impl(model, sv, dout, grad_arena)
+        grads = []
+        for p, off in zip(model._param_list(), model._arena_offsets):
+            grads.append(grad_arena[off:off + p.numel()].view(p.shape) if p.requires_grad else None)
+        ctx.sv = None
+        return (None, None, None, None, None, None, *grads)
+
+
+def mape(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """torchmetrics.functional.mean_absolute_percentage_error (reference models.py:16,194)."""
+    return torch.sum((pred - target).abs() / target.abs().clamp(min=1.17e-06)) / target.numel()
+
+
+class PNApcsaftL(nn.Module):
+    """The reference's Lightning wrapper (models.py:138-202) without the Lightning dependency:
+    holds `self.model` (so checkpoint keys carry the `model.` prefix), builds the same
+    optimizer / scheduler, and computes the same training loss."""
+
+    def __init__(self, pna_params: PnaconvsParams, mlp_params: ReadoutMLPParams, config):
+        super().__init__()
+        self.config = config
+        self.model = PNAPCSAFT(config.hidden_dim, pna_params=pna_params, mlp_params=mlp_params)
+
+    def forward(self, data):
+        return self.model(data)
+
+    def configure_optimizers(self):
+        if self.config.optimizer == "adam":
+            opt = torch.optim.AdamW(self.parameters(), lr=self.config.learning_rate,
+                                    weight_decay=self.config.weight_decay, amsgrad=True, eps=1e-5)
+        elif self.config.optimizer == "sgd":
+            opt = torch.optim.SGD(self.parameters(), lr=self.config.learning_rate, momentum=self.config.momentum,
+                                  weight_decay=self.config.weight_decay, nesterov=True)
+        else:
+            raise ValueError(f"Unsupported optimizer: {self.config.optimizer}.")
+        sched = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, self.config.warmup_steps)
+        return {"optimizer": opt, "lr_scheduler": {"scheduler": sched, "interval": "step", "frequency": 1}}
+
+    def training_step(self, graphs, batch_idx=0):
+        target = graphs.para.view(-1, self.config.num_para)
+        pred = self(graphs)
+        return mape(pred, target)

@@ -1,0 +1,238 @@
+/* gnnepcsaft_b200 — C ABI of the B200 (sm_100a) PNAPCSAFT message-passing path.
+ *
+ * The reference (wildsonbbl/GNN-ePC-SAFT) has no native boundary: every op of
+ * gnnepcsaft/train/models.py:105-135 is a PyTorch / PyG / OGB library call.  Each entry
+ * point below replaces one of those library-call sites (cited per function) and is what a
+ * ctypes/cffi binding on the reference side binds.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host
+ *  - the caller owns all memory; nothing is allocated inside; workspaces are sized by the
+ *    *_workspace_bytes() queries
+ *  - launches are enqueued on `stream` (a cudaStream_t passed as void*) and return
+ *    immediately; no global state, so calls are thread-safe per stream
+ *  - return value: 0 = ok, >0 = cudaError_t of the launch, <0 = argument error
+ *    (GNN_ERR_*); gnn_error_string() renders either
+ *  - float tensors are fp32 row-major; `ld*` are leading dimensions in elements
+ */
+#ifndef GNNEPCSAFT_B200_H
+#define GNNEPCSAFT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNN_ERR_BAD_ARG (-1)
+#define GNN_ERR_TOO_LARGE (-2)
+#define GNN_ERR_UNSUPPORTED (-3)
+#define GNN_ERR_WORKSPACE (-4)
+
+#define GNN_NUM_ATOM_FEATS 9
+#define GNN_NUM_BOND_FEATS 3
+#define GNN_NUM_BOND_CODES 60 /* 5*6*2, code = a0*12 + a1*2 + a2; self-loop = code 0 */
+
+const char* gnn_error_string(int code);
+int gnn_abi_version(void);
+/* device properties seen by the library: out[0]=sm count, out[1]=cc major, out[2]=cc minor */
+int gnn_device_info(int32_t* out_host);
+
+/* ---------------------------------------------------------------- graph structure
+ * Replaces: PyG add_self_loops (models.py:118-121) and the per-layer scatter index
+ * handling inside MessagePassing/scatter (models.py:128 -> PNAConv.propagate).
+ * Builds, on device, the destination-grouped CSR (stable: original edge order inside a
+ * segment, the implicit self-loop last, matching PyG's cat([edges, loops])) and the
+ * source-grouped list of CSR slots used by the backward pass.
+ *   rowptr   int32 [N+1]   col_src int32 [E']  col_code uint8 [E']  col_eid int32 [E']
+ *   srcptr   int32 [N+1]   src_slot int32 [E']      E' = E + (self_loops ? N : 0)
+ * col_eid[s] is the index into the PyG-order edge list (loops are E+i).
+ * err_flag (int32[1], may be NULL) is set non-zero if an index or bond feature is out of
+ * range (the reference would raise an IndexError). */
+int64_t gnn_build_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
+int gnn_build_csr(const int64_t* edge_index, const int64_t* edge_attr, int64_t num_nodes,
+                  int64_t num_edges, int self_loops, int32_t* rowptr, int32_t* col_src,
+                  uint8_t* col_code, int32_t* col_eid, int32_t* srcptr, int32_t* src_slot,
+                  int32_t* err_flag, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* batch vector (int64, sorted, PyG `Batch.batch`) -> int32 node->graph map and graph_ptr
+ * [B+1].  Replaces the index handling of global_add_pool (models.py:133). */
+int64_t gnn_graph_ptr_workspace_bytes(int64_t num_graphs);
+int gnn_graph_ptr_from_batch(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
+                             int32_t* node_graph, int32_t* graph_ptr, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+
+/* Device collate. Replaces PyG DataLoader/Collater/Batch.from_data_list (train.py:74-79)
+ * over an InMemoryDataset-format packed store (graphdataset.py:48,137): concatenated
+ * tensors with graph-local edge_index plus slices.  For the selected graph ids writes the
+ * PyG-layout int64 batch (x, edge_index incremented, edge_attr, batch, ptr) bit-exactly.
+ *   ids int64 [B]; node_slices/edge_slices int64 [G+1]
+ *   out_ptr int64 [B+1], out_eptr int64 [B+1] (edge offsets, scratch/output) */
+int64_t gnn_collate_workspace_bytes(int64_t num_ids);
+int gnn_collate_offsets(const int64_t* ids, int64_t num_ids, const int64_t* node_slices,
+                        const int64_t* edge_slices, int64_t* out_ptr, int64_t* out_eptr,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+int gnn_collate_gather(const int64_t* ids, int64_t num_ids, const int64_t* node_slices,
+                       const int64_t* edge_slices, const int64_t* store_x,
+                       const int64_t* store_edge_index, int64_t store_num_edges,
+                       const int64_t* store_edge_attr, const int64_t* out_ptr,
+                       const int64_t* out_eptr, int64_t total_nodes, int64_t total_edges,
+                       int64_t* x, int64_t* edge_index, int64_t* edge_attr, int64_t* batch,
+                       void* stream);
+
+/* ---------------------------------------------------------------- encoders
+ * OGB AtomEncoder (models.py:65,122): out[i,:] = sum_k table[row_off[k] + x[i,k], :].
+ * `tables` is the 9 embedding weights stacked along rows (174 rows), row_off int32[9]. */
+int gnn_atom_embed_fwd(const int64_t* x, int64_t num_nodes, const float* tables,
+                       const int32_t* row_off, int32_t total_rows, int hidden, float* out,
+                       void* stream);
+/* d tables[row] += sum_i dout[i,:] (tables gradient must be zeroed by the caller) */
+int gnn_atom_embed_bwd(const int64_t* x, int64_t num_nodes, const float* dout,
+                       const int32_t* row_off, int32_t total_rows, int hidden, float* dtables,
+                       void* stream);
+
+/* OGB BondEncoder + PNAConv.edge_encoder + the bond third of pre_nns[t][0]
+ * (models.py:66,123; PyG pna_conv.py message()).  With pre_layers == 1 the per-edge pre-NN
+ * is linear, so the bond contribution depends only on the 60 possible bond codes:
+ *   emb[c,:]  = sum_k bond_tables[boff[k] + c_k, :]                       [60,H]
+ *   enc[c,:]  = emb[c,:] . Wee^T + bee                                    [60,F]
+ *   tab[c, t*F+f] = sum_k Wpre_t[f, 2F+k] * enc[c,k]                      [60,T*F]
+ * wpre points at layer 0's pre_nns[0][0].weight, towers are `wpre_tower_stride` floats apart,
+ * ld = 3F; all `num_layers` conv layers are done in one launch, the parameters of layer l sit
+ * `l*layer_stride` floats after layer 0's (flat parameter arena), outputs are [L,60,F] /
+ * [L,60,T*F].  enc is also returned (needed by backward). */
+int gnn_bond_table_fwd(const float* bond_tables, const float* wee, const float* bee,
+                       const float* wpre, int64_t wpre_tower_stride, int64_t layer_stride,
+                       int num_layers, int hidden, int towers, float* enc, float* tab,
+                       void* stream);
+/* backward of the above given dtab [L,60,T*F]: accumulates into dbond_tables [13,H],
+ * dwee [F,H], dbee [F], dwpre (bond third only; same addressing as the parameters).
+ * denc_ws: scratch [L,60,F]. */
+int gnn_bond_table_bwd(const float* dtab, const float* bond_tables, const float* wee,
+                       const float* wpre, int64_t wpre_tower_stride, int64_t layer_stride,
+                       int num_layers, const float* enc, int hidden, int towers, float* denc_ws,
+                       float* dbond_tables, float* dwee, float* dbee, float* dwpre, void* stream);
+
+/* ---------------------------------------------------------------- fused message + aggregate
+ * Replaces MessagePassing._collect/message + MultiAggregation(mean,min,max,std)
+ * (PyG pna_conv.py, nn/aggr/{multi,basic,scaler}.py; called from models.py:128).
+ * Inputs: P [N, 2C] = [Pdst | Psrc] node projections (C = towers*F), tab [60,C].
+ *   q_e = Psrc[src_e] + tab[code_e];   m_e = Pdst[dst_e] + q_e
+ * Output A [N, towers, 4, F]: mean, min, max (of m) and std (of q; shift invariant), with
+ * empty segments -> 0 and std = sqrt(max(var,1e-5)) masked to 0 when <= sqrt(1e-5).
+ * One warp per destination node, single pass, Welford variance. */
+int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int32_t* rowptr,
+                          const int32_t* col_src, const uint8_t* col_code, int64_t num_nodes,
+                          int towers, int F, float* A, void* stream);
+/* Backward: gA [N,towers,4,F] -> dP[:, 0:C] (dst part), dq [E',C] per CSR slot and
+ * dtab_accum [60,C] (+=, caller zeroes).  min/max gradients are split evenly over ties
+ * (torch scatter_reduce amin/amax semantics). */
+int gnn_pna_aggregate_bwd(const float* gA, const float* P, const float* tab, const float* A,
+                          const int32_t* rowptr, const int32_t* col_src,
+                          const uint8_t* col_code, int64_t num_nodes, int towers, int F,
+                          float* dP, float* dq, float* dtab_accum, void* stream);
+/* dP[:, C:2C][j] = sum over out-edges of j of dq[slot] (deterministic order) */
+int gnn_scatter_src_bwd(const float* dq, const int32_t* srcptr, const int32_t* src_slot,
+                        int64_t num_nodes, int C, float* dP, void* stream);
+
+/* General message path (pre_layers > 1): per-edge hidden h_e = relu(Pdst[dst]+Psrc[src]+tab[code])
+ * in CSR slot order, [E', C]. */
+int gnn_edge_hidden_fwd(const float* P, const float* tab, const int32_t* rowptr,
+                        const int32_t* col_src, const uint8_t* col_code, int64_t num_nodes,
+                        int C, int relu, float* hidden_out, void* stream);
+/* Aggregate materialised per-slot messages m [E', C] (CSR order) -> A. */
+int gnn_pna_aggregate_msg_fwd(const float* m, const int32_t* rowptr, int64_t num_nodes,
+                              int towers, int F, float* A, void* stream);
+int gnn_pna_aggregate_msg_bwd(const float* gA, const float* m, const float* A,
+                              const int32_t* rowptr, int64_t num_nodes, int towers, int F,
+                              float* dm, void* stream);
+/* backward of gnn_edge_hidden_fwd: dh [E',C] (already masked by relu) -> dP dst half (+=0,
+ * written), dq copy is dh itself; accumulates dtab. */
+int gnn_edge_hidden_bwd(const float* dh, const int32_t* rowptr, const uint8_t* col_code,
+                        int64_t num_nodes, int C, float* dP, float* dtab_accum, void* stream);
+
+/* ---------------------------------------------------------------- dense stages (fp32 SIMT)
+ * Replace torch.nn.Linear / PyG Linear (addmm) at pna_conv.py pre_nns/post_nns/lin and the
+ * MLP head (models.py:84-103).  All are  C[M,N] (+)= op(A) . op(B) with row-major storage.
+ *
+ * gnn_linear_fwd:  Y[M,N] = act(X[M,K] . W[N,K]^T + bias)        (act: 0 none, 1 relu)
+ * gnn_linear_dgrad: dX[M,K] (+)= dY[M,N] . W[N,K]                (accumulate: 0/1)
+ * gnn_linear_wgrad: dW[N,K] += dY[M,N]^T . X[M,K],  db[N] += colsum(dY)  (db may be NULL)
+ * gnn_relu_bwd:     dY[i] = Y_act[i] > 0 ? dY[i] : 0   (ReLU between Linear layers of pre/post nns)
+ */
+int gnn_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
+                   int64_t M, int N, int K, int act, float* Y, int64_t ldy, void* stream);
+int gnn_linear_dgrad(const float* dY, int64_t lddy, const float* W, int64_t ldw, int64_t M,
+                     int N, int K, int accumulate, float* dX, int64_t lddx, void* stream);
+int gnn_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t M,
+                     int N, int K, float* dW, int64_t lddw, float* db, void* stream);
+int gnn_relu_bwd(float* dY, const float* Y_act, int64_t numel, void* stream);
+
+/* Degree scalers of DegreeScalerAggregation (PyG nn/aggr/scaler.py): scal[i] = (amp_i, att_i),
+ * amp = log(d+1)/avg_deg_log, att = avg_deg_log/log(max(d,1)+1), d = in-degree incl. loops. */
+int gnn_pna_scalers(const int32_t* rowptr, const float* avg_deg_log, int64_t num_nodes,
+                    float* scal, void* stream);
+
+/* PNAConv post_nns[t][0] over the virtual concatenation [x | A_t | amp*A_t | att*A_t]
+ * (K = 13F) - the [N,T,12F]/[N,T,13F] tensors of DegreeScalerAggregation / PNAConv.forward
+ * are never materialised.
+ *   fwd:   O[:, t*F_out:(t+1)*F_out] = act(cat . Wpost_t^T + bpost_t),  Wpost_t [F_out,13F]
+ *   dgrad: dx[N,F] += sum_t dO_t . Wpost_t[:, :F];  gA[:, t, :, :] = folded scaler gradient
+ *   wgrad: dWpost_t += dO_t^T . cat ;  dbpost_t += colsum(dO_t)
+ * wpost/bpost point at tower 0; towers are *_tower_stride floats apart. */
+int gnn_pna_post_fwd(const float* x, const float* A, const float* scal, const float* wpost,
+                     int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
+                     int64_t num_nodes, int F, int F_out, int towers, int act, float* O,
+                     void* stream);
+int gnn_pna_post_dgrad(const float* dO, const float* scal, const float* wpost,
+                       int64_t wpost_tower_stride, int64_t num_nodes, int F, int F_out, int towers,
+                       float* dx, float* gA, void* stream);
+int gnn_pna_post_wgrad(const float* dO, const float* x, const float* A, const float* scal,
+                       int64_t num_nodes, int F, int F_out, int towers, float* dwpost,
+                       int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride,
+                       void* stream);
+
+/* ---------------------------------------------------------------- BatchNorm / ReLU / skip
+ * Replaces PyG BatchNorm / torch BatchNorm1d + F.relu + skip (models.py:128-131, head BN).
+ * Training: batch statistics (biased var for normalisation, unbiased for running_var,
+ * momentum 0.1), num_batches_tracked += 1.  stats = [mean[C] | rstd[C]] is written for
+ * backward.  Eval: stats derived from running_mean / running_var. */
+int64_t gnn_bn_workspace_bytes(int64_t rows, int C);
+int gnn_bn_stats(const float* Y, int64_t rows, int C, int training, float eps, float momentum,
+                 float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                 float* stats, void* workspace, int64_t workspace_bytes, void* stream);
+/* out = relu(gamma*(Y-mean)*rstd+beta) [+ skip]  (relu: 0/1, skip may be NULL) */
+int gnn_bn_act_fwd(const float* Y, const float* stats, const float* gamma, const float* beta,
+                   const float* skip, int64_t rows, int C, int relu, float* out, void* stream);
+/* dY from dOut; also dgamma[C] += , dbeta[C] += .  training=0 uses the eval formula. */
+int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* stats, const float* gamma,
+                   const float* beta, int64_t rows, int C, int relu, int training, float* dY,
+                   float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
+                   void* stream);
+
+/* ---------------------------------------------------------------- pooling, loss, optimiser
+ * global_add_pool (models.py:133): out[g,:] = sum_{i in graph g} x[i,:]; graph_ptr int32 [B+1] */
+int gnn_segment_pool_fwd(const float* x, const int32_t* graph_ptr, int64_t num_graphs, int C,
+                         float* out, void* stream);
+int gnn_segment_pool_bwd(const float* dout, const int32_t* node_graph, int64_t num_nodes, int C,
+                         int accumulate, float* dx, void* stream);
+/* torchmetrics MAPE (models.py:194): loss[0] = mean(|p-t| / max(|t|,1.17e-6));
+ * dpred = d loss / d pred * grad_scale.  loss_accum (optional) += loss. */
+int gnn_mape_fwd_bwd(const float* pred, const float* target, int64_t numel, float grad_scale,
+                     float* loss, float* dpred, void* stream);
+/* AdamW(amsgrad=True) + CosineAnnealingWarmRestarts(T_0) stepped per step
+ * (models.py:162-188).  step_count int64[1] on device is read (t = step_count before this
+ * step), the caller bumps it with gnn_step_increment.  grad_scale multiplies grads (1/world). */
+int gnn_adamw_amsgrad_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           float* max_exp_avg_sq, int64_t numel, const int64_t* step_count,
+                           float lr0, float beta1, float beta2, float eps, float weight_decay,
+                           int64_t t0_restart, float grad_scale, void* stream);
+int gnn_step_increment(int64_t* step_count, void* stream);
+int gnn_fill_zero(void* ptr, int64_t bytes, void* stream);
+/* out[i] = a[i] + b[i] (fp32) — skip-connection gradient merge */
+int gnn_add_inplace(float* acc, const float* src, int64_t numel, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
