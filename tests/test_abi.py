@@ -23,7 +23,7 @@ def test_library_is_sm100a_and_free_of_torch():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     ldd = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert "torch" not in ldd and "c10" not in ldd
+    assert "libtorch" not in ldd and "libc10" not in ldd
 
 
 def test_argument_errors_without_gpu():

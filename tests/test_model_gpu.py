@@ -1,0 +1,189 @@
+"""PNAPCSAFT on the CUDA kernels against the oracle (SURVEY.md section 8c parity protocol).
+
+Truth is the float64 oracle.  Forward: max|d| / max|y| <= 1e-5 vs the fp32 oracle and
+err(cuda, fp64) <= 2 * err(oracle32, fp64) (+1e-6 slack).  Gradients: global relative L2 <= 2e-3
+(the fp32-vs-fp64 floor of the reference arithmetic itself is 6-8e-4), zero-gradient biases
+excluded.  Train-mode forward may additionally show std-threshold flips (floor 1.4e-4)."""
+import os
+
+import pytest
+import torch
+
+from gnnepcsaft_b200.data.graph import collate
+from gnnepcsaft_b200.data.synth import batch_from_packed, make_packed_graphs
+from gnnepcsaft_b200.train import models as M
+from oracle import pna_oracle as O
+from tests.helpers import CONFIGS, cfg, flat_grads, make_pair, tiny_graphs, zero_grad_bias_mask
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "pna_golden.pt")
+
+
+def _errs(y, y32, y64):
+    scale = float(y64.abs().max())
+    return (float((y.double().cpu() - y64).abs().max()) / scale, float((y32.double() - y64).abs().max()) / scale,
+            float((y.double().cpu() - y32.double()).abs().max()) / scale)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_forward_eval_parity(name):
+    c = cfg(**CONFIGS[name])
+    packed = make_packed_graphs(200, seed=7, skewed=name == "wide_small", num_para=c.num_para)
+    batch = batch_from_packed(packed)
+    o32, o64, m = make_pair(c, packed.in_degree_histogram())
+    for mod in (o32, o64, m):
+        mod.eval()
+    m.to(DEV)
+    with torch.no_grad():
+        y32, y64, y = o32(batch), o64(batch), m(batch.to(DEV))
+    e_m, e_o, e_mo = _errs(y, y32, y64)
+    assert y.shape == (200, c.num_para) and y.dtype == torch.float32
+    assert e_mo <= 1e-5, f"vs fp32 oracle {e_mo:.2e}"
+    assert e_m <= 2 * e_o + 1e-6, f"cuda vs fp64 {e_m:.2e}, oracle32 vs fp64 {e_o:.2e}"
+
+
+def test_forward_eval_config1_1024_graphs():
+    """BASELINE config 1: default model, 1024-graph batch, eval forward."""
+    c = cfg()
+    packed = make_packed_graphs(1024, seed=0)
+    batch = batch_from_packed(packed)
+    o32, o64, m = make_pair(c, packed.in_degree_histogram())
+    for mod in (o32, o64, m):
+        mod.eval()
+    m.to(DEV)
+    with torch.no_grad():
+        y32, y64, y = o32(batch), o64(batch), m(batch.to(DEV))
+    e_m, e_o, e_mo = _errs(y, y32, y64)
+    rms = float(((y.double().cpu() - y64) ** 2).mean().sqrt() / (y64 ** 2).mean().sqrt())
+    print(f"config1: cuda-vs-fp64 {e_m:.2e} (oracle32-vs-fp64 {e_o:.2e}), cuda-vs-oracle32 {e_mo:.2e}, rms {rms:.2e}")
+    assert e_mo <= 1e-5 and rms <= 1e-5 and e_m <= 2 * e_o + 1e-6
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_train_forward_backward_parity(name):
+    c = cfg(**CONFIGS[name])
+    packed = make_packed_graphs(96, seed=5, num_para=c.num_para)
+    batch = batch_from_packed(packed)
+    o32, o64, m = make_pair(c, packed.in_degree_histogram())
+    for mod in (o32, o64, m):
+        mod.train()
+    m.to(DEV)
+    tgt = batch.para.view(-1, c.num_para)
+    y64 = o64(batch)
+    O.mape(y64, tgt.double()).backward()
+    y32 = o32(batch)
+    O.mape(y32, tgt).backward()
+    y = m(batch.to(DEV))
+    loss = M.mape(y, tgt.to(DEV))
+    loss.backward()
+    e_m, e_o, _ = _errs(y.detach(), y32.detach(), y64.detach())
+    assert e_m <= max(2 * e_o, 2e-4), f"train forward: cuda vs fp64 {e_m:.2e}, oracle32 vs fp64 {e_o:.2e}"
+    mask = zero_grad_bias_mask(m)
+    g64, g32, g = flat_grads(o64), flat_grads(o32), flat_grads(m)
+    rel = float((g - g64)[mask].norm() / g64[mask].norm())
+    rel_o = float((g32 - g64)[mask].norm() / g64[mask].norm())
+    print(f"{name}: grad rel-L2 cuda {rel:.2e} oracle32 {rel_o:.2e}")
+    assert rel <= max(2e-3, 2 * rel_o)
+    for (k, bo), (_, bm) in zip(o32.named_buffers(), m.named_buffers()):     # BN running stats, counters
+        torch.testing.assert_close(bm.float().cpu(), bo.float(), rtol=1e-4, atol=1e-5, msg=k)
+
+
+def test_golden_vectors():
+    gold = torch.load(GOLDEN)
+    from oracle.make_golden import CASES, build_case, grad_projections
+    for name in CASES:
+        o32, batch, c = build_case(name)
+        m = M.PNAPCSAFT(c.hidden_dim, o32.pna_params, o32.mlp_params) if False else None
+        from gnnepcsaft_b200.train.utils import create_model
+        m = create_model(c, o32.pna_params.deg)
+        m.load_state_dict(o32.state_dict(), strict=True)
+        m.to(DEV).eval()
+        with torch.no_grad():
+            y = m(batch.to(DEV)).cpu()
+        g64 = gold[name]["eval_out_fp64"]
+        scale = float(g64.abs().max())
+        assert float((y.double() - g64).abs().max()) / scale <= 1e-5, name
+        m.train()
+        tgt = batch.para.view(-1, c.num_para).to(DEV)
+        yt = m(batch.to(DEV))
+        loss = M.mape(yt, tgt)
+        loss.backward()
+        assert abs(float(loss) - float(gold[name]["train_loss_fp64"])) <= 2e-4 * abs(float(gold[name]["train_loss_fp64"]))
+        flat = flat_grads(m)
+        proj, gproj = grad_projections(flat), gold[name]["train_grad_proj_fp64"]
+        assert float((proj - gproj).norm() / gproj.norm()) <= 5e-3, name
+
+
+def test_tiny_graphs_edge_cases_and_batch_none():
+    c = cfg(propagation_depth=3)
+    o32, o64, m = make_pair(c, torch.tensor([1, 6, 8, 2, 1]))
+    o64.eval(), m.eval()
+    m.to(DEV)
+    graphs = tiny_graphs()
+    with torch.no_grad():
+        torch.testing.assert_close(m(collate(graphs).to(DEV)).double().cpu(), o64(collate(graphs)), rtol=1e-5, atol=1e-5)
+        for g in graphs:                              # single molecule, data.batch is None
+            y = m(g.to(DEV))
+            assert y.shape == (1, 5)
+            torch.testing.assert_close(y.double().cpu(), o64(g), rtol=1e-5, atol=1e-5)
+    # isolated atoms without self-loops: deg-0 segments
+    c2 = cfg(propagation_depth=2, add_self_loops=False)
+    o32, o64, m = make_pair(c2, torch.tensor([1, 6, 8, 2, 1]))
+    o64.eval(), m.eval()
+    m.to(DEV)
+    with torch.no_grad():
+        torch.testing.assert_close(m(collate(graphs).to(DEV)).double().cpu(), o64(collate(graphs)), rtol=1e-5, atol=1e-5)
+
+
+def test_state_dict_contract_on_device():
+    c = cfg(propagation_depth=2)
+    o32, _, m = make_pair(c, torch.tensor([0, 3, 2, 1]), dtype64=False)
+    m.to(DEV)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(o32.state_dict().keys())
+    o32.load_state_dict({k: v.cpu() for k, v in sd.items()}, strict=True)
+    packed = make_packed_graphs(8, seed=1)
+    m.eval()
+    with torch.no_grad():
+        y1 = m(batch_from_packed(packed).to(DEV))
+        m.load_state_dict({k: v.clone() for k, v in sd.items()})
+        y2 = m(batch_from_packed(packed).to(DEV))
+    assert torch.equal(y1, y2)
+
+
+def test_no_cpu_path_and_loud_failure():
+    c = cfg(propagation_depth=1)
+    _, _, m = make_pair(c, torch.tensor([0, 3, 2, 1]), dtype64=False)
+    m.to(DEV)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(batch_from_packed(make_packed_graphs(2, seed=0)))          # CPU batch on a CUDA model
+
+
+def test_full_size_properties_4096_graphs():
+    """BASELINE config 2 size: properties that need no oracle run.
+    (a) permuting the graphs of a batch permutes the eval outputs; (b) a batch equals the
+    concatenation of its halves in eval mode; (c) the training loss is finite and gradients are
+    non-zero for every live parameter."""
+    c = cfg()
+    packed = make_packed_graphs(4096, seed=1)
+    _, _, m = make_pair(c, packed.in_degree_histogram(), dtype64=False)
+    m.to(DEV).eval()
+    g = torch.Generator().manual_seed(0)
+    perm = torch.randperm(4096, generator=g)
+    with torch.no_grad():
+        y = m(batch_from_packed(packed).to(DEV))
+        yp = m(batch_from_packed(packed, perm).to(DEV))
+        ya = m(batch_from_packed(packed, torch.arange(0, 2048)).to(DEV))
+        yb = m(batch_from_packed(packed, torch.arange(2048, 4096)).to(DEV))
+    torch.testing.assert_close(yp, y[perm.to(DEV)], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(torch.cat([ya, yb]), y, rtol=1e-5, atol=1e-5)
+    m.train()
+    batch = batch_from_packed(packed).to(DEV)
+    loss = M.mape(m(batch), batch.para.view(-1, 5))
+    loss.backward()
+    assert torch.isfinite(loss)
+    mask = zero_grad_bias_mask(m)
+    for (name, p) in m.named_parameters():
+        assert torch.isfinite(p.grad).all(), name
+    assert float(flat_grads(m)[mask].abs().max()) > 0
