@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -21,6 +22,7 @@ from .. import _lib
 from ..data.graph import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS, NUM_BOND_CODES
 
 TOWERS = 2  # reference models.py:76
+DEFAULT_MATMUL = "simt"
 
 
 @dataclasses.dataclass
@@ -102,8 +104,91 @@ class _BatchNorm(nn.Module):             # PyG BatchNorm: `.module` = BatchNorm1
 
 
 # ----------------------------------------------------------------------------- helpers
+class KernelProfiler:
+    """Optional CUDA-event timing of ABI calls on the launching stream (used by bench.py)."""
+
+    def __init__(self, watch=None):
+        self.watch = set(watch) if watch is not None else None
+        self.records = []          # (name, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, s, e in self.records:
+            tot, cnt = out.get(name, (0.0, 0))
+            out[name] = (tot + s.elapsed_time(e), cnt + 1)
+        return out          # name -> (total ms, calls)
+
+
+_PROFILER: Optional[KernelProfiler] = None
+ABI_CALLS = 0               # number of C-ABI calls issued by this process (each launches >= 1 kernel)
+
+
+def set_profiler(prof: Optional[KernelProfiler]):
+    global _PROFILER
+    _PROFILER = prof
+
+
 def _c(name, *args):
-    _lib.call(name, *args, _lib.stream_ptr())
+    global ABI_CALLS
+    ABI_CALLS += 1
+    prof = _PROFILER
+    if prof is not None and (prof.watch is None or name in prof.watch):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        _lib.call(name, *args, _lib.stream_ptr())
+        e.record()
+        prof.records.append((name, s, e))
+    else:
+        _lib.call(name, *args, _lib.stream_ptr())
+
+
+# dense-stage dispatch: which kernel family runs the Linear layers
+MATMUL_MODES = {"simt": -1, "tf32x3": 0, "bf16": 2}
+
+
+def _lin_fwd(mm, X, ldx, W, ldw, bias, M, N, K, act, Y, ldy):
+    if mm < 0:
+        _c("gnn_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy)
+    else:
+        _c("gnn_tc_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, mm)
+
+
+def _lin_dgrad(mm, dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx):
+    if mm < 0:
+        _c("gnn_linear_dgrad", dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx)
+    else:
+        _c("gnn_tc_linear_dgrad", dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, mm)
+
+
+def _lin_wgrad(mm, dY, lddy, X, ldx, M, N, K, dW, lddw, db):
+    if mm < 0:
+        _c("gnn_linear_wgrad", dY, lddy, X, ldx, M, N, K, dW, lddw, db)
+    else:
+        _c("gnn_tc_linear_wgrad", dY, lddy, X, ldx, M, N, K, dW, lddw, mm)
+        if db is not None:
+            _c("gnn_colsum_accum", dY, lddy, M, N, db)
+
+
+def _post_fwd(mm, *args):
+    if mm < 0:
+        _c("gnn_pna_post_fwd", *args)
+    else:
+        _c("gnn_tc_pna_post_fwd", *args, mm)
+
+
+def _post_dgrad(mm, *args):
+    if mm < 0:
+        _c("gnn_pna_post_dgrad", *args)
+    else:
+        _c("gnn_tc_pna_post_dgrad", *args, mm)
+
+
+def _post_wgrad(mm, *args):
+    if mm < 0:
+        _c("gnn_pna_post_wgrad", *args)
+    else:
+        _c("gnn_tc_pna_post_wgrad", *args, mm)
 
 
 class _Workspace:
@@ -200,6 +285,17 @@ class PNAPCSAFT(nn.Module):
         self._arena: Optional[torch.Tensor] = None
         self._arena_offsets: List[int] = []
         self._row_off = None
+        # dense stages: "tf32x3" = tcgen05 with fp32 operands split into tf32 hi+lo (fp32-level accuracy),
+        # "bf16" = tcgen05 bf16 operands / fp32 accumulate (torch "medium" matmul precision, which the
+        # reference itself sets at train.py:319), "simt" = plain fp32 FMA kernels
+        self.matmul_precision = os.environ.get("GNN_B200_MATMUL", DEFAULT_MATMUL)
+
+    def _matmul_mode(self) -> int:
+        try:
+            mm = MATMUL_MODES[self.matmul_precision]
+        except KeyError:
+            raise ValueError(f"matmul_precision must be one of {sorted(MATMUL_MODES)}") from None
+        return mm
 
     # ---- flat parameter arena -------------------------------------------------------------
     def _param_list(self):
@@ -318,6 +414,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         raise NotImplementedError("gnnepcsaft_b200: dropout > 0 in training mode is not implemented "
                                   "(the reference configs use dropout_rate = 0.0)")
     dev = x_idx.device
+    mm = model._matmul_mode()
     H = model.hidden_dim
     F, Fo, T = H, H // TOWERS, TOWERS
     C = T * F
@@ -365,8 +462,8 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         for t in range(T):
             w = conv.pre_nns[t][0].weight
             b = conv.pre_nns[t][0].bias
-            _c("gnn_linear_fwd", x, H, w, 3 * F, b, n, F, F, 0, P[:, t * F:], 2 * C)
-            _c("gnn_linear_fwd", x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
+            _lin_fwd(mm, x, H, w, 3 * F, b, n, F, F, 0, P[:, t * F:], 2 * C)
+            _lin_fwd(mm, x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
         A = torch.empty(n, T * 4 * F, **f32)
         rec.P = P
         if pp.pre_layers == 1:
@@ -381,7 +478,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
                 last = k == pp.pre_layers - 1
                 for t in range(T):
                     lin = conv.pre_nns[t][2 * k]
-                    _c("gnn_linear_fwd", h[:, t * F:], C, lin.weight, F, lin.bias, g.ep, F, F, 0 if last else 1,
+                    _lin_fwd(mm, h[:, t * F:], C, lin.weight, F, lin.bias, g.ep, F, F, 0 if last else 1,
                        h2[:, t * F:], C)
                 hs.append(h2)
                 h = h2
@@ -396,7 +493,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         bias_stride_post = model._offset_of(conv.post_nns[1][0].bias) - model._offset_of(conv.post_nns[0][0].bias)
         rec.post_strides = (tower_stride_post, bias_stride_post)
         O = torch.empty(n, H, **f32)
-        _c("gnn_pna_post_fwd", x, A, scal, conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias,
+        _post_fwd(mm, x, A, scal, conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias,
            bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O)
         os_ = [O]
         for k in range(1, pp.post_layers):
@@ -404,13 +501,13 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
             last = k == pp.post_layers - 1
             for t in range(T):
                 lin = conv.post_nns[t][2 * k]
-                _c("gnn_linear_fwd", O[:, t * Fo:], H, lin.weight, Fo, lin.bias, n, Fo, Fo, 0 if last else 1,
+                _lin_fwd(mm, O[:, t * Fo:], H, lin.weight, Fo, lin.bias, n, Fo, Fo, 0 if last else 1,
                    O2[:, t * Fo:], H)
             os_.append(O2)
             O = O2
         rec.os = os_
         y = torch.empty(n, H, **f32)
-        _c("gnn_linear_fwd", O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H)
+        _lin_fwd(mm, O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H)
         rec.y = y
         x, rec.stats, rec.bn_batch = _bn_forward(y, bn, training, rec.x_in if pp.skip_connections else None, True)
         if save:
@@ -429,7 +526,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         rec = _Saved()
         rec.inp, rec.lin, rec.bn = hcur, lin, bn
         z = torch.empty(hcur.shape[0], lin.out_features, **f32)
-        _c("gnn_linear_fwd", hcur, lin.in_features, lin.weight, lin.in_features, lin.bias, hcur.shape[0],
+        _lin_fwd(mm, hcur, lin.in_features, lin.weight, lin.in_features, lin.bias, hcur.shape[0],
            lin.out_features, lin.in_features, 0, z, lin.out_features)
         rec.z = z
         if bn is not None:
@@ -450,7 +547,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         sv.g, sv.layers, sv.head, sv.enc, sv.tab = g, layers, head, enc, tab
         sv.x_idx, sv.x_final, sv.n, sv.num_graphs = x_idx, x, n, num_graphs
         sv.layer_stride, sv.tower_stride_pre = layer_stride, tower_stride_pre
-        sv.training = training
+        sv.training, sv.mm = training, mm
     return out, sv
 
 
@@ -459,6 +556,7 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
     as the parameter arena)."""
     pp = model.pna_params
     dev = dout.device
+    mm = sv.mm
     H = model.hidden_dim
     F, Fo, T = H, H // TOWERS, TOWERS
     C = T * F
@@ -487,10 +585,10 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
         if rec.bn is not None:
             d = bn_backward(d, rec.z, rec.stats, rec.bn, True, rec.bn_batch)
         rows = rec.inp.shape[0]
-        _c("gnn_linear_wgrad", d, lin.out_features, rec.inp, lin.in_features, rows, lin.out_features,
+        _lin_wgrad(mm, d, lin.out_features, rec.inp, lin.in_features, rows, lin.out_features,
            lin.in_features, gview(lin.weight), lin.in_features, gview(lin.bias))
         dprev = torch.empty(rows, lin.in_features, **f32)
-        _c("gnn_linear_dgrad", d, lin.out_features, lin.weight, lin.in_features, rows, lin.out_features,
+        _lin_dgrad(mm, d, lin.out_features, lin.weight, lin.in_features, rows, lin.out_features,
            lin.in_features, 0, dprev, lin.in_features)
         d = dprev
     # ---- pool
@@ -507,25 +605,25 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
             dx = torch.zeros(n, H, **f32)        # else: dx (the skip gradient) keeps accumulating
         # lin
         O_last = rec.os[-1]
-        _c("gnn_linear_wgrad", dy, H, O_last, H, n, H, H, gview(conv.lin.weight), H, gview(conv.lin.bias))
+        _lin_wgrad(mm, dy, H, O_last, H, n, H, H, gview(conv.lin.weight), H, gview(conv.lin.bias))
         dO = torch.empty(n, H, **f32)
-        _c("gnn_linear_dgrad", dy, H, conv.lin.weight, H, n, H, H, 0, dO, H)
+        _lin_dgrad(mm, dy, H, conv.lin.weight, H, n, H, H, 0, dO, H)
         # extra post layers
         for k in reversed(range(1, pp.post_layers)):
             O_in = rec.os[k - 1]
             dprev = torch.empty(n, H, **f32)
             for t in range(T):
                 lin = conv.post_nns[t][2 * k]
-                _c("gnn_linear_wgrad", dO[:, t * Fo:], H, O_in[:, t * Fo:], H, n, Fo, Fo, gview(lin.weight), Fo,
+                _lin_wgrad(mm, dO[:, t * Fo:], H, O_in[:, t * Fo:], H, n, Fo, Fo, gview(lin.weight), Fo,
                    gview(lin.bias))
-                _c("gnn_linear_dgrad", dO[:, t * Fo:], H, lin.weight, Fo, n, Fo, Fo, 0, dprev[:, t * Fo:], H)
+                _lin_dgrad(mm, dO[:, t * Fo:], H, lin.weight, Fo, n, Fo, Fo, 0, dprev[:, t * Fo:], H)
             _c("gnn_relu_bwd", dprev, O_in, n * H)
             dO = dprev
         ts_post, bs_post = rec.post_strides
         w0, b0 = conv.post_nns[0][0].weight, conv.post_nns[0][0].bias
-        _c("gnn_pna_post_wgrad", dO, x_in, rec.A, rec.scal, n, F, Fo, T, gview(w0), ts_post, gview(b0), bs_post)
+        _post_wgrad(mm, dO, x_in, rec.A, rec.scal, n, F, Fo, T, gview(w0), ts_post, gview(b0), bs_post)
         gA = torch.empty(n, T * 4 * F, **f32)
-        _c("gnn_pna_post_dgrad", dO, rec.scal, w0, ts_post, n, F, Fo, T, dx, gA)
+        _post_dgrad(mm, dO, rec.scal, w0, ts_post, n, F, Fo, T, dx, gA)
         # aggregation + message
         dP = torch.empty(n, 2 * C, **f32)
         if pp.pre_layers == 1:
@@ -541,9 +639,9 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
                 dprev = torch.empty(max(g.ep, 1), C, **f32)
                 for t in range(T):
                     lin = conv.pre_nns[t][2 * k]
-                    _c("gnn_linear_wgrad", dm[:, t * F:], C, h_in[:, t * F:], C, g.ep, F, F, gview(lin.weight), F,
+                    _lin_wgrad(mm, dm[:, t * F:], C, h_in[:, t * F:], C, g.ep, F, F, gview(lin.weight), F,
                        gview(lin.bias))
-                    _c("gnn_linear_dgrad", dm[:, t * F:], C, lin.weight, F, g.ep, F, F, 0, dprev[:, t * F:], C)
+                    _lin_dgrad(mm, dm[:, t * F:], C, lin.weight, F, g.ep, F, F, 0, dprev[:, t * F:], C)
                 _c("gnn_relu_bwd", dprev, h_in, g.ep * C)
                 dm = dprev
             dq = dm
@@ -553,10 +651,10 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
         for t in range(T):
             lin = conv.pre_nns[t][0]
             gw = gview(lin.weight)
-            _c("gnn_linear_wgrad", dP[:, t * F:], 2 * C, x_in, H, n, F, F, gw, 3 * F, gview(lin.bias))
-            _c("gnn_linear_wgrad", dP[:, C + t * F:], 2 * C, x_in, H, n, F, F, gw[:, F:], 3 * F, None)
-            _c("gnn_linear_dgrad", dP[:, t * F:], 2 * C, lin.weight, 3 * F, n, F, F, 1, dx, H)
-            _c("gnn_linear_dgrad", dP[:, C + t * F:], 2 * C, lin.weight[:, F:], 3 * F, n, F, F, 1, dx, H)
+            _lin_wgrad(mm, dP[:, t * F:], 2 * C, x_in, H, n, F, F, gw, 3 * F, gview(lin.bias))
+            _lin_wgrad(mm, dP[:, C + t * F:], 2 * C, x_in, H, n, F, F, gw[:, F:], 3 * F, None)
+            _lin_dgrad(mm, dP[:, t * F:], 2 * C, lin.weight, 3 * F, n, F, F, 1, dx, H)
+            _lin_dgrad(mm, dP[:, C + t * F:], 2 * C, lin.weight[:, F:], 3 * F, n, F, F, 1, dx, H)
 
     # ---- encoders
     atom_tab = model.node_embed.atom_embedding_list[0].weight

@@ -192,6 +192,33 @@ int gnn_pna_post_wgrad(const float* dO, const float* x, const float* A, const fl
                        int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride,
                        void* stream);
 
+/* ---------------------------------------------------------------- dense stages (tcgen05 / TMEM)
+ * The same contractions on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+ * `precision`: 0 = TF32x3 (fp32 operands split into tf32 hi+lo, 3 MMAs: fp32-level accuracy, the
+ * parity path), 2 = BF16 operands, fp32 accumulate (the reference's own
+ * torch.set_float32_matmul_precision("medium"), train.py:319).  Semantics equal the gnn_linear_* /
+ * gnn_pna_post_* entry points above, except that weight-gradient calls do not produce bias
+ * gradients: use gnn_colsum_accum (db[n] += sum_i dY[i,n]). */
+int gnn_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
+                      int64_t M, int N, int K, int act, float* Y, int64_t ldy, int precision,
+                      void* stream);
+int gnn_tc_linear_dgrad(const float* dY, int64_t lddy, const float* W, int64_t ldw, int64_t M, int N,
+                        int K, int accumulate, float* dX, int64_t lddx, int precision, void* stream);
+int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t M, int N,
+                        int K, float* dW, int64_t lddw, int precision, void* stream);
+int gnn_colsum_accum(const float* dY, int64_t lddy, int64_t M, int N, float* db, void* stream);
+int gnn_tc_pna_post_fwd(const float* x, const float* A, const float* scal, const float* wpost,
+                        int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
+                        int64_t num_nodes, int F, int F_out, int towers, int act, float* O,
+                        int precision, void* stream);
+int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const float* wpost,
+                          int64_t wpost_tower_stride, int64_t num_nodes, int F, int F_out, int towers,
+                          float* dx, float* gA, int precision, void* stream);
+int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const float* scal,
+                          int64_t num_nodes, int F, int F_out, int towers, float* dwpost,
+                          int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride,
+                          int precision, void* stream);
+
 /* ---------------------------------------------------------------- BatchNorm / ReLU / skip
  * Replaces PyG BatchNorm / torch BatchNorm1d + F.relu + skip (models.py:128-131, head BN).
  * Training: batch statistics (biased var for normalisation, unbiased for running_var,

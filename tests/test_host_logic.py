@@ -92,3 +92,37 @@ def test_cpu_tensors_are_rejected():
     _, _, m = make_pair(c, torch.tensor([0, 3, 2, 1]), dtype64=False)
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(batch_from_packed(make_packed_graphs(2, seed=0)))
+
+
+def test_engine_steps_match_reference_training_loop(cpu_backend):
+    """TrainEngine.step == reference training_step + AdamW(amsgrad) + CosineAnnealingWarmRestarts per step."""
+    from gnnepcsaft_b200.train.engine import TrainEngine
+    c = cfg(propagation_depth=2, warmup_steps=3)
+    packed = make_packed_graphs(12, seed=4)
+    o32, _, m = make_pair(c, packed.in_degree_histogram(), dtype64=False)
+    o32.train()
+    opt = torch.optim.AdamW(o32.parameters(), lr=c.learning_rate, weight_decay=c.weight_decay, amsgrad=True, eps=1e-5)
+    sched = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, c.warmup_steps)
+    engine = TrainEngine.from_config(m, c, distributed=False)
+    p_start = torch.cat([p.data.reshape(-1).clone() for p in o32.parameters()])
+    for it in range(5):
+        batch = batch_from_packed(packed, torch.arange(it % 2 * 6, it % 2 * 6 + 6))
+        opt.zero_grad()
+        loss_ref = O.mape(o32(batch), batch.para.view(-1, c.num_para))
+        loss_ref.backward()
+        opt.step()
+        sched.step()
+        loss = engine.step(batch)
+        assert abs(float(loss) - float(loss_ref)) <= 1e-4 * abs(float(loss_ref)) + 1e-6, it
+    # Adam normalises each element by its own gradient scale, so elements whose gradient is rounding
+    # noise move by up to ~lr in either implementation: compare the update as a whole, not elementwise
+    p_ref = torch.cat([p.data.reshape(-1) for p in o32.parameters()])
+    p_eng = torch.cat([p.data.reshape(-1) for p in m.parameters()])
+    rel = float((p_eng - p_ref).norm() / (p_ref - p_start).norm())
+    assert rel < 5e-2, rel
+    out = engine.predict(batch_from_packed(packed))
+    o32.eval()
+    with torch.no_grad():
+        torch.testing.assert_close(out, o32(batch_from_packed(packed)), rtol=1e-3, atol=1e-4)
+    sd = engine.optimizer_state_dict()
+    assert len(sd["state"]) == len(list(m.parameters())) and sd["param_groups"][0]["amsgrad"]

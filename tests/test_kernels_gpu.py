@@ -421,3 +421,73 @@ def test_adamw_amsgrad_cosine_restarts_vs_torch():
     torch.cuda.synchronize()
     assert int(step.item()) == 25
     close(p, ref.detach(), 2e-6, "parameters after 25 fused AdamW steps")
+
+
+# ------------------------------------------------------------------ tcgen05 / TMEM dense stages
+# precision 0 = TF32x3 (fp32-level: 1e-5), 2 = bf16 operands (stated tolerance 2e-2 of the tensor scale)
+TC_TOL = {0: 1e-5, 2: 2e-2}
+
+
+@pytest.mark.parametrize("precision", [0, 2])
+@pytest.mark.parametrize("M,N,K,ldx,ldw,ldy", [(1000, 64, 64, 64, 192, 256), (1, 5, 16, 16, 16, 5),
+                                               (333, 32, 832, 832, 832, 64), (129, 256, 64, 70, 64, 256),
+                                               (4096, 16, 32, 32, 32, 16), (77, 10, 20, 20, 20, 10),
+                                               (5000, 64, 100, 100, 100, 64)])
+def test_tc_linear_fwd_dgrad_wgrad(precision, M, N, K, ldx, ldw, ldy):
+    tol = TC_TOL[precision]
+    g = torch.Generator().manual_seed(M + N + K)
+    X, W, b = torch.randn(M, ldx, generator=g), torch.randn(N, ldw, generator=g) * 0.1, torch.randn(N, generator=g)
+    for act in (0, 1):
+        Y = torch.full((M, ldy), 7.0)
+        cpu, gpu = run_both("gnn_tc_linear_fwd", X, ldx, W, ldw, b, M, N, K, act, Y, ldy, precision)
+        close(gpu[-3], cpu[-3], tol, "tc linear fwd")
+    dY = torch.randn(M, ldy, generator=g)
+    for acc in (0, 1):
+        dX = torch.randn(M, ldx, generator=g)
+        cpu, gpu = run_both("gnn_tc_linear_dgrad", dY, ldy, W, ldw, M, N, K, acc, dX, ldx, precision)
+        close(gpu[-3], cpu[-3], tol, "tc linear dgrad")
+    dW = torch.randn(N, ldw, generator=g)
+    cpu, gpu = run_both("gnn_tc_linear_wgrad", dY, ldy, X, ldx, M, N, K, dW, ldw, precision)
+    close(gpu[-3], cpu[-3], 2 * tol, "tc linear wgrad")
+    db = torch.randn(N, generator=g)
+    cpu, gpu = run_both("gnn_colsum_accum", dY, ldy, M, N, db)
+    close(gpu[-1], cpu[-1], 2e-5, "colsum")
+
+
+@pytest.mark.parametrize("precision", [0, 2])
+@pytest.mark.parametrize("n,F", [(300, 64), (70, 16), (1, 8), (130, 128), (257, 256), (90, 40)])
+def test_tc_pna_post_fwd_dgrad_wgrad(precision, n, F):
+    tol = TC_TOL[precision]
+    T, Fo = 2, F // 2
+    g = torch.Generator().manual_seed(n + F)
+    x, A = torch.randn(n, F, generator=g), torch.randn(n, T * 4 * F, generator=g)
+    scal = torch.rand(n, 2, generator=g) + 0.5
+    wts = Fo * 13 * F + Fo + 4
+    wbuf = torch.randn(T * wts, generator=g) * 0.1
+    bts, boff = wts, Fo * 13 * F
+    for act in (0, 1):
+        res = []
+        for dev in ("cpu", DEV):
+            base = wbuf.to(dev).clone()
+            args = [x.to(dev), A.to(dev), scal.to(dev), base, wts, base[boff:], bts, n, F, Fo, T, act,
+                    torch.zeros(n, T * Fo).to(dev), precision]
+            R.gnn_tc_pna_post_fwd(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_post_fwd", *args, _lib.stream_ptr())
+            res.append(args[-2])
+        close(res[1], res[0], tol, "tc post fwd")
+    dO = torch.randn(n, T * Fo, generator=g)
+    res = []
+    for dev in ("cpu", DEV):
+        base = wbuf.to(dev).clone()
+        dx, gA = torch.ones(n, F).to(dev), torch.zeros(n, T * 4 * F).to(dev)
+        args = [dO.to(dev), scal.to(dev), base, wts, n, F, Fo, T, dx, gA, precision]
+        R.gnn_tc_pna_post_dgrad(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_post_dgrad", *args, _lib.stream_ptr())
+        res.append((dx, gA))
+    close(res[1][0], res[0][0], tol, "tc post dgrad dx")
+    close(res[1][1], res[0][1], tol, "tc post dgrad gA")
+    res = []
+    for dev in ("cpu", DEV):
+        gbase = torch.zeros(T * wts).to(dev)
+        args = [dO.to(dev), x.to(dev), A.to(dev), scal.to(dev), n, F, Fo, T, gbase, wts, gbase[boff:], bts, precision]
+        R.gnn_tc_pna_post_wgrad(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_post_wgrad", *args, _lib.stream_ptr())
+        res.append(gbase)
+    close(res[1], res[0], 2 * tol, "tc post wgrad")

@@ -187,3 +187,34 @@ def test_full_size_properties_4096_graphs():
     for (name, p) in m.named_parameters():
         assert torch.isfinite(p.grad).all(), name
     assert float(flat_grads(m)[mask].abs().max()) > 0
+
+
+@pytest.mark.parametrize("precision,fwd_tol,grad_tol", [("tf32x3", 1e-5, 2e-3), ("bf16", 3e-2, 1e-1)])
+@pytest.mark.parametrize("name", ["default", "pre2_post2", "wide_small"])
+def test_tensor_core_dense_stages(name, precision, fwd_tol, grad_tol):
+    """Dense stages on tcgen05: TF32x3 must meet the fp32 parity bar; bf16 operands (the reference's
+    own torch "medium" matmul precision) are held to the stated tolerance: 3e-2 of max|y| forward,
+    1e-1 relative L2 on the gradient."""
+    c = cfg(**CONFIGS[name])
+    packed = make_packed_graphs(128, seed=6, num_para=c.num_para)
+    batch = batch_from_packed(packed)
+    o32, o64, m = make_pair(c, packed.in_degree_histogram())
+    m.matmul_precision = precision
+    m.to(DEV)
+    for mod in (o32, o64, m):
+        mod.eval()
+    with torch.no_grad():
+        y32, y64, y = o32(batch), o64(batch), m(batch.to(DEV))
+    e_m, e_o, e_mo = _errs(y, y32, y64)
+    print(f"{name}/{precision}: eval fwd cuda-vs-fp64 {e_m:.2e} (oracle32 {e_o:.2e})")
+    assert e_m <= max(fwd_tol, 2 * e_o + 1e-6)
+    for mod in (o64, m):
+        mod.train()
+    tgt = batch.para.view(-1, c.num_para)
+    O.mape(o64(batch), tgt.double()).backward()
+    M.mape(m(batch.to(DEV)), tgt.to(DEV)).backward()
+    mask = zero_grad_bias_mask(m)
+    g64, g = flat_grads(o64), flat_grads(m)
+    rel = float((g - g64)[mask].norm() / g64[mask].norm())
+    print(f"{name}/{precision}: grad rel-L2 {rel:.2e}")
+    assert rel <= grad_tol
