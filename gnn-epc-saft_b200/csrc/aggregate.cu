@@ -44,72 +44,125 @@ __device__ __forceinline__ void store_aggregates(float* __restrict__ A, int64_t 
 }
 
 // ------------------------------------------------------------------ forward, factorised message
-template <int CHUNKS>
-__global__ void __launch_bounds__(AGG_THREADS)
+// One warp walks the CSR slots of NODES_PER_WARP consecutive destination nodes as ONE edge stream:
+//   * rowptr / col_src / col_code of the whole chunk are fetched with coalesced lane-parallel loads
+//     and distributed by shuffles (no dependent scalar index loads per edge);
+//   * gathers are issued four edges ahead of their use (memory-level parallelism), Pdst of the next
+//     node is prefetched while the current node accumulates;
+//   * statistics are single-pass on data shifted by the segment's first message q0:
+//     s1 = sum(q-q0), s2 = sum((q-q0)^2) -> mean = q0 + s1/n, var = s2/n - (s1/n)^2  (the shift removes
+//     the cancellation of the textbook E[q^2]-E[q]^2 form; no per-edge division as in Welford);
+//   * results leave through streaming 128-bit stores.
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // max rel. error 2^-23, one MUFU op
+    return y;
+}
+__device__ __forceinline__ float pna_std_fast(float var) {
+    return var > 1e-5f ? sqrt_approx(var) : 0.0f;             // == sqrt(clamp(var,1e-5)) masked at the floor
+}
+
+struct SegStat {
+    float4 q0, s1, s2, mn, mx;
+};
+
+__device__ __forceinline__ void seg_first(SegStat& st, float4 q) {
+    st.q0 = q;
+    st.mn = q;
+    st.mx = q;
+    st.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    st.s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ void seg_add(SegStat& st, float4 q) {
+    float dx = q.x - st.q0.x, dy = q.y - st.q0.y, dz = q.z - st.q0.z, dw = q.w - st.q0.w;
+    st.s1.x += dx; st.s1.y += dy; st.s1.z += dz; st.s1.w += dw;
+    st.s2.x = fmaf(dx, dx, st.s2.x); st.s2.y = fmaf(dy, dy, st.s2.y);
+    st.s2.z = fmaf(dz, dz, st.s2.z); st.s2.w = fmaf(dw, dw, st.s2.w);
+    st.mn = make_float4(fminf(st.mn.x, q.x), fminf(st.mn.y, q.y), fminf(st.mn.z, q.z), fminf(st.mn.w, q.w));
+    st.mx = make_float4(fmaxf(st.mx.x, q.x), fmaxf(st.mx.y, q.y), fmaxf(st.mx.z, q.z), fmaxf(st.mx.w, q.w));
+}
+__device__ __forceinline__ void seg_finish(const SegStat& st, int cnt, float4 pd, float* __restrict__ A, int64_t node,
+                                           int C, int F, int c) {
+    if (cnt == 0) {
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        store_aggregates(A, node, C, F, c, z, z, z, z);
+        return;
+    }
+    const float inv = __frcp_rn((float)cnt);
+    float4 m1 = make_float4(st.s1.x * inv, st.s1.y * inv, st.s1.z * inv, st.s1.w * inv);
+    float4 sd = make_float4(pna_std_fast(fmaf(-m1.x, m1.x, st.s2.x * inv)), pna_std_fast(fmaf(-m1.y, m1.y, st.s2.y * inv)),
+                            pna_std_fast(fmaf(-m1.z, m1.z, st.s2.z * inv)), pna_std_fast(fmaf(-m1.w, m1.w, st.s2.w * inv)));
+    float4 mean = make_float4(st.q0.x + m1.x + pd.x, st.q0.y + m1.y + pd.y, st.q0.z + m1.z + pd.z, st.q0.w + m1.w + pd.w);
+    store_aggregates(A, node, C, F, c, mean, add4(st.mn, pd), add4(st.mx, pd), sd);
+}
+
+// one warp per destination node, 128 channels per pass; the gather of edge k+1 is in flight while edge k
+// is accumulated (software pipelining), indices come from one lane-parallel load + shuffles.
+__global__ void __launch_bounds__(AGG_THREADS, 4)
 pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ tab,
                          const int* __restrict__ rowptr, const int* __restrict__ col_src,
                          const uint8_t* __restrict__ col_code, int64_t n, int C, int F, float* __restrict__ A) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * AGG_WARPS;
-    const int64_t ldp = 2 * (int64_t)C;
+    const int ldp = 2 * C;
     for (int64_t node = warp0; node < n; node += nwarps) {
-        const int beg = rowptr[node], end = rowptr[node + 1];
+        const int rp = __ldg(rowptr + node + (lane & 1));
+        const int beg = __shfl_sync(GNN_FULL_MASK, rp, 0), end = __shfl_sync(GNN_FULL_MASK, rp, 1);
         const int cnt = end - beg;
-        Stat4 st[CHUNKS];
-#pragma unroll
-        for (int j = 0; j < CHUNKS; ++j) {
-            st[j].mean = make_float4(0.f, 0.f, 0.f, 0.f);
-            st[j].m2 = make_float4(0.f, 0.f, 0.f, 0.f);
-            st[j].mn = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
-            st[j].mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+        // row offsets of the first 32 in-edges (all of them for molecular graphs), pre-scaled
+        int my_src = 0, my_code = 0;
+        if (lane < cnt) {
+            my_src = __ldg(col_src + beg + lane) * ldp + C;
+            my_code = (int)__ldg(col_code + beg + lane) * C;
         }
-        for (int base = beg; base < end; base += 32) {
-            const int m = min(32, end - base);
-            int my_src = 0, my_code = 0;
-            if (lane < m) {
-                my_src = __ldg(col_src + base + lane);
-                my_code = __ldg(col_code + base + lane);
+        for (int cb = 0; cb < C; cb += 128) {                  // warp-uniform trip count (shuffles inside)
+            const int c = cb + lane * 4;
+            const bool live = c < C;
+            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cnt == 0) {
+                if (live) store_aggregates(A, node, C, F, c, zero, zero, zero, zero);
+                continue;
             }
-            for (int k = 0; k < m; ++k) {
-                const int src = __shfl_sync(GNN_FULL_MASK, my_src, k);
-                const int code = __shfl_sync(GNN_FULL_MASK, my_code, k);
-                const float inv_k = 1.0f / (float)(base - beg + k + 1);
-                const float* prow = P + (int64_t)src * ldp + C;
-                const float* trow = tab + (int64_t)code * C;
-#pragma unroll
-                for (int j = 0; j < CHUNKS; ++j) {
-                    const int c = j * 128 + lane * 4;
-                    if (c < C) {
-                        float4 q = add4(ldg4(prow + c), ldg4(trow + c));
-                        welford_update(st[j].mean.x, st[j].m2.x, q.x, inv_k);
-                        welford_update(st[j].mean.y, st[j].m2.y, q.y, inv_k);
-                        welford_update(st[j].mean.z, st[j].m2.z, q.z, inv_k);
-                        welford_update(st[j].mean.w, st[j].m2.w, q.w, inv_k);
-                        st[j].mn = make_float4(fminf(st[j].mn.x, q.x), fminf(st[j].mn.y, q.y),
-                                               fminf(st[j].mn.z, q.z), fminf(st[j].mn.w, q.w));
-                        st[j].mx = make_float4(fmaxf(st[j].mx.x, q.x), fmaxf(st[j].mx.y, q.y),
-                                               fmaxf(st[j].mx.z, q.z), fmaxf(st[j].mx.w, q.w));
+            const float* pbase = P + c;
+            const float* tbase = tab + c;
+            const float4 pd = live ? ldg4(pbase + node * ldp) : zero;
+            const int m = min(cnt, 32);
+            // edge 0 defines the shift
+            int so = __shfl_sync(GNN_FULL_MASK, my_src, 0), co = __shfl_sync(GNN_FULL_MASK, my_code, 0);
+            float4 pn = live ? ldg4(pbase + so) : zero, tn = live ? ldg4(tbase + co) : zero;
+            SegStat st;
+            {
+                const float4 pc = pn, tc_ = tn;
+                if (1 < m) {
+                    so = __shfl_sync(GNN_FULL_MASK, my_src, 1);
+                    co = __shfl_sync(GNN_FULL_MASK, my_code, 1);
+                    if (live) {
+                        pn = ldg4(pbase + so);
+                        tn = ldg4(tbase + co);
                     }
                 }
+                seg_first(st, add4(pc, tc_));
             }
-        }
-        const float inv_cnt = cnt > 0 ? 1.0f / (float)cnt : 0.0f;
-#pragma unroll
-        for (int j = 0; j < CHUNKS; ++j) {
-            const int c = j * 128 + lane * 4;
-            if (c < C) {
-                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (cnt == 0) {
-                    store_aggregates(A, node, C, F, c, z, z, z, z);
-                } else {
-                    float4 pd = ldg4(P + node * ldp + c);
-                    float4 sd = make_float4(pna_std(st[j].m2.x * inv_cnt), pna_std(st[j].m2.y * inv_cnt),
-                                            pna_std(st[j].m2.z * inv_cnt), pna_std(st[j].m2.w * inv_cnt));
-                    store_aggregates(A, node, C, F, c, add4(st[j].mean, pd), add4(st[j].mn, pd),
-                                     add4(st[j].mx, pd), sd);
+            for (int k = 1; k < m; ++k) {
+                const float4 pc = pn, tc_ = tn;
+                if (k + 1 < m) {                                           // warp-uniform: prefetch the next edge
+                    so = __shfl_sync(GNN_FULL_MASK, my_src, k + 1);
+                    co = __shfl_sync(GNN_FULL_MASK, my_code, k + 1);
+                    if (live) {
+                        pn = ldg4(pbase + so);
+                        tn = ldg4(tbase + co);
+                    }
                 }
+                seg_add(st, add4(pc, tc_));
             }
+            // in-degree > 32 (never for molecules): plain loop over the remaining slots
+            for (int s = beg + 32; s < end; ++s) {
+                const int so2 = __ldg(col_src + s) * ldp + C, co2 = (int)__ldg(col_code + s) * C;
+                if (live) seg_add(st, add4(ldg4(pbase + so2), ldg4(tbase + co2)));
+            }
+            if (live) seg_finish(st, cnt, pd, A, node, C, F, c);
         }
     }
 }
@@ -128,20 +181,11 @@ extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int
     if (n < 0 || towers < 1 || F < 4 || (F & 3)) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
     const int C = towers * F;
-    const int chunks = (C + 127) / 128;
     cudaStream_t st = gnn_stream(stream);
-    const int grid = agg_grid(n);
-#define LAUNCH_FWD(CH) pna_aggregate_fwd_kernel<CH><<<grid, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, n, C, F, A)
-    switch (chunks) {
-        case 1: LAUNCH_FWD(1); break;
-        case 2: LAUNCH_FWD(2); break;
-        case 3: LAUNCH_FWD(3); break;
-        case 4: LAUNCH_FWD(4); break;
-        case 5: case 6: LAUNCH_FWD(6); break;
-        case 7: case 8: LAUNCH_FWD(8); break;
-        default: return GNN_ERR_UNSUPPORTED;
-    }
-#undef LAUNCH_FWD
+    int64_t blocks = gnn_ceil_div(n, AGG_WARPS);
+    int64_t cap = (int64_t)gnn_sm_count() * 48;
+    if (blocks > cap) blocks = cap;
+    pna_aggregate_fwd_kernel<<<(unsigned)blocks, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, n, C, F, A);
     return gnn_launch_status();
 }
 

@@ -22,7 +22,7 @@ from .. import _lib
 from ..data.graph import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS, NUM_BOND_CODES
 
 TOWERS = 2  # reference models.py:76
-DEFAULT_MATMUL = "simt"
+DEFAULT_MATMUL = "tf32x3"
 
 
 @dataclasses.dataclass
@@ -151,14 +151,16 @@ def _lin_fwd(mm, X, ldx, W, ldw, bias, M, N, K, act, Y, ldy):
     if mm < 0:
         _c("gnn_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy)
     else:
-        _c("gnn_tc_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, mm)
+        ws = _pack_ws(Y.device)
+        _c("gnn_tc_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, mm, ws, ws.numel())
 
 
 def _lin_dgrad(mm, dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx):
     if mm < 0:
         _c("gnn_linear_dgrad", dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx)
     else:
-        _c("gnn_tc_linear_dgrad", dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, mm)
+        ws = _pack_ws(dX.device)
+        _c("gnn_tc_linear_dgrad", dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, mm, ws, ws.numel())
 
 
 def _lin_wgrad(mm, dY, lddy, X, ldx, M, N, K, dW, lddw, db):
@@ -174,14 +176,16 @@ def _post_fwd(mm, *args):
     if mm < 0:
         _c("gnn_pna_post_fwd", *args)
     else:
-        _c("gnn_tc_pna_post_fwd", *args, mm)
+        ws = _pack_ws(args[-1].device)
+        _c("gnn_tc_pna_post_fwd", *args, mm, ws, ws.numel())
 
 
 def _post_dgrad(mm, *args):
     if mm < 0:
         _c("gnn_pna_post_dgrad", *args)
     else:
-        _c("gnn_tc_pna_post_dgrad", *args, mm)
+        ws = _pack_ws(args[-1].device)
+        _c("gnn_tc_pna_post_dgrad", *args, mm, ws, ws.numel())
 
 
 def _post_wgrad(mm, *args):
@@ -206,6 +210,12 @@ class _Workspace:
 
 
 _WS = _Workspace()
+PACK_WS_BYTES = 4 << 20
+
+
+def _pack_ws(device):
+    """Scratch for the packed weight operand of the tensor-core GEMMs (stream-ordered reuse)."""
+    return _WS.get("pack", PACK_WS_BYTES, device)
 
 
 class GraphStructure:
@@ -459,11 +469,12 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         rec.x_in = x
         # node projections  P = [Pdst_t0 | Pdst_t1 | Psrc_t0 | Psrc_t1]
         P = torch.empty(n, 2 * C, **f32)
+        mm_proj = 0 if mm == 2 else mm      # bf16 mode: messages stay fp32-accurate (min/max/std are selection-sensitive)
         for t in range(T):
             w = conv.pre_nns[t][0].weight
             b = conv.pre_nns[t][0].bias
-            _lin_fwd(mm, x, H, w, 3 * F, b, n, F, F, 0, P[:, t * F:], 2 * C)
-            _lin_fwd(mm, x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
+            _lin_fwd(mm_proj, x, H, w, 3 * F, b, n, F, F, 0, P[:, t * F:], 2 * C)
+            _lin_fwd(mm_proj, x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
         A = torch.empty(n, T * 4 * F, **f32)
         rec.P = P
         if pp.pre_layers == 1:

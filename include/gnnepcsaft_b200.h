@@ -198,22 +198,27 @@ int gnn_pna_post_wgrad(const float* dO, const float* x, const float* A, const fl
  * parity path), 2 = BF16 operands, fp32 accumulate (the reference's own
  * torch.set_float32_matmul_precision("medium"), train.py:319).  Semantics equal the gnn_linear_* /
  * gnn_pna_post_* entry points above, except that weight-gradient calls do not produce bias
- * gradients: use gnn_colsum_accum (db[n] += sum_i dY[i,n]). */
+ * gradients: use gnn_colsum_accum (db[n] += sum_i dY[i,n]).
+ * pack_ws (optional, 128-byte aligned, may be NULL): scratch in which the weight operand is first packed
+ * as the exact shared-memory tile image (swizzled, hi/lo planes) so the GEMM fetches it with TMA bulk
+ * copies instead of re-converting it for every 128-row tile; 4 MiB covers every shape of the model. */
 int gnn_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
                       int64_t M, int N, int K, int act, float* Y, int64_t ldy, int precision,
-                      void* stream);
+                      void* pack_ws, int64_t pack_ws_bytes, void* stream);
 int gnn_tc_linear_dgrad(const float* dY, int64_t lddy, const float* W, int64_t ldw, int64_t M, int N,
-                        int K, int accumulate, float* dX, int64_t lddx, int precision, void* stream);
+                        int K, int accumulate, float* dX, int64_t lddx, int precision, void* pack_ws,
+                        int64_t pack_ws_bytes, void* stream);
 int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t M, int N,
                         int K, float* dW, int64_t lddw, int precision, void* stream);
 int gnn_colsum_accum(const float* dY, int64_t lddy, int64_t M, int N, float* db, void* stream);
 int gnn_tc_pna_post_fwd(const float* x, const float* A, const float* scal, const float* wpost,
                         int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
                         int64_t num_nodes, int F, int F_out, int towers, int act, float* O,
-                        int precision, void* stream);
+                        int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream);
 int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const float* wpost,
                           int64_t wpost_tower_stride, int64_t num_nodes, int F, int F_out, int towers,
-                          float* dx, float* gA, int precision, void* stream);
+                          float* dx, float* gA, int precision, void* pack_ws, int64_t pack_ws_bytes,
+                          void* stream);
 int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const float* scal,
                           int64_t num_nodes, int F, int F_out, int towers, float* dwpost,
                           int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride,

@@ -334,11 +334,13 @@ def gnn_pna_post_wgrad(dO, x, A, scal, n, f, f_out, towers, dwpost, wts, dbpost,
 
 
 # tensor-core entry points: same semantics (precision only changes the rounding of the operands)
-def gnn_tc_linear_fwd(X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, precision, stream=None):
+def gnn_tc_linear_fwd(X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, precision, pack_ws=None, pack_ws_bytes=0,
+                      stream=None):
     gnn_linear_fwd(X, ldx, W, ldw, bias, M, N, K, act, Y, ldy)
 
 
-def gnn_tc_linear_dgrad(dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, precision, stream=None):
+def gnn_tc_linear_dgrad(dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, precision, pack_ws=None, pack_ws_bytes=0,
+                        stream=None):
     gnn_linear_dgrad(dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx)
 
 
@@ -350,11 +352,13 @@ def gnn_colsum_accum(dY, lddy, M, N, db, stream=None):
     _flat(db, N).add_(_mat(dY, M, N, lddy).sum(0))
 
 
-def gnn_tc_pna_post_fwd(x, A, scal, wpost, wts, bpost, bts, n, f, f_out, towers, act, O, precision, stream=None):
+def gnn_tc_pna_post_fwd(x, A, scal, wpost, wts, bpost, bts, n, f, f_out, towers, act, O, precision, pack_ws=None,
+                        pack_ws_bytes=0, stream=None):
     gnn_pna_post_fwd(x, A, scal, wpost, wts, bpost, bts, n, f, f_out, towers, act, O)
 
 
-def gnn_tc_pna_post_dgrad(dO, scal, wpost, wts, n, f, f_out, towers, dx, gA, precision, stream=None):
+def gnn_tc_pna_post_dgrad(dO, scal, wpost, wts, n, f, f_out, towers, dx, gA, precision, pack_ws=None,
+                          pack_ws_bytes=0, stream=None):
     gnn_pna_post_dgrad(dO, scal, wpost, wts, n, f, f_out, towers, dx, gA)
 
 

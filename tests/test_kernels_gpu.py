@@ -439,13 +439,15 @@ def test_tc_linear_fwd_dgrad_wgrad(precision, M, N, K, ldx, ldw, ldy):
     X, W, b = torch.randn(M, ldx, generator=g), torch.randn(N, ldw, generator=g) * 0.1, torch.randn(N, generator=g)
     for act in (0, 1):
         Y = torch.full((M, ldy), 7.0)
-        cpu, gpu = run_both("gnn_tc_linear_fwd", X, ldx, W, ldw, b, M, N, K, act, Y, ldy, precision)
-        close(gpu[-3], cpu[-3], tol, "tc linear fwd")
+        for ws in (None, torch.zeros(4 << 20, dtype=torch.uint8)):         # without / with the packed-weight path
+            cpu, gpu = run_both("gnn_tc_linear_fwd", X, ldx, W, ldw, b, M, N, K, act, Y, ldy, precision, ws, 4 << 20)
+            close(gpu[-5], cpu[-5], tol, "tc linear fwd")
     dY = torch.randn(M, ldy, generator=g)
     for acc in (0, 1):
         dX = torch.randn(M, ldx, generator=g)
-        cpu, gpu = run_both("gnn_tc_linear_dgrad", dY, ldy, W, ldw, M, N, K, acc, dX, ldx, precision)
-        close(gpu[-3], cpu[-3], tol, "tc linear dgrad")
+        for ws in (None, torch.zeros(4 << 20, dtype=torch.uint8)):
+            cpu, gpu = run_both("gnn_tc_linear_dgrad", dY, ldy, W, ldw, M, N, K, acc, dX, ldx, precision, ws, 4 << 20)
+            close(gpu[-5], cpu[-5], tol, "tc linear dgrad")
     dW = torch.randn(N, ldw, generator=g)
     cpu, gpu = run_both("gnn_tc_linear_wgrad", dY, ldy, X, ldx, M, N, K, dW, ldw, precision)
     close(gpu[-3], cpu[-3], 2 * tol, "tc linear wgrad")
@@ -470,16 +472,17 @@ def test_tc_pna_post_fwd_dgrad_wgrad(precision, n, F):
         for dev in ("cpu", DEV):
             base = wbuf.to(dev).clone()
             args = [x.to(dev), A.to(dev), scal.to(dev), base, wts, base[boff:], bts, n, F, Fo, T, act,
-                    torch.zeros(n, T * Fo).to(dev), precision]
+                    torch.zeros(n, T * Fo).to(dev), precision, torch.zeros(4 << 20, dtype=torch.uint8).to(dev), 4 << 20]
             R.gnn_tc_pna_post_fwd(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_post_fwd", *args, _lib.stream_ptr())
-            res.append(args[-2])
+            res.append(args[-4])
         close(res[1], res[0], tol, "tc post fwd")
     dO = torch.randn(n, T * Fo, generator=g)
     res = []
     for dev in ("cpu", DEV):
         base = wbuf.to(dev).clone()
         dx, gA = torch.ones(n, F).to(dev), torch.zeros(n, T * 4 * F).to(dev)
-        args = [dO.to(dev), scal.to(dev), base, wts, n, F, Fo, T, dx, gA, precision]
+        args = [dO.to(dev), scal.to(dev), base, wts, n, F, Fo, T, dx, gA, precision,
+                torch.zeros(4 << 20, dtype=torch.uint8).to(dev), 4 << 20]
         R.gnn_tc_pna_post_dgrad(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_post_dgrad", *args, _lib.stream_ptr())
         res.append((dx, gA))
     close(res[1][0], res[0][0], tol, "tc post dgrad dx")
