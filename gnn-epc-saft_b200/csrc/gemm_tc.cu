@@ -124,13 +124,24 @@ __device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major SWIZZLE_128B (the MN dimension is contiguous: 128-byte rows of 32 tf32 / 64 bf16 elements, atoms of
+// 8 K-rows x 128 B): leading byte offset = distance between MN groups, stride byte offset = distance between
+// groups of 8 K.
+// 16-bit types use layout type 2 (atoms of 8 K rows, 16-byte swizzle); tf32 must use SWIZZLE_128B_BASE32B (layout
+// type 1: atoms of 4 K rows x 128 B, 32-byte chunks XOR-ed with (k & 3)) - the only MN-major layout for tf32.
+__device__ __forceinline__ uint64_t smem_desc_sw128_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                       uint32_t layout_type) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout_type << 61);
+}
 __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
     return (uint32_t)row * ROW_BYTES + (uint32_t)((chunk ^ (row & 7)) << 4);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a/b format, K-major both, N>>3, M>>4
-__host__ __device__ inline uint32_t instr_desc(int mode, int n) {
+__host__ __device__ inline uint32_t instr_desc(int mode, int n, int mn_major) {
     uint32_t fmt = mode == MODE_TF32X3 ? 2u : 1u;   // TF32 = 2, BF16 = 1
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    uint32_t major = mn_major ? ((1u << 15) | (1u << 16)) : 0u;   // a_major / b_major: 0 = K, 1 = MN
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | major | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ operand functors
@@ -170,37 +181,6 @@ struct VTransposed {        // element (r, k) = p[k*ld + r]
     }
 };
 // [x | A_t] (node i, k in [0,5F)); group = tower.  F % 4 == 0.
-struct VCat5 {
-    static constexpr bool kTransposed = false;   // lanes of a producer warp run along K
-    const float* x;
-    const float* A;
-    int64_t n;
-    int F, towers, tower;
-    __device__ __forceinline__ void set_group(int g) { tower = g; }
-    __device__ __forceinline__ float4 get4(int64_t i, int64_t k) const {
-        if (i >= n || k >= 5 * (int64_t)F) return make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k < F) return ldg4(x + i * F + k);
-        return ldg4(A + (i * towers + tower) * (4 * (int64_t)F) + (k - F));
-    }
-};
-// transposed view of the same: row = column of [x | A_t] restricted to [col0, col0+rows), k = node
-struct VCat5T {
-    static constexpr bool kTransposed = true;   // lanes of a producer warp run along rows
-    const float* x;
-    const float* A;
-    int64_t n;
-    int F, towers, tower, col0, rows;
-    __device__ __forceinline__ void set_group(int g) { tower = g; }
-    __device__ __forceinline__ float elem(int64_t i, int c) const {
-        if (i >= n) return 0.f;
-        return c < F ? __ldg(x + i * F + c) : __ldg(A + (i * towers + tower) * (4 * (int64_t)F) + (c - F));
-    }
-    __device__ __forceinline__ float4 get4(int64_t r, int64_t k) const {
-        if (r >= rows) return make_float4(0.f, 0.f, 0.f, 0.f);
-        int c = col0 + (int)r;
-        return make_float4(elem(k, c), elem(k + 1, c), elem(k + 2, c), elem(k + 3, c));
-    }
-};
 // post forward weights.  Output features are tiled FoP at a time (FoP multiple of 16); tile j holds
 // rows [j*3*FoP, (j+1)*3*FoP) = three scaler groups of FoP rows: row r -> (tile, s, oo), o = tile*FoP + oo.
 //   k <  F : s == 0 ? Wpost_t[o, k] : 0          k >= F : Wpost_t[o, F + s*4F + (k-F)]
@@ -225,55 +205,6 @@ struct VPostWeight {
     }
 };
 // [dO_t | amp dO_t | att dO_t] as K-major A operand: (node i, k = s*F_out + o)
-struct VScaledGrad {
-    static constexpr bool kTransposed = false;   // lanes of a producer warp run along K
-    const float* dO;
-    const float* scal;
-    int64_t n;
-    int F_out, towers, tower;
-    __device__ __forceinline__ void set_group(int g) { tower = g; }
-    __device__ __forceinline__ float elem(int64_t i, int64_t k) const {
-        if (k >= 3 * (int64_t)F_out) return 0.f;
-        int s = (int)k / F_out, o = (int)k - s * F_out;
-        float v = __ldg(dO + i * ((int64_t)towers * F_out) + tower * F_out + o);
-        return s == 0 ? v : v * __ldg(scal + 2 * i + (s - 1));
-    }
-    __device__ __forceinline__ float4 get4(int64_t i, int64_t k) const {
-        if (i >= n || k >= 3 * (int64_t)F_out) return make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((F_out & 3) == 0) {                                    // four columns of one scaler group
-            const int s = (int)k / F_out, o = (int)k - s * F_out;
-            float4 v = ldg4(dO + i * ((int64_t)towers * F_out) + tower * F_out + o);
-            if (s == 0) return v;
-            const float f = __ldg(scal + 2 * i + (s - 1));
-            return make_float4(v.x * f, v.y * f, v.z * f, v.w * f);
-        }
-        return make_float4(elem(i, k), elem(i, k + 1), elem(i, k + 2), elem(i, k + 3));
-    }
-};
-// the same, transposed: row r = s*FoP + o, k = node (wgrad A operand)
-struct VScaledGradT {
-    static constexpr bool kTransposed = true;   // lanes of a producer warp run along rows
-    const float* dO;
-    const float* scal;
-    int64_t n;
-    int F_out, FoP, towers, tower;
-    __device__ __forceinline__ void set_group(int g) { tower = g; }
-    __device__ __forceinline__ float4 get4(int64_t r, int64_t k) const {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        int s = (int)r / FoP, o = (int)r - s * FoP;
-        if (s >= 3 || o >= F_out) return v;
-        float* pv = &v.x;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int64_t i = k + j;
-            if (i < n) {
-                float d = __ldg(dO + i * ((int64_t)towers * F_out) + tower * F_out + o);
-                pv[j] = s == 0 ? d : d * __ldg(scal + 2 * i + (s - 1));
-            }
-        }
-        return v;
-    }
-};
 // post dgrad B operand: row = r in [0,4F) (column of A_t), k = s*F_out + o -> Wpost_t[o, F + s*4F + r]
 struct VPostWeightT {
     static constexpr bool kTransposed = true;   // lanes of a producer warp run along rows
@@ -291,6 +222,43 @@ struct VPostWeightT {
         return make_float4(elem(r, k), elem(r, k + 1), elem(r, k + 2), elem(r, k + 3));
     }
 };
+
+// ------------------------------------------------------------------ activation operands: segmented rows
+// Every activation operand of the model is a row-major [node][column] matrix whose columns are a
+// concatenation of up to three slices of real tensors, optionally multiplied by a per-node degree scaler:
+//   [x | A_t]  (post forward),  [dO_t | amp dO_t | att dO_t]  (post backward),  plain X / dY (Linear).
+// A producer thread owns one 16-byte column chunk, resolves its segment once per k-block and then only walks
+// rows with pointer arithmetic.  Segment starts / widths are multiples of 4 columns.
+struct Seg {
+    const float* base;       // element (row 0, first column of the segment), before the group offset
+    int64_t ld;              // row stride (elements)
+    int64_t group_stride;    // added to base per group (tower)
+    int start, width;        // columns [start, start + width) of the operand
+    int scale;               // -1: none, 0: amplification, 1: attenuation  (scal[2*row + scale])
+};
+struct SegOperand {
+    Seg seg[3];
+    int nseg;
+    int64_t rows;            // valid rows (nodes)
+    const float* scal;       // [rows, 2]
+};
+struct SegRef {
+    const float* ptr;        // address of (row 0, col) or nullptr when the column is padding
+    int64_t ld;
+    int scale;
+};
+__device__ __forceinline__ SegRef seg_resolve(const SegOperand& op, int64_t col, int grp) {
+    SegRef r{nullptr, 0, -1};
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        if (s < op.nseg && col >= op.seg[s].start && col < op.seg[s].start + op.seg[s].width) {
+            r.ptr = op.seg[s].base + (int64_t)grp * op.seg[s].group_stride + (col - op.seg[s].start);
+            r.ld = op.seg[s].ld;
+            r.scale = op.seg[s].scale;
+        }
+    }
+    return r;
+}
 
 // ------------------------------------------------------------------ epilogues
 // emit4(m, n, N, v): four consecutive output columns n..n+3 of row m (n % 4 == 0); lanes of a warp
@@ -495,6 +463,105 @@ __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_
     }
 }
 
+// K-major A tile from a segmented operand: 128 rows (nodes m0..) x one k-block of columns.  Thread p owns the
+// 16-byte chunk c = p & 7 of rows r0 + 16 i: every load is a 128-bit coalesced access (8 lanes = 128 contiguous
+// bytes of one row), all eight are issued before the first conversion, smem offsets are compile-time strides.
+template <int MODE>
+__device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes,
+                                              int64_t m0, int64_t kbase, int64_t k_end, int p) {
+    constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
+    const int c = p & 7, r0 = p >> 3;
+    const int64_t k = kbase + c * EPC;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    SegRef s0 = k < k_end ? seg_resolve(op, k, grp) : SegRef{nullptr, 0, -1};
+    SegRef s1 = (MODE == MODE_BF16 && k + 4 < k_end) ? seg_resolve(op, k + 4, grp) : SegRef{nullptr, 0, -1};
+    const int64_t row0 = m0 + r0;
+    const uint32_t off0 = (uint32_t)r0 * ROW_BYTES + (uint32_t)((c ^ (r0 & 7)) << 4);   // (r0 + 16 i) & 7 == r0 & 7
+    float4 v[8], w[MODE == MODE_BF16 ? 8 : 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t row = row0 + 16 * i;
+        v[i] = (s0.ptr != nullptr && row < op.rows) ? ldg4(s0.ptr + row * s0.ld) : zero;
+        if (MODE == MODE_BF16) w[i] = (s1.ptr != nullptr && row < op.rows) ? ldg4(s1.ptr + row * s1.ld) : zero;
+    }
+    if (s0.scale >= 0 || (MODE == MODE_BF16 && s1.scale >= 0)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t row = row0 + 16 * i;
+            if (row < op.rows) {
+                if (s0.scale >= 0) {
+                    const float f = __ldg(op.scal + 2 * row + s0.scale);
+                    v[i] = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
+                }
+                if (MODE == MODE_BF16 && s1.scale >= 0) {
+                    const float f = __ldg(op.scal + 2 * row + s1.scale);
+                    w[i] = make_float4(w[i].x * f, w[i].y * f, w[i].z * f, w[i].w * f);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t off = off0 + (uint32_t)i * (16 * ROW_BYTES);
+        if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, off, v[i]);
+        else put_chunk_bf16(tile, off, v[i], w[MODE == MODE_BF16 ? i : 0]);
+    }
+}
+
+// MN-major tile from a segmented operand (weight gradients: the reduction index is the node).
+// R = MN extent of the tile in {32, 64, 128, 256}, KB K-rows (nodes kbase..).  Layout: [K group][MN group of
+// 128 B][KR rows x 128 B], KR = 4 K rows per atom for tf32 (SWIZZLE_128B_BASE32B: 32-byte chunks XOR (k & 3)),
+// 8 for bf16 (16-byte chunks XOR (k & 7)).  Thread p owns one 16-byte MN chunk and walks nodes: plain coalesced
+// vector copies, no transposition.
+template <int MODE>
+__device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes, int R,
+                                               int64_t mn0, int64_t kbase, int64_t k_end, int p) {
+    constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
+    constexpr int KB = MODE == MODE_TF32X3 ? 32 : 64;
+    constexpr int KR = MODE == MODE_TF32X3 ? 4 : 8;
+    constexpr uint32_t ATOM = KR * 128;
+    const int cpr = R / EPC;                                     // chunks per K row: power of two, 4..64
+    const int ch = p & (cpr - 1), kk0 = p / cpr, step = PROD_GROUP_THREADS / cpr;
+    const uint32_t kgs = (uint32_t)(cpr >> 3) * ATOM;            // bytes between K groups
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t col = mn0 + (int64_t)ch * EPC;
+    const SegRef s0 = seg_resolve(op, col, grp);
+    const SegRef s1 = MODE == MODE_BF16 ? seg_resolve(op, col + 4, grp) : SegRef{nullptr, 0, -1};
+    const int mg = ch >> 3, c8 = ch & 7;
+    const int64_t lim = k_end < op.rows ? k_end : op.rows;
+    for (int kb0 = kk0; kb0 < KB; kb0 += 8 * step) {
+        float4 v[8], w[MODE == MODE_BF16 ? 8 : 1];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kk = kb0 + i * step;
+            const int64_t k = kbase + kk;
+            const bool ok = kk < KB && k < lim;
+            v[i] = (ok && s0.ptr != nullptr) ? ldg4(s0.ptr + k * s0.ld) : zero;
+            if (MODE == MODE_BF16) w[i] = (ok && s1.ptr != nullptr) ? ldg4(s1.ptr + k * s1.ld) : zero;
+            if (ok && s0.scale >= 0) {
+                const float f = __ldg(op.scal + 2 * k + s0.scale);
+                v[i] = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
+            }
+            if (MODE == MODE_BF16 && ok && s1.scale >= 0) {
+                const float f = __ldg(op.scal + 2 * k + s1.scale);
+                w[i] = make_float4(w[i].x * f, w[i].y * f, w[i].z * f, w[i].w * f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int kk = kb0 + i * step;
+            if (kk < KB) {
+                const int kr = kk & (KR - 1);
+                const uint32_t swz = MODE == MODE_TF32X3 ? (uint32_t)((((c8 >> 1) ^ kr) << 5) | ((c8 & 1) << 4))
+                                                         : (uint32_t)((c8 ^ kr) << 4);
+                const uint32_t off = (uint32_t)(kk / KR) * kgs + (uint32_t)mg * ATOM + (uint32_t)kr * 128u + swz;
+                if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, off, v[i]);
+                else put_chunk_bf16(tile, off, v[i], w[MODE == MODE_BF16 ? i : 0]);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 // Persistent, warp-specialised: work item = (m tile, n tile, group, k split).
 //   producers (4 groups x 4 warps): global -> registers -> (tf32 hi/lo | bf16) -> SWIZZLE_128B smem ring
@@ -517,9 +584,9 @@ pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t*
     produce_tile<MODE>(bl, tile, b_plane, BN, (int64_t)nt * BN, (int64_t)kb * KB_ELEMS, K, threadIdx.x);
 }
 
-template <int MODE, bool PACKED, class AL, class BL, class EP>
+template <int MODE, bool PACKED, bool MN_MAJOR, class BL, class EP>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tc_kernel(const AL al0, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b) {
+gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
@@ -627,7 +694,7 @@ gemm_tc_kernel(const AL al0, const BL bl0, const EP ep0, const Geom g, const uin
         }
     } else if (warp == MMA_WARP) {
         // =============================== MMA issuer ===============================
-        const uint32_t idesc = instr_desc(MODE, BN);
+        const uint32_t idesc = instr_desc(MODE, BN, MN_MAJOR ? 1 : 0);
         uint32_t it = 0, t = 0;
         for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) {
             int64_t m0, k_begin, k_end;
@@ -646,15 +713,33 @@ gemm_tc_kernel(const AL al0, const BL bl0, const EP ep0, const Geom g, const uin
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + a_plane;
                     const uint32_t b_hi = a_hi + PARTS * a_plane, b_lo = b_hi + b_plane;
 #pragma unroll
-                    for (int j = 0; j < CHUNKS / 2; ++j) {       // one MMA consumes 32 bytes of K
-                        const uint32_t koff = j * 32;
+                    for (int j = 0; j < CHUNKS / 2; ++j) {       // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
                         const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
-                        if (MODE == MODE_TF32X3) {
-                            umma<MODE>(tmem_d, smem_desc_sw128(a_lo + koff), smem_desc_sw128(b_hi + koff), idesc, first);
-                            umma<MODE>(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_lo + koff), idesc, 1u);
-                            umma<MODE>(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc, 1u);
+                        uint64_t dah, dal, dbh, dbl;
+                        if (MN_MAJOR) {
+                            // one MMA spans two K groups (tf32: 2 x 4 rows, bf16: 2 x 8 rows) linked by the stride offset
+                            constexpr uint32_t ATOM = MODE == MODE_TF32X3 ? 512 : 1024;
+                            constexpr uint32_t LT = MODE == MODE_TF32X3 ? 1 : 2;
+                            const uint32_t a_kgs = (BM * (MODE == MODE_TF32X3 ? 4 : 2) / 128) * ATOM;
+                            const uint32_t b_kgs = ((uint32_t)BN * (MODE == MODE_TF32X3 ? 4 : 2) / 128) * ATOM;
+                            const uint32_t ao = j * 2 * a_kgs, bo = j * 2 * b_kgs;
+                            dah = smem_desc_sw128_mn(a_hi + ao, ATOM, a_kgs, LT);
+                            dal = smem_desc_sw128_mn(a_lo + ao, ATOM, a_kgs, LT);
+                            dbh = smem_desc_sw128_mn(b_hi + bo, ATOM, b_kgs, LT);
+                            dbl = smem_desc_sw128_mn(b_lo + bo, ATOM, b_kgs, LT);
                         } else {
-                            umma<MODE>(tmem_d, smem_desc_sw128(a_hi + koff), smem_desc_sw128(b_hi + koff), idesc, first);
+                            const uint32_t koff = j * 32;
+                            dah = smem_desc_sw128(a_hi + koff);
+                            dal = smem_desc_sw128(a_lo + koff);
+                            dbh = smem_desc_sw128(b_hi + koff);
+                            dbl = smem_desc_sw128(b_lo + koff);
+                        }
+                        if (MODE == MODE_TF32X3) {
+                            umma<MODE>(tmem_d, dal, dbh, idesc, first);
+                            umma<MODE>(tmem_d, dah, dbl, idesc, 1u);
+                            umma<MODE>(tmem_d, dah, dbh, idesc, 1u);
+                        } else {
+                            umma<MODE>(tmem_d, dah, dbh, idesc, first);
                         }
                     }
                     umma_commit(&empty_bar[s]);                       // smem stage reusable once these MMAs retire
@@ -676,10 +761,8 @@ gemm_tc_kernel(const AL al0, const BL bl0, const EP ep0, const Geom g, const uin
             int64_t m0, k_begin, k_end;
             int n0, grp;
             decode(item, m0, n0, grp, k_begin, k_end);
-            AL al = al0;
             BL bl = bl0;
-            al.set_group(grp);
-            bl.set_group(grp);
+            if constexpr (!MN_MAJOR) bl.set_group(grp);
             const int num_kb = (int)((k_end - k_begin + KB_ELEMS - 1) / KB_ELEMS);
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 if ((int)(it % NS) != pg) continue;                // group pg owns ring stage pg (see below)
@@ -687,7 +770,7 @@ gemm_tc_kernel(const AL al0, const BL bl0, const EP ep0, const Geom g, const uin
                 if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
                 uint8_t* stage = smem + (size_t)s * stage_bytes;
                 const int64_t kbase = k_begin + (int64_t)kb * KB_ELEMS;
-                if (PACKED) {
+                if constexpr (PACKED) {
                     // the weight operand was pre-packed as the smem image: one TMA bulk copy per k-block
                     if (p == 0) {
                         const uint32_t bytes = PARTS * b_plane;
@@ -695,9 +778,12 @@ gemm_tc_kernel(const AL al0, const BL bl0, const EP ep0, const Geom g, const uin
                         mbar_expect_tx(&full_bar[s], bytes);
                         bulk_g2s(stage + PARTS * a_plane, packed_b + tile_idx * bytes, bytes, &full_bar[s]);
                     }
-                    produce_tile<MODE>(al, stage, a_plane, BM, m0, kbase, k_end, p);
+                    produce_a_seg<MODE>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
+                } else if constexpr (MN_MAJOR) {
+                    produce_mn_seg<MODE>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p);
+                    produce_mn_seg<MODE>(bl, grp, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
                 } else {
-                    produce_tile<MODE>(al, stage, a_plane, BM, m0, kbase, k_end, p);
+                    produce_a_seg<MODE>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
                     produce_tile<MODE>(bl, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
                 }
                 fence_async_smem();                                 // generic-proxy writes -> async (tensor core) proxy
@@ -713,9 +799,10 @@ gemm_tc_kernel(const AL al0, const BL bl0, const EP ep0, const Geom g, const uin
 // ------------------------------------------------------------------ host side
 static const size_t kSmemLimit = 232448;     // 227 KB opt-in maximum per CTA
 
-template <int MODE, class AL, class BL, class EP>
-static int launch(AL al, BL bl, EP ep, int64_t M, int N, int BN, int64_t K, int64_t k_chunk, int splits, int groups,
-                  cudaStream_t st, void* pack_ws = nullptr, int64_t pack_ws_bytes = 0) {
+// BL: K-major weight functor (packed through pack_ws when possible) or, for MN_MAJOR, a SegOperand
+template <int MODE, bool MN_MAJOR = false, class BL, class EP>
+static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN, int64_t K, int64_t k_chunk, int splits,
+                  int groups, cudaStream_t st, void* pack_ws = nullptr, int64_t pack_ws_bytes = 0) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     if (BN % 16 != 0 || BN < 16 || BN > 256) return GNN_ERR_UNSUPPORTED;
     constexpr int parts = MODE == MODE_TF32X3 ? 2 : 1;
@@ -737,24 +824,32 @@ static int launch(AL al, BL bl, EP ep, int64_t M, int N, int BN, int64_t K, int6
     const size_t smem = (size_t)stages * stage_bytes + fixed;
     int64_t grid = g.num_items < gnn_sm_count() ? g.num_items : gnn_sm_count();
 
-    // weights (B) packed once per call when a workspace is given and the M loop re-uses them
-    const int num_kb = (int)gnn_ceil_div(K, kb_elems);
-    const int64_t pack_bytes = (int64_t)groups * g.n_tiles * num_kb * parts * BN * ROW_BYTES;
-    const bool packed = pack_ws != nullptr && splits == 1 && g.m_tiles >= 2 && pack_bytes <= pack_ws_bytes &&
-                        (reinterpret_cast<uintptr_t>(pack_ws) & 127) == 0;
-    if (packed) {
-        dim3 pgrid((unsigned)num_kb, (unsigned)g.n_tiles, (unsigned)groups);
-        pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
-                                                                      reinterpret_cast<uint8_t*>(pack_ws));
-        auto kern = gemm_tc_kernel<MODE, true, AL, BL, EP>;
+    if constexpr (MN_MAJOR) {
+        if ((BN & (BN - 1)) != 0 || BN < (MODE == MODE_TF32X3 ? 32 : 64)) return GNN_ERR_UNSUPPORTED;   // whole 128-byte groups
+        auto kern = gemm_tc_kernel<MODE, false, true, BL, EP>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)grid, THREADS, smem, st>>>(al, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws));
+        kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, nullptr);
     } else {
-        auto kern = gemm_tc_kernel<MODE, false, AL, BL, EP>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)grid, THREADS, smem, st>>>(al, bl, ep, g, nullptr);
+        // weights (B) are packed once per call when a workspace is given and the M loop re-uses them
+        const int num_kb = (int)gnn_ceil_div(K, kb_elems);
+        const int64_t pack_bytes = (int64_t)groups * g.n_tiles * num_kb * parts * BN * ROW_BYTES;
+        const bool packed = pack_ws != nullptr && splits == 1 && g.m_tiles >= 2 && pack_bytes <= pack_ws_bytes &&
+                            (reinterpret_cast<uintptr_t>(pack_ws) & 127) == 0;
+        if (packed) {
+            dim3 pgrid((unsigned)num_kb, (unsigned)g.n_tiles, (unsigned)groups);
+            pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
+                                                                          reinterpret_cast<uint8_t*>(pack_ws));
+            auto kern = gemm_tc_kernel<MODE, true, false, BL, EP>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws));
+        } else {
+            auto kern = gemm_tc_kernel<MODE, false, false, BL, EP>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, nullptr);
+        }
     }
     return gnn_launch_status();
 }
@@ -762,6 +857,11 @@ static int launch(AL al, BL bl, EP ep, int64_t M, int N, int BN, int64_t K, int6
 static int pick_bn(int n) {
     int bn = (n + 15) / 16 * 16;
     return bn > 256 ? 256 : bn;
+}
+static int pick_bn_mn(int n, int mode) {          // MN-major tiles: (32 tf32 only) / 64 / 128 / 256 columns
+    int bn = mode == MODE_TF32X3 ? 32 : 64;
+    while (bn < n && bn < 256) bn <<= 1;
+    return bn;
 }
 static int is_vec(const void* p, int64_t ld) { return (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0); }
 
@@ -777,6 +877,16 @@ static void splitk(int64_t K, int64_t tiles, int kb_elems, int64_t& k_chunk, int
     splits = (int)gnn_ceil_div(K, k_chunk);
 }
 
+// one plain row-major matrix as a segmented operand
+static SegOperand seg_plain(const float* p, int64_t ld, int64_t rows, int cols) {
+    SegOperand op{};
+    op.seg[0] = Seg{p, ld, 0, 0, cols, -1};
+    op.nseg = 1;
+    op.rows = rows;
+    op.scal = nullptr;
+    return op;
+}
+
 }  // namespace tc
 
 using namespace tc;
@@ -788,15 +898,20 @@ using namespace tc;
         else return GNN_ERR_BAD_ARG;                           \
     } while (0)
 
+// The vectorised producers need 16-byte aligned rows: leading dimensions and column offsets % 4 == 0.
+#define REQUIRE_VEC(p, ld) do { if (!is_vec((p), (ld))) return GNN_ERR_UNSUPPORTED; } while (0)
+
 extern "C" int gnn_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias, int64_t M,
                                  int N, int K, int act, float* Y, int64_t ldy, int precision, void* pack_ws,
                                  int64_t pack_ws_bytes, void* stream) {
     if (M < 0 || N < 1 || K < 1) return GNN_ERR_BAD_ARG;
-    VRowMajor al{X, ldx, M, K, 0, is_vec(X, ldx)};
+    REQUIRE_VEC(X, ldx);
+    if (K % 4 != 0) return GNN_ERR_UNSUPPORTED;
+    SegOperand aop = seg_plain(X, ldx, M, K);
     VRowMajor bl{W, ldw, N, K, 0, is_vec(W, ldw)};
     EStore ep{Y, ldy, 0, bias, 0, act, 0, is_vec(Y, ldy) && (bias == nullptr || is_vec(bias, 0))};
     const int BN = pick_bn(N);
-    DISPATCH_MODE(precision, return (launch<MODE>(al, bl, ep, M, N, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
+    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, M, N, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
                                                   pack_ws_bytes)));
 }
 
@@ -804,27 +919,32 @@ extern "C" int gnn_tc_linear_dgrad(const float* dY, int64_t lddy, const float* W
                                    int accumulate, float* dX, int64_t lddx, int precision, void* pack_ws,
                                    int64_t pack_ws_bytes, void* stream) {
     if (M < 0 || N < 1 || K < 1) return GNN_ERR_BAD_ARG;
-    VRowMajor al{dY, lddy, M, N, 0, is_vec(dY, lddy)};     // (m, n) reduction over n
+    REQUIRE_VEC(dY, lddy);
+    if (N % 4 != 0) return GNN_ERR_UNSUPPORTED;
+    SegOperand aop = seg_plain(dY, lddy, M, N);            // (m, n): reduction over n
     VTransposed bl{W, ldw, K, N, 0};                       // row kk, k = n -> W[n, kk]
     EStore ep{dX, lddx, 0, nullptr, 0, 0, accumulate, is_vec(dX, lddx)};
     const int BN = pick_bn(K);
-    DISPATCH_MODE(precision, return (launch<MODE>(al, bl, ep, M, K, BN, N, N, 1, 1, gnn_stream(stream), pack_ws,
+    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, M, K, BN, N, N, 1, 1, gnn_stream(stream), pack_ws,
                                                   pack_ws_bytes)));
 }
 
 extern "C" int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t M, int N, int K,
                                    float* dW, int64_t lddw, int precision, void* stream) {
     if (M < 0 || N < 1 || K < 1) return GNN_ERR_BAD_ARG;
-    VTransposed al{dY, lddy, N, M, 0};                     // row o, k = i -> dY[i, o]
-    VTransposed bl{X, ldx, K, M, 0};                       // row kk, k = i -> X[i, kk]
+    REQUIRE_VEC(dY, lddy);
+    REQUIRE_VEC(X, ldx);
+    if (N % 4 != 0 || K % 4 != 0) return GNN_ERR_UNSUPPORTED;
+    SegOperand aop = seg_plain(dY, lddy, M, N);            // (node i, o) -> dY[i, o]
+    SegOperand bop = seg_plain(X, ldx, M, K);              // (node i, kk) -> X[i, kk]
     EAtomic ep{dW, lddw, 0, is_vec(dW, lddw)};
-    const int BN = pick_bn(K);
-    const int64_t tiles = gnn_ceil_div(N, BM) * gnn_ceil_div(K, BN);
     int64_t k_chunk;
     int splits;
     DISPATCH_MODE(precision, {
+        const int BN = pick_bn_mn(K, MODE);
+        const int64_t tiles = gnn_ceil_div(N, BM) * gnn_ceil_div(K, BN);
         splitk(M, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
-        return (launch<MODE>(al, bl, ep, N, K, BN, M, k_chunk, splits, 1, gnn_stream(stream)));
+        return (launch<MODE, true>(aop, bop, ep, N, K, BN, M, k_chunk, splits, 1, gnn_stream(stream)));
     });
 }
 
@@ -857,19 +977,40 @@ extern "C" int gnn_colsum_accum(const float* dY, int64_t lddy, int64_t M, int N,
 }
 
 // ------------------------------------------------------------------ PNA post stage on tensor cores
+static SegOperand seg_cat5(const float* x, const float* A, int64_t n, int F, int towers) {   // [x | A_t], group = tower
+    SegOperand op{};
+    op.seg[0] = Seg{x, F, 0, 0, F, -1};
+    op.seg[1] = Seg{A, (int64_t)towers * 4 * F, 4 * (int64_t)F, F, 4 * F, -1};
+    op.nseg = 2;
+    op.rows = n;
+    op.scal = nullptr;
+    return op;
+}
+// [dO_t | amp dO_t | att dO_t], group = tower; the three groups start `pitch` columns apart (>= F_out)
+static SegOperand seg_scaled_grad(const float* dO, const float* scal, int64_t n, int F_out, int towers, int pitch) {
+    SegOperand op{};
+    for (int s = 0; s < 3; ++s) op.seg[s] = Seg{dO, (int64_t)towers * F_out, F_out, s * pitch, F_out, s - 1};
+    op.nseg = 3;
+    op.rows = n;
+    op.scal = scal;
+    return op;
+}
+
 extern "C" int gnn_tc_pna_post_fwd(const float* x, const float* A, const float* scal, const float* wpost,
                                    int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
                                    int64_t n, int F, int F_out, int towers, int act, float* O, int precision,
                                    void* pack_ws, int64_t pack_ws_bytes, void* stream) {
     if (n < 0 || F < 4 || (F & 3) || F_out < 1 || towers < 1) return GNN_ERR_BAD_ARG;
+    REQUIRE_VEC(x, F);
+    REQUIRE_VEC(A, 4 * (int64_t)F);
     int FoP = (F_out + 15) / 16 * 16;      // output-feature tile: three scaler groups of FoP columns per CTA
     if (FoP > 64) FoP = 64;
     const int tiles = (F_out + FoP - 1) / FoP;
-    VCat5 al{x, A, n, F, towers, 0};
+    SegOperand aop = seg_cat5(x, A, n, F, towers);
     VPostWeight bl{wpost, wpost_tower_stride, F, F_out, FoP};
     EPostCombine ep{O, scal, bpost, bpost_tower_stride, F_out, FoP, towers, 0, act,
                     (F_out % 4 == 0) && is_vec(O, 0) && is_vec(bpost, bpost_tower_stride)};
-    DISPATCH_MODE(precision, return (launch<MODE>(al, bl, ep, n, tiles * 3 * FoP, 3 * FoP, 5 * (int64_t)F,
+    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, tiles * 3 * FoP, 3 * FoP, 5 * (int64_t)F,
                                                   5 * (int64_t)F, 1, towers, gnn_stream(stream), pack_ws, pack_ws_bytes)));
 }
 
@@ -877,15 +1018,17 @@ extern "C" int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const f
                                      int64_t n, int F, int F_out, int towers, float* dx, float* gA, int precision,
                                      void* pack_ws, int64_t pack_ws_bytes, void* stream) {
     if (n < 0 || F < 4 || (F & 3) || F_out < 1 || towers < 1) return GNN_ERR_BAD_ARG;
+    if (F_out % 4 != 0) return GNN_ERR_UNSUPPORTED;
+    REQUIRE_VEC(dO, (int64_t)towers * F_out);
     cudaStream_t st = gnn_stream(stream);
     // gA[:, t, :] = [dO_t | amp dO_t | att dO_t] . Wslices_t          (M = n, N = 4F, K = 3 F_out)
     {
-        VScaledGrad al{dO, scal, n, F_out, towers, 0};
+        SegOperand aop = seg_scaled_grad(dO, scal, n, F_out, towers, F_out);
         VPostWeightT bl{wpost, wpost_tower_stride, F, F_out};
         EStore ep{gA, (int64_t)towers * 4 * F, 4 * (int64_t)F, nullptr, 0, 0, 0, is_vec(gA, 0)};
         const int BN = pick_bn(4 * F);
         int rc;
-        DISPATCH_MODE(precision, rc = (launch<MODE>(al, bl, ep, n, 4 * F, BN, 3 * (int64_t)F_out, 3 * (int64_t)F_out, 1,
+        DISPATCH_MODE(precision, rc = (launch<MODE>(aop, bl, ep, n, 4 * F, BN, 3 * (int64_t)F_out, 3 * (int64_t)F_out, 1,
                                                     towers, st, pack_ws, pack_ws_bytes)));
         if (rc) return rc;
     }
@@ -893,12 +1036,12 @@ extern "C" int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const f
     for (int t = 0; t < towers; ++t) {
         const float* d = dO + t * F_out;
         const float* w = wpost + t * wpost_tower_stride;
-        VRowMajor al{d, (int64_t)towers * F_out, n, F_out, 0, is_vec(d, (int64_t)towers * F_out)};
+        SegOperand aop = seg_plain(d, (int64_t)towers * F_out, n, F_out);
         VTransposed bl{w, 13 * (int64_t)F, F, F_out, 0};
         EStore ep{dx, F, 0, nullptr, 0, 0, 1, is_vec(dx, F)};
         const int BN = pick_bn(F);
         int rc;
-        DISPATCH_MODE(precision, rc = (launch<MODE>(al, bl, ep, n, F, BN, (int64_t)F_out, (int64_t)F_out, 1, 1, st,
+        DISPATCH_MODE(precision, rc = (launch<MODE>(aop, bl, ep, n, F, BN, (int64_t)F_out, (int64_t)F_out, 1, 1, st,
                                                     pack_ws, pack_ws_bytes)));
         if (rc) return rc;
     }
@@ -910,36 +1053,43 @@ extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const floa
                                      float* dbpost, int64_t bpost_tower_stride, int precision, void* stream) {
     if (n < 0 || F < 4 || (F & 3) || F_out < 1 || towers < 1) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
+    if (F_out % 4 != 0) return GNN_ERR_UNSUPPORTED;
+    REQUIRE_VEC(dO, (int64_t)towers * F_out);
+    REQUIRE_VEC(x, F);
+    REQUIRE_VEC(A, 4 * (int64_t)F);
     cudaStream_t st = gnn_stream(stream);
     const int FoP = (F_out + 15) / 16 * 16;
-    // (1) aggregate part: D[(s,o), r] = sum_i scale_s(i) dO[i,o] A_t[i,r]   (M = 3 FoP, N = 4F, K = n)
+    // (1) aggregate part: D[(s,o), r] = sum_i scale_s(i) dO[i,o] A_t[i,r]   (M = 3 FoP, N = 4F, K = n), MN-major
     {
-        VScaledGradT al{dO, scal, n, F_out, FoP, towers, 0};
-        VCat5T bl{x, A, n, F, towers, 0, F, 4 * F};
+        SegOperand aop = seg_scaled_grad(dO, scal, n, F_out, towers, FoP);
+        SegOperand bop{};
+        bop.seg[0] = Seg{A, (int64_t)towers * 4 * F, 4 * (int64_t)F, 0, 4 * F, -1};
+        bop.nseg = 1;
+        bop.rows = n;
         EPostWgrad ep{dwpost, wpost_tower_stride, F, F_out, FoP, is_vec(dwpost, wpost_tower_stride)};
-        const int BN = pick_bn(4 * F);
-        const int64_t tiles = gnn_ceil_div(4 * F, BN) * gnn_ceil_div(3 * FoP, BM) * towers;
         int64_t k_chunk;
         int splits, rc;
         DISPATCH_MODE(precision, {
+            const int BN = pick_bn_mn(4 * F, MODE);
+            const int64_t tiles = gnn_ceil_div(4 * F, BN) * gnn_ceil_div(3 * FoP, BM) * towers;
             splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
-            rc = (launch<MODE>(al, bl, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st));
+            rc = (launch<MODE, true>(aop, bop, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st));
         });
         if (rc) return rc;
     }
     // (2) x part: dWpost_t[o, :F] += dO_t^T x
     for (int t = 0; t < towers; ++t) {
         const float* d = dO + t * F_out;
-        VTransposed al{d, (int64_t)towers * F_out, F_out, n, 0};
-        VTransposed bl{x, F, F, n, 0};
+        SegOperand aop = seg_plain(d, (int64_t)towers * F_out, n, F_out);
+        SegOperand bop = seg_plain(x, F, n, F);
         EAtomic ep{dwpost + t * wpost_tower_stride, 13 * (int64_t)F, 0, is_vec(dwpost + t * wpost_tower_stride, F)};
-        const int BN = pick_bn(F);
-        const int64_t tiles = gnn_ceil_div(F, BN);
         int64_t k_chunk;
         int splits, rc;
         DISPATCH_MODE(precision, {
+            const int BN = pick_bn_mn(F, MODE);
+            const int64_t tiles = gnn_ceil_div(F, BN);
             splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
-            rc = (launch<MODE>(al, bl, ep, F_out, F, BN, n, k_chunk, splits, 1, st));
+            rc = (launch<MODE, true>(aop, bop, ep, F_out, F, BN, n, k_chunk, splits, 1, st));
         });
         if (rc) return rc;
         rc = gnn_colsum_accum(d, (int64_t)towers * F_out, n, F_out, dbpost + t * bpost_tower_stride, stream);

@@ -147,8 +147,13 @@ def _c(name, *args):
 MATMUL_MODES = {"simt": -1, "tf32x3": 0, "bf16": 2}
 
 
+def _al(t, *dims):
+    """128-bit accessible: 16-byte aligned base and all given dimensions multiples of 4."""
+    return (t.data_ptr() & 15) == 0 and all((d & 3) == 0 for d in dims)
+
+
 def _lin_fwd(mm, X, ldx, W, ldw, bias, M, N, K, act, Y, ldy):
-    if mm < 0:
+    if mm < 0 or not _al(X, ldx, K):
         _c("gnn_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy)
     else:
         ws = _pack_ws(Y.device)
@@ -156,7 +161,7 @@ def _lin_fwd(mm, X, ldx, W, ldw, bias, M, N, K, act, Y, ldy):
 
 
 def _lin_dgrad(mm, dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx):
-    if mm < 0:
+    if mm < 0 or not _al(dY, lddy, N):
         _c("gnn_linear_dgrad", dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx)
     else:
         ws = _pack_ws(dX.device)
@@ -164,7 +169,7 @@ def _lin_dgrad(mm, dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx):
 
 
 def _lin_wgrad(mm, dY, lddy, X, ldx, M, N, K, dW, lddw, db):
-    if mm < 0:
+    if mm < 0 or not (_al(dY, lddy, N) and _al(X, ldx, K)):
         _c("gnn_linear_wgrad", dY, lddy, X, ldx, M, N, K, dW, lddw, db)
     else:
         _c("gnn_tc_linear_wgrad", dY, lddy, X, ldx, M, N, K, dW, lddw, mm)

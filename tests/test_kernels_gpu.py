@@ -429,10 +429,10 @@ TC_TOL = {0: 1e-5, 2: 2e-2}
 
 
 @pytest.mark.parametrize("precision", [0, 2])
-@pytest.mark.parametrize("M,N,K,ldx,ldw,ldy", [(1000, 64, 64, 64, 192, 256), (1, 5, 16, 16, 16, 5),
-                                               (333, 32, 832, 832, 832, 64), (129, 256, 64, 70, 64, 256),
-                                               (4096, 16, 32, 32, 32, 16), (77, 10, 20, 20, 20, 10),
-                                               (5000, 64, 100, 100, 100, 64)])
+@pytest.mark.parametrize("M,N,K,ldx,ldw,ldy", [(1000, 64, 64, 64, 192, 256), (1, 8, 16, 16, 16, 8),
+                                               (333, 32, 832, 832, 832, 64), (129, 256, 64, 72, 64, 256),
+                                               (4096, 16, 32, 32, 32, 16), (77, 12, 20, 20, 20, 12),
+                                               (5000, 64, 100, 100, 100, 64), (20000, 64, 256, 256, 256, 64)])
 def test_tc_linear_fwd_dgrad_wgrad(precision, M, N, K, ldx, ldw, ldy):
     tol = TC_TOL[precision]
     g = torch.Generator().manual_seed(M + N + K)
@@ -494,3 +494,18 @@ def test_tc_pna_post_fwd_dgrad_wgrad(precision, n, F):
         R.gnn_tc_pna_post_wgrad(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_post_wgrad", *args, _lib.stream_ptr())
         res.append(gbase)
     close(res[1], res[0], 2 * tol, "tc post wgrad")
+
+
+def test_tc_rejects_unaligned_operands():
+    """The tensor-core producers use 128-bit accesses: shapes that are not 4-column aligned are refused
+    (the host falls back to the SIMT kernels for them), never silently mis-read."""
+    lib = _lib.load()
+    X = torch.zeros(64, 70, device=DEV)
+    W = torch.zeros(8, 70, device=DEV)
+    Y = torch.zeros(64, 8, device=DEV)
+    rc = lib.gnn_tc_linear_fwd(X.data_ptr(), 70, W.data_ptr(), 70, None, 64, 8, 70, 0, Y.data_ptr(), 8, 0, None, 0,
+                               _lib.stream_ptr())
+    assert rc == -3
+    rc = lib.gnn_tc_linear_dgrad(Y.data_ptr(), 5, W.data_ptr(), 70, 64, 5, 70, 0, X.data_ptr(), 70, 0, None, 0,
+                                 _lib.stream_ptr())
+    assert rc == -3
