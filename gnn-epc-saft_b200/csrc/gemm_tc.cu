@@ -223,6 +223,47 @@ struct VPostWeightT {
     }
 };
 
+// projection weights of PNAConv.pre_nns[t][0] (first two thirds): row n = part*C + t*F + f (part 0 = destination,
+// 1 = source), k in [0,F)  ->  Wpre_t[f, part*F + k]
+struct VProjWeight {
+    static constexpr bool kTransposed = false;
+    const float* w;
+    int64_t tower_stride;
+    int F, towers;
+    __device__ __forceinline__ void set_group(int) {}
+    __device__ __forceinline__ float4 get4(int64_t r, int64_t k) const {
+        const int C = towers * F;
+        if (r >= 2 * C || k >= F) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const int part = (int)r / C, rem = (int)r - part * C, t = rem / F, f = rem - t * F;
+        return ldg4(w + (int64_t)t * tower_stride + (int64_t)f * 3 * F + part * F + k);
+    }
+};
+// B operand of the fused dx GEMM: row kk in [0,F), k over [dP (2C) | dO (T*F_out)]:
+//   k <  2C : (part,t,f) -> Wpre_t[f, part*F + kk]        k >= 2C : (t,o) -> Wpost_t[o, kk]
+struct VDxWeight {
+    static constexpr bool kTransposed = true;
+    const float* wpre;
+    const float* wpost;
+    int64_t wpre_tower_stride, wpost_tower_stride;
+    int F, F_out, towers;
+    __device__ __forceinline__ void set_group(int) {}
+    __device__ __forceinline__ float elem(int64_t kk, int64_t k) const {
+        const int C = towers * F;
+        if (k < 2 * C) {
+            const int part = (int)k / C, rem = (int)k - part * C, t = rem / F, f = rem - t * F;
+            return __ldg(wpre + (int64_t)t * wpre_tower_stride + (int64_t)f * 3 * F + part * F + kk);
+        }
+        const int j = (int)k - 2 * C;
+        if (j >= towers * F_out) return 0.f;
+        const int t = j / F_out, o = j - t * F_out;
+        return __ldg(wpost + (int64_t)t * wpost_tower_stride + (int64_t)o * 13 * F + kk);
+    }
+    __device__ __forceinline__ float4 get4(int64_t kk, int64_t k) const {
+        if (kk >= F) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return make_float4(elem(kk, k), elem(kk, k + 1), elem(kk, k + 2), elem(kk, k + 3));
+    }
+};
+
 // ------------------------------------------------------------------ activation operands: segmented rows
 // Every activation operand of the model is a row-major [node][column] matrix whose columns are a
 // concatenation of up to three slices of real tensors, optionally multiplied by a per-node degree scaler:
@@ -375,11 +416,60 @@ struct EPostWgrad {
     }
 };
 
+// fused projection forward: P[i, n] = acc + (n < C ? bpre_{t}[f] : 0), n = part*C + t*F + f
+struct EProjStore {
+    float* P;
+    const float* bias;
+    int64_t bias_tower_stride;
+    int F, towers;
+    static constexpr int kCombine3 = 0;
+    __device__ __forceinline__ void set_group(int) {}
+    __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
+        const int C = towers * F;
+        if (n < C) {
+            const int t = n / F, f = n - t * F;
+            const float* b = bias + (int64_t)t * bias_tower_stride + f;
+            v = make_float4(v.x + __ldg(b), v.y + __ldg(b + 1), v.z + __ldg(b + 2), v.w + __ldg(b + 3));
+        }
+        *reinterpret_cast<float4*>(P + m * (2 * (int64_t)C) + n) = v;     // N = 2C, C % 4 == 0
+    }
+};
+// fused projection weight gradient: D[(part,t,f), kk] -> dWpre_t[f, part*F + kk]
+struct EProjWgrad {
+    float* dw;
+    int64_t tower_stride;
+    int F, towers;
+    static constexpr int kCombine3 = 0;
+    __device__ __forceinline__ void set_group(int) {}
+    __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
+        const int C = towers * F;
+        if (m >= 2 * C) return;
+        const int part = (int)m / C, rem = (int)m - part * C, t = rem / F, f = rem - t * F;
+        float* dst = dw + (int64_t)t * tower_stride + (int64_t)f * 3 * F + part * F + n;
+        if (n + 3 < N) {
+            atomicAdd(reinterpret_cast<float4*>(dst), v);
+            return;
+        }
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (n + j < N) atomicAdd(dst + j, e[j]);
+    }
+};
+
 // ------------------------------------------------------------------ geometry of one launch
+// bias gradient of a weight-gradient GEMM: db[target(col)] += sum over nodes of the A operand column `col`
+// (col < ncols), target = base + group*group_stride + (col / tower_cols)*tower_stride + col % tower_cols
+struct ColSum {
+    float* base;
+    int64_t group_stride, tower_stride;
+    int ncols, tower_cols;
+};
 struct Geom {
     int64_t M, K, k_chunk, num_items;
     int N, BN, splits, groups, m_tiles, n_tiles, stages;
     uint32_t tmem_cols;
+    ColSum colsum;
 };
 
 // ------------------------------------------------------------------ operand producers
@@ -515,7 +605,7 @@ __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uin
 // vector copies, no transposition.
 template <int MODE>
 __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes, int R,
-                                               int64_t mn0, int64_t kbase, int64_t k_end, int p) {
+                                               int64_t mn0, int64_t kbase, int64_t k_end, int p, float4* colacc = nullptr) {
     constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
     constexpr int KB = MODE == MODE_TF32X3 ? 32 : 64;
     constexpr int KR = MODE == MODE_TF32X3 ? 4 : 8;
@@ -545,6 +635,15 @@ __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, ui
             if (MODE == MODE_BF16 && ok && s1.scale >= 0) {
                 const float f = __ldg(op.scal + 2 * k + s1.scale);
                 w[i] = make_float4(w[i].x * f, w[i].y * f, w[i].z * f, w[i].w * f);
+            }
+        }
+        if (colacc != nullptr) {                                  // running column sums (bias gradient)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                colacc[0] = make_float4(colacc[0].x + v[i].x, colacc[0].y + v[i].y, colacc[0].z + v[i].z, colacc[0].w + v[i].w);
+                if (MODE == MODE_BF16)
+                    colacc[1] = make_float4(colacc[1].x + w[i].x, colacc[1].y + w[i].y, colacc[1].z + w[i].z,
+                                            colacc[1].w + w[i].w);
             }
         }
 #pragma unroll
@@ -764,6 +863,8 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             BL bl = bl0;
             if constexpr (!MN_MAJOR) bl.set_group(grp);
             const int num_kb = (int)((k_end - k_begin + KB_ELEMS - 1) / KB_ELEMS);
+            float4 colacc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+            const bool do_colsum = MN_MAJOR && g.colsum.base != nullptr && n0 == 0;
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 if ((int)(it % NS) != pg) continue;                // group pg owns ring stage pg (see below)
                 const uint32_t s = it % NS, use = it / NS;
@@ -780,7 +881,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     }
                     produce_a_seg<MODE>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
                 } else if constexpr (MN_MAJOR) {
-                    produce_mn_seg<MODE>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p);
+                    produce_mn_seg<MODE>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p, do_colsum ? colacc : nullptr);
                     produce_mn_seg<MODE>(bl, grp, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
                 } else {
                     produce_a_seg<MODE>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
@@ -788,6 +889,23 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 }
                 fence_async_smem();                                 // generic-proxy writes -> async (tensor core) proxy
                 mbar_arrive(&full_bar[s]);
+            }
+            if constexpr (MN_MAJOR) {
+                if (do_colsum && pg < NS) {                         // flush this thread's column chunk
+                    constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
+                    const int cpr = BM / EPC;
+                    const int col0 = (int)m0 + (p & (cpr - 1)) * EPC;
+                    const float e[8] = {colacc[0].x, colacc[0].y, colacc[0].z, colacc[0].w,
+                                        colacc[1].x, colacc[1].y, colacc[1].z, colacc[1].w};
+#pragma unroll
+                    for (int j = 0; j < EPC; ++j) {
+                        const int col = col0 + j;
+                        if (col < g.colsum.ncols && e[j] != 0.f)
+                            atomicAdd(g.colsum.base + (int64_t)grp * g.colsum.group_stride +
+                                          (int64_t)(col / g.colsum.tower_cols) * g.colsum.tower_stride +
+                                          col % g.colsum.tower_cols, e[j]);
+                    }
+                }
             }
         }
     }
@@ -802,7 +920,8 @@ static const size_t kSmemLimit = 232448;     // 227 KB opt-in maximum per CTA
 // BL: K-major weight functor (packed through pack_ws when possible) or, for MN_MAJOR, a SegOperand
 template <int MODE, bool MN_MAJOR = false, class BL, class EP>
 static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN, int64_t K, int64_t k_chunk, int splits,
-                  int groups, cudaStream_t st, void* pack_ws = nullptr, int64_t pack_ws_bytes = 0) {
+                  int groups, cudaStream_t st, void* pack_ws = nullptr, int64_t pack_ws_bytes = 0,
+                  ColSum colsum = ColSum{nullptr, 0, 0, 0, 1}) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     if (BN % 16 != 0 || BN < 16 || BN > 256) return GNN_ERR_UNSUPPORTED;
     constexpr int parts = MODE == MODE_TF32X3 ? 2 : 1;
@@ -821,6 +940,7 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
     uint32_t cols = 32;
     while ((int)cols < 2 * BN) cols <<= 1;
     g.tmem_cols = cols;
+    g.colsum = colsum;
     const size_t smem = (size_t)stages * stage_bytes + fixed;
     int64_t grid = g.num_items < gnn_sm_count() ? g.num_items : gnn_sm_count();
 
@@ -930,7 +1050,7 @@ extern "C" int gnn_tc_linear_dgrad(const float* dY, int64_t lddy, const float* W
 }
 
 extern "C" int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t M, int N, int K,
-                                   float* dW, int64_t lddw, int precision, void* stream) {
+                                   float* dW, int64_t lddw, float* db, int precision, void* stream) {
     if (M < 0 || N < 1 || K < 1) return GNN_ERR_BAD_ARG;
     REQUIRE_VEC(dY, lddy);
     REQUIRE_VEC(X, ldx);
@@ -944,7 +1064,8 @@ extern "C" int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X
         const int BN = pick_bn_mn(K, MODE);
         const int64_t tiles = gnn_ceil_div(N, BM) * gnn_ceil_div(K, BN);
         splitk(M, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
-        return (launch<MODE, true>(aop, bop, ep, N, K, BN, M, k_chunk, splits, 1, gnn_stream(stream)));
+        return (launch<MODE, true>(aop, bop, ep, N, K, BN, M, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
+                                   ColSum{db, 0, 0, db ? N : 0, N}));
     });
 }
 
@@ -1032,6 +1153,7 @@ extern "C" int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const f
                                                     towers, st, pack_ws, pack_ws_bytes)));
         if (rc) return rc;
     }
+    if (dx == nullptr) return 0;       // the caller folds the x part into gnn_tc_pna_dx_dgrad
     // dx += sum_t dO_t . Wpost_t[:, :F]     (towers accumulate into the same dx -> sequential launches)
     for (int t = 0; t < towers; ++t) {
         const float* d = dO + t * F_out;
@@ -1046,6 +1168,73 @@ extern "C" int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const f
         if (rc) return rc;
     }
     return 0;
+}
+
+// ------------------------------------------------------------------ fused projection / dx GEMMs
+// P = [x Wdst_t^T + b_t | x Wsrc_t^T] for both towers in one launch  (replaces 4 Linear calls)
+extern "C" int gnn_tc_pna_proj_fwd(const float* x, const float* wpre, int64_t wpre_tower_stride, const float* bpre,
+                                   int64_t bpre_tower_stride, int64_t n, int F, int towers, float* P, int precision,
+                                   void* pack_ws, int64_t pack_ws_bytes, void* stream) {
+    if (n < 0 || F < 4 || (F & 3) || towers < 1) return GNN_ERR_BAD_ARG;
+    REQUIRE_VEC(x, F);
+    REQUIRE_VEC(P, 2 * (int64_t)towers * F);
+    REQUIRE_VEC(wpre, wpre_tower_stride);
+    REQUIRE_VEC(bpre, bpre_tower_stride);
+    const int C = towers * F;
+    SegOperand aop = seg_plain(x, F, n, F);
+    VProjWeight bl{wpre, wpre_tower_stride, F, towers};
+    EProjStore ep{P, bpre, bpre_tower_stride, F, towers};
+    int BN = pick_bn(2 * C);
+    if (BN > 128) BN = 128;
+    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, 2 * C, BN, (int64_t)F, (int64_t)F, 1, 1,
+                                                  gnn_stream(stream), pack_ws, pack_ws_bytes)));
+}
+
+// dx (+)= dP . Wproj + sum_t dO_t . Wpost_t[:, :F]   (replaces 4 projection dgrads + 2 post x-part dgrads)
+extern "C" int gnn_tc_pna_dx_dgrad(const float* dP, const float* dO, const float* wpre, int64_t wpre_tower_stride,
+                                   const float* wpost, int64_t wpost_tower_stride, int64_t n, int F, int F_out,
+                                   int towers, int accumulate, float* dx, int precision, void* pack_ws,
+                                   int64_t pack_ws_bytes, void* stream) {
+    if (n < 0 || F < 4 || (F & 3) || F_out < 4 || (F_out & 3) || towers < 1) return GNN_ERR_BAD_ARG;
+    const int C = towers * F;
+    REQUIRE_VEC(dP, 2 * (int64_t)C);
+    REQUIRE_VEC(dO, (int64_t)towers * F_out);
+    REQUIRE_VEC(dx, F);
+    SegOperand aop{};
+    aop.seg[0] = Seg{dP, 2 * (int64_t)C, 0, 0, 2 * C, -1};
+    aop.seg[1] = Seg{dO, (int64_t)towers * F_out, 0, 2 * C, towers * F_out, -1};
+    aop.nseg = 2;
+    aop.rows = n;
+    VDxWeight bl{wpre, wpost, wpre_tower_stride, wpost_tower_stride, F, F_out, towers};
+    EStore ep{dx, F, 0, nullptr, 0, 0, accumulate, is_vec(dx, F)};
+    const int64_t K = 2 * (int64_t)C + (int64_t)towers * F_out;
+    const int BN = pick_bn(F);
+    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, F, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
+                                                  pack_ws_bytes)));
+}
+
+// dWpre_t[:, :2F] += dP^T x, dbpre_t += colsum(dPdst_t)   (replaces 4 Linear wgrads + colsum)
+extern "C" int gnn_tc_pna_proj_wgrad(const float* dP, const float* x, int64_t n, int F, int towers, float* dwpre,
+                                     int64_t wpre_tower_stride, float* dbpre, int64_t bpre_tower_stride, int precision,
+                                     void* stream) {
+    if (n < 0 || F < 4 || (F & 3) || towers < 1) return GNN_ERR_BAD_ARG;
+    if (n == 0) return 0;
+    const int C = towers * F;
+    REQUIRE_VEC(dP, 2 * (int64_t)C);
+    REQUIRE_VEC(x, F);
+    REQUIRE_VEC(dwpre, wpre_tower_stride);
+    SegOperand aop = seg_plain(dP, 2 * (int64_t)C, n, 2 * C);
+    SegOperand bop = seg_plain(x, F, n, F);
+    EProjWgrad ep{dwpre, wpre_tower_stride, F, towers};
+    int64_t k_chunk;
+    int splits;
+    DISPATCH_MODE(precision, {
+        const int BN = pick_bn_mn(F, MODE);
+        const int64_t tiles = gnn_ceil_div(2 * C, BM) * gnn_ceil_div(F, BN);
+        splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
+        return (launch<MODE, true>(aop, bop, ep, 2 * C, F, BN, n, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
+                                   ColSum{dbpre, 0, bpre_tower_stride, dbpre ? C : 0, F}));
+    });
 }
 
 extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const float* scal, int64_t n,
@@ -1073,26 +1262,27 @@ extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const floa
             const int BN = pick_bn_mn(4 * F, MODE);
             const int64_t tiles = gnn_ceil_div(4 * F, BN) * gnn_ceil_div(3 * FoP, BM) * towers;
             splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
-            rc = (launch<MODE, true>(aop, bop, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st));
+            rc = (launch<MODE, true>(aop, bop, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st, nullptr, 0,
+                                     ColSum{dbpost, bpost_tower_stride, 0, dbpost ? F_out : 0, F_out}));
         });
         if (rc) return rc;
     }
-    // (2) x part: dWpost_t[o, :F] += dO_t^T x
-    for (int t = 0; t < towers; ++t) {
-        const float* d = dO + t * F_out;
-        SegOperand aop = seg_plain(d, (int64_t)towers * F_out, n, F_out);
+    // (2) x part: dWpost_t[o, :F] += dO_t^T x   (both towers in one launch: group = tower)
+    {
+        SegOperand aop{};
+        aop.seg[0] = Seg{dO, (int64_t)towers * F_out, F_out, 0, F_out, -1};
+        aop.nseg = 1;
+        aop.rows = n;
         SegOperand bop = seg_plain(x, F, n, F);
-        EAtomic ep{dwpost + t * wpost_tower_stride, 13 * (int64_t)F, 0, is_vec(dwpost + t * wpost_tower_stride, F)};
+        EAtomic ep{dwpost, 13 * (int64_t)F, wpost_tower_stride, is_vec(dwpost, F) && (wpost_tower_stride % 4 == 0)};
         int64_t k_chunk;
         int splits, rc;
         DISPATCH_MODE(precision, {
             const int BN = pick_bn_mn(F, MODE);
-            const int64_t tiles = gnn_ceil_div(F, BN);
+            const int64_t tiles = gnn_ceil_div(F, BN) * towers;
             splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
-            rc = (launch<MODE, true>(aop, bop, ep, F_out, F, BN, n, k_chunk, splits, 1, st));
+            rc = (launch<MODE, true>(aop, bop, ep, F_out, F, BN, n, k_chunk, splits, towers, st));
         });
-        if (rc) return rc;
-        rc = gnn_colsum_accum(d, (int64_t)towers * F_out, n, F_out, dbpost + t * bpost_tower_stride, stream);
         if (rc) return rc;
     }
     return 0;

@@ -172,9 +172,7 @@ def _lin_wgrad(mm, dY, lddy, X, ldx, M, N, K, dW, lddw, db):
     if mm < 0 or not (_al(dY, lddy, N) and _al(X, ldx, K)):
         _c("gnn_linear_wgrad", dY, lddy, X, ldx, M, N, K, dW, lddw, db)
     else:
-        _c("gnn_tc_linear_wgrad", dY, lddy, X, ldx, M, N, K, dW, lddw, mm)
-        if db is not None:
-            _c("gnn_colsum_accum", dY, lddy, M, N, db)
+        _c("gnn_tc_linear_wgrad", dY, lddy, X, ldx, M, N, K, dW, lddw, db, mm)
 
 
 def _post_fwd(mm, *args):
@@ -475,11 +473,19 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         # node projections  P = [Pdst_t0 | Pdst_t1 | Psrc_t0 | Psrc_t1]
         P = torch.empty(n, 2 * C, **f32)
         mm_proj = 0 if mm == 2 else mm      # bf16 mode: messages stay fp32-accurate (min/max/std are selection-sensitive)
-        for t in range(T):
-            w = conv.pre_nns[t][0].weight
-            b = conv.pre_nns[t][0].bias
-            _lin_fwd(mm_proj, x, H, w, 3 * F, b, n, F, F, 0, P[:, t * F:], 2 * C)
-            _lin_fwd(mm_proj, x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
+        pre0 = conv.pre_nns[0][0]
+        ts_pre = model._offset_of(conv.pre_nns[1][0].weight) - model._offset_of(pre0.weight)
+        bs_pre = model._offset_of(conv.pre_nns[1][0].bias) - model._offset_of(pre0.bias)
+        rec.pre_strides = (ts_pre, bs_pre)
+        if mm_proj >= 0:
+            ws = _pack_ws(dev)
+            _c("gnn_tc_pna_proj_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, ws.numel())
+        else:
+            for t in range(T):
+                w = conv.pre_nns[t][0].weight
+                b = conv.pre_nns[t][0].bias
+                _lin_fwd(mm_proj, x, H, w, 3 * F, b, n, F, F, 0, P[:, t * F:], 2 * C)
+                _lin_fwd(mm_proj, x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
         A = torch.empty(n, T * 4 * F, **f32)
         rec.P = P
         if pp.pre_layers == 1:
@@ -639,7 +645,8 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
         w0, b0 = conv.post_nns[0][0].weight, conv.post_nns[0][0].bias
         _post_wgrad(mm, dO, x_in, rec.A, rec.scal, n, F, Fo, T, gview(w0), ts_post, gview(b0), bs_post)
         gA = torch.empty(n, T * 4 * F, **f32)
-        _post_dgrad(mm, dO, rec.scal, w0, ts_post, n, F, Fo, T, dx, gA)
+        fused_dx = mm >= 0        # tensor-core path: every node-feature gradient of the layer in ONE GEMM (below)
+        _post_dgrad(mm, dO, rec.scal, w0, ts_post, n, F, Fo, T, None if fused_dx else dx, gA)
         # aggregation + message
         dP = torch.empty(n, 2 * C, **f32)
         if pp.pre_layers == 1:
@@ -664,13 +671,20 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
             _c("gnn_edge_hidden_bwd", dq, g.rowptr, g.col_code, n, C, dP, dtab[l])
         _c("gnn_scatter_src_bwd", dq, g.srcptr, g.src_slot, n, C, dP)
         # projections
-        for t in range(T):
-            lin = conv.pre_nns[t][0]
-            gw = gview(lin.weight)
-            _lin_wgrad(mm, dP[:, t * F:], 2 * C, x_in, H, n, F, F, gw, 3 * F, gview(lin.bias))
-            _lin_wgrad(mm, dP[:, C + t * F:], 2 * C, x_in, H, n, F, F, gw[:, F:], 3 * F, None)
-            _lin_dgrad(mm, dP[:, t * F:], 2 * C, lin.weight, 3 * F, n, F, F, 1, dx, H)
-            _lin_dgrad(mm, dP[:, C + t * F:], 2 * C, lin.weight[:, F:], 3 * F, n, F, F, 1, dx, H)
+        if fused_dx:
+            pre0 = conv.pre_nns[0][0]
+            ts_pre, bs_pre = rec.pre_strides
+            _c("gnn_tc_pna_proj_wgrad", dP, x_in, n, F, T, gview(pre0.weight), ts_pre, gview(pre0.bias), bs_pre, mm)
+            ws = _pack_ws(dev)
+            _c("gnn_tc_pna_dx_dgrad", dP, dO, pre0.weight, ts_pre, w0, ts_post, n, F, Fo, T, 1, dx, mm, ws, ws.numel())
+        else:
+            for t in range(T):
+                lin = conv.pre_nns[t][0]
+                gw = gview(lin.weight)
+                _lin_wgrad(mm, dP[:, t * F:], 2 * C, x_in, H, n, F, F, gw, 3 * F, gview(lin.bias))
+                _lin_wgrad(mm, dP[:, C + t * F:], 2 * C, x_in, H, n, F, F, gw[:, F:], 3 * F, None)
+                _lin_dgrad(mm, dP[:, t * F:], 2 * C, lin.weight, 3 * F, n, F, F, 1, dx, H)
+                _lin_dgrad(mm, dP[:, C + t * F:], 2 * C, lin.weight[:, F:], 3 * F, n, F, F, 1, dx, H)
 
     # ---- encoders
     atom_tab = model.node_embed.atom_embedding_list[0].weight

@@ -197,8 +197,11 @@ int gnn_pna_post_wgrad(const float* dO, const float* x, const float* A, const fl
  * `precision`: 0 = TF32x3 (fp32 operands split into tf32 hi+lo, 3 MMAs: fp32-level accuracy, the
  * parity path), 2 = BF16 operands, fp32 accumulate (the reference's own
  * torch.set_float32_matmul_precision("medium"), train.py:319).  Semantics equal the gnn_linear_* /
- * gnn_pna_post_* entry points above, except that weight-gradient calls do not produce bias
- * gradients: use gnn_colsum_accum (db[n] += sum_i dY[i,n]).
+ * gnn_pna_post_* entry points above (bias gradients are column sums taken by the operand producers of the
+ * weight-gradient kernels; gnn_colsum_accum is the stand-alone version).  Operands must be 128-bit
+ * accessible (16-byte aligned, leading dimensions and K / N multiples of 4), else GNN_ERR_UNSUPPORTED.
+ * gnn_tc_pna_post_dgrad: dx may be NULL (then only gA is produced and the x part goes through
+ * gnn_tc_pna_dx_dgrad).
  * pack_ws (optional, 128-byte aligned, may be NULL): scratch in which the weight operand is first packed
  * as the exact shared-memory tile image (swizzled, hi/lo planes) so the GEMM fetches it with TMA bulk
  * copies instead of re-converting it for every 128-row tile; 4 MiB covers every shape of the model. */
@@ -209,7 +212,7 @@ int gnn_tc_linear_dgrad(const float* dY, int64_t lddy, const float* W, int64_t l
                         int K, int accumulate, float* dX, int64_t lddx, int precision, void* pack_ws,
                         int64_t pack_ws_bytes, void* stream);
 int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t M, int N,
-                        int K, float* dW, int64_t lddw, int precision, void* stream);
+                        int K, float* dW, int64_t lddw, float* db, int precision, void* stream);
 int gnn_colsum_accum(const float* dY, int64_t lddy, int64_t M, int N, float* db, void* stream);
 int gnn_tc_pna_post_fwd(const float* x, const float* A, const float* scal, const float* wpost,
                         int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
@@ -222,6 +225,22 @@ int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const float* wpost
 int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const float* scal,
                           int64_t num_nodes, int F, int F_out, int towers, float* dwpost,
                           int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride,
+                          int precision, void* stream);
+
+/* Fused projection stage of PNAConv (pre_nns[t][0], first two thirds of its input), all towers in one
+ * launch.  wpre / bpre point at tower 0 of the layer, towers are *_tower_stride floats apart.
+ *   proj_fwd : P[N, 2C] = [x Wdst_t^T + b_t | x Wsrc_t^T]                    (C = towers*F)
+ *   dx_dgrad : dx (+)= dP . [Wdst | Wsrc] + sum_t dO_t . Wpost_t[:, :F]      (all node-feature gradients of a layer)
+ *   proj_wgrad: dWpre_t[:, :2F] += dP^T x ;  dbpre_t += colsum(dPdst_t) */
+int gnn_tc_pna_proj_fwd(const float* x, const float* wpre, int64_t wpre_tower_stride, const float* bpre,
+                        int64_t bpre_tower_stride, int64_t num_nodes, int F, int towers, float* P,
+                        int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream);
+int gnn_tc_pna_dx_dgrad(const float* dP, const float* dO, const float* wpre, int64_t wpre_tower_stride,
+                        const float* wpost, int64_t wpost_tower_stride, int64_t num_nodes, int F, int F_out,
+                        int towers, int accumulate, float* dx, int precision, void* pack_ws,
+                        int64_t pack_ws_bytes, void* stream);
+int gnn_tc_pna_proj_wgrad(const float* dP, const float* x, int64_t num_nodes, int F, int towers,
+                          float* dwpre, int64_t wpre_tower_stride, float* dbpre, int64_t bpre_tower_stride,
                           int precision, void* stream);
 
 /* ---------------------------------------------------------------- BatchNorm / ReLU / skip

@@ -344,8 +344,8 @@ def gnn_tc_linear_dgrad(dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, precisi
     gnn_linear_dgrad(dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx)
 
 
-def gnn_tc_linear_wgrad(dY, lddy, X, ldx, M, N, K, dW, lddw, precision, stream=None):
-    gnn_linear_wgrad(dY, lddy, X, ldx, M, N, K, dW, lddw, None)
+def gnn_tc_linear_wgrad(dY, lddy, X, ldx, M, N, K, dW, lddw, db, precision, stream=None):
+    gnn_linear_wgrad(dY, lddy, X, ldx, M, N, K, dW, lddw, db)
 
 
 def gnn_colsum_accum(dY, lddy, M, N, db, stream=None):
@@ -359,7 +359,40 @@ def gnn_tc_pna_post_fwd(x, A, scal, wpost, wts, bpost, bts, n, f, f_out, towers,
 
 def gnn_tc_pna_post_dgrad(dO, scal, wpost, wts, n, f, f_out, towers, dx, gA, precision, pack_ws=None,
                           pack_ws_bytes=0, stream=None):
-    gnn_pna_post_dgrad(dO, scal, wpost, wts, n, f, f_out, towers, dx, gA)
+    scratch = dx if dx is not None else torch.zeros(n, f, dtype=gA.dtype)
+    gnn_pna_post_dgrad(dO, scal, wpost, wts, n, f, f_out, towers, scratch, gA)
+
+
+def gnn_tc_pna_proj_fwd(x, wpre, wts, bpre, bts, n, f, towers, P, precision, pack_ws=None, pack_ws_bytes=0,
+                        stream=None):
+    c = towers * f
+    for t in range(towers):
+        w = _mat(wpre, f, 3 * f, 3 * f, t * wts)
+        b = _flat(bpre, f, t * bts)
+        P[:n, t * f:(t + 1) * f] = x[:n] @ w[:, :f].t() + b
+        P[:n, c + t * f:c + (t + 1) * f] = x[:n] @ w[:, f:2 * f].t()
+
+
+def gnn_tc_pna_dx_dgrad(dP, dO, wpre, wpre_ts, wpost, wpost_ts, n, f, f_out, towers, accumulate, dx, precision,
+                        pack_ws=None, pack_ws_bytes=0, stream=None):
+    c = towers * f
+    acc = dx[:n].clone() if accumulate else torch.zeros_like(dx[:n])
+    for t in range(towers):
+        w = _mat(wpre, f, 3 * f, 3 * f, t * wpre_ts)
+        acc += dP[:n, t * f:(t + 1) * f] @ w[:, :f] + dP[:n, c + t * f:c + (t + 1) * f] @ w[:, f:2 * f]
+        wp = _mat(wpost, f_out, 13 * f, 13 * f, t * wpost_ts)
+        acc += dO[:n, t * f_out:(t + 1) * f_out] @ wp[:, :f]
+    dx[:n] = acc
+
+
+def gnn_tc_pna_proj_wgrad(dP, x, n, f, towers, dwpre, wts, dbpre, bts, precision, stream=None):
+    c = towers * f
+    for t in range(towers):
+        dw = _mat(dwpre, f, 3 * f, 3 * f, t * wts)
+        dw[:, :f] += dP[:n, t * f:(t + 1) * f].t() @ x[:n]
+        dw[:, f:2 * f] += dP[:n, c + t * f:c + (t + 1) * f].t() @ x[:n]
+        if dbpre is not None:
+            _flat(dbpre, f, t * bts).add_(dP[:n, t * f:(t + 1) * f].sum(0))
 
 
 def gnn_tc_pna_post_wgrad(dO, x, A, scal, n, f, f_out, towers, dwpost, wts, dbpost, bts, precision, stream=None):

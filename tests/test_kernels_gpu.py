@@ -448,9 +448,12 @@ def test_tc_linear_fwd_dgrad_wgrad(precision, M, N, K, ldx, ldw, ldy):
         for ws in (None, torch.zeros(4 << 20, dtype=torch.uint8)):
             cpu, gpu = run_both("gnn_tc_linear_dgrad", dY, ldy, W, ldw, M, N, K, acc, dX, ldx, precision, ws, 4 << 20)
             close(gpu[-5], cpu[-5], tol, "tc linear dgrad")
-    dW = torch.randn(N, ldw, generator=g)
-    cpu, gpu = run_both("gnn_tc_linear_wgrad", dY, ldy, X, ldx, M, N, K, dW, ldw, precision)
-    close(gpu[-3], cpu[-3], 2 * tol, "tc linear wgrad")
+    dW, db = torch.randn(N, ldw, generator=g), torch.randn(N, generator=g)
+    cpu, gpu = run_both("gnn_tc_linear_wgrad", dY, ldy, X, ldx, M, N, K, dW, ldw, db, precision)
+    close(gpu[-4], cpu[-4], 2 * tol, "tc linear wgrad")
+    close(gpu[-2], cpu[-2], 2e-5 if precision == 0 else tol, "tc linear wgrad bias")
+    cpu, gpu = run_both("gnn_tc_linear_wgrad", dY, ldy, X, ldx, M, N, K, dW, ldw, None, precision)
+    close(gpu[-4], cpu[-4], 2 * tol, "tc linear wgrad (no bias)")
     db = torch.randn(N, generator=g)
     cpu, gpu = run_both("gnn_colsum_accum", dY, ldy, M, N, db)
     close(gpu[-1], cpu[-1], 2e-5, "colsum")
@@ -487,6 +490,10 @@ def test_tc_pna_post_fwd_dgrad_wgrad(precision, n, F):
         res.append((dx, gA))
     close(res[1][0], res[0][0], tol, "tc post dgrad dx")
     close(res[1][1], res[0][1], tol, "tc post dgrad gA")
+    gA2 = torch.zeros(n, T * 4 * F, device=DEV)                   # dx = NULL: only gA
+    _lib.call("gnn_tc_pna_post_dgrad", dO.to(DEV), scal.to(DEV), wbuf.to(DEV), wts, n, F, Fo, T, None, gA2, precision,
+              torch.zeros(4 << 20, dtype=torch.uint8, device=DEV), 4 << 20, _lib.stream_ptr())
+    close(gA2, res[0][1], tol, "tc post dgrad gA (dx=NULL)")
     res = []
     for dev in ("cpu", DEV):
         gbase = torch.zeros(T * wts).to(dev)
@@ -509,3 +516,42 @@ def test_tc_rejects_unaligned_operands():
     rc = lib.gnn_tc_linear_dgrad(Y.data_ptr(), 5, W.data_ptr(), 70, 64, 5, 70, 0, X.data_ptr(), 70, 0, None, 0,
                                  _lib.stream_ptr())
     assert rc == -3
+
+
+@pytest.mark.parametrize("precision", [0, 2])
+@pytest.mark.parametrize("n,F", [(1000, 64), (70, 16), (3, 8), (300, 128)])
+def test_tc_fused_projection_stage(precision, n, F):
+    """proj_fwd / dx_dgrad / proj_wgrad: the four projection Linears (and the x part of the post stage) in one GEMM each."""
+    tol = TC_TOL[precision]
+    T, Fo, C = 2, F // 2, 2 * F
+    g = torch.Generator().manual_seed(n + F)
+    x = torch.randn(n, F, generator=g)
+    pre_ts = F * 3 * F + F + 4            # [weight F x 3F | bias F | pad] per tower
+    pre = torch.randn(T * pre_ts, generator=g) * 0.1
+    post_ts = Fo * 13 * F + Fo + 4
+    post = torch.randn(T * post_ts, generator=g) * 0.1
+    ws = lambda dev: torch.zeros(4 << 20, dtype=torch.uint8, device=dev)
+    res = []
+    for dev in ("cpu", DEV):
+        b = pre.to(dev)
+        args = [x.to(dev), b, pre_ts, b[F * 3 * F:], pre_ts, n, F, T, torch.zeros(n, 2 * C, device=dev), precision, ws(dev), 4 << 20]
+        R.gnn_tc_pna_proj_fwd(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_proj_fwd", *args, _lib.stream_ptr())
+        res.append(args[8])
+    close(res[1], res[0], tol, "proj fwd")
+    dP, dO = torch.randn(n, 2 * C, generator=g), torch.randn(n, T * Fo, generator=g)
+    for acc in (0, 1):
+        res = []
+        for dev in ("cpu", DEV):
+            dx = torch.ones(n, F, device=dev) * 0.5
+            args = [dP.to(dev), dO.to(dev), pre.to(dev), pre_ts, post.to(dev), post_ts, n, F, Fo, T, acc, dx, precision,
+                    ws(dev), 4 << 20]
+            R.gnn_tc_pna_dx_dgrad(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_dx_dgrad", *args, _lib.stream_ptr())
+            res.append(dx)
+        close(res[1], res[0], tol, "fused dx dgrad")
+    res = []
+    for dev in ("cpu", DEV):
+        gb = torch.zeros(T * pre_ts, device=dev)
+        args = [dP.to(dev), x.to(dev), n, F, T, gb, pre_ts, gb[F * 3 * F:], pre_ts, precision]
+        R.gnn_tc_pna_proj_wgrad(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_proj_wgrad", *args, _lib.stream_ptr())
+        res.append(gb)
+    close(res[1], res[0], 2 * tol, "proj wgrad")
