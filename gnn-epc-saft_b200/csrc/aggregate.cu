@@ -181,6 +181,7 @@ extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int
     if (n < 0 || towers < 1 || F < 4 || (F & 3)) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
     const int C = towers * F;
+    if ((int64_t)n * 2 * C >= (1ll << 31)) return GNN_ERR_TOO_LARGE;    // 32-bit row offsets in the gather
     cudaStream_t st = gnn_stream(stream);
     int64_t blocks = gnn_ceil_div(n, AGG_WARPS);
     int64_t cap = (int64_t)gnn_sm_count() * 48;
@@ -190,131 +191,155 @@ extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int
 }
 
 // ------------------------------------------------------------------ backward, factorised message
-// Per destination node: recompute the segment statistics of q (same order as forward, so the
-// mean/min/max are bitwise those of the forward), count ties, then emit
+// Per destination node: recompute the segment statistics of q (shifted by the first message exactly as in the
+// forward kernel), count ties, then emit
 //   dq_e = g_mean/cnt + g_min*[q_e==min]/n_min + g_max*[q_e==max]/n_max + g_std*(q_e-mean)/(cnt*std)
-// per CSR slot, dPdst = (g_mean+g_min+g_max)*[cnt>0] and the per-bond-code sum of dq
-// (CTA-private shared table when it fits, flushed once per CTA).
-template <bool SMEM_TAB>
+// per CSR slot, dPdst = (g_mean+g_min+g_max)*[cnt>0] and the per-bond-code sum of dq.  sm_100 has no native
+// fp32 shared-memory atomic add (it compiles to a CAS spin loop), so the bond-code sums go to one of DTAB_PARTS
+// partial tables in global memory with native 128-bit reductions (RED.E.ADD.F32x4 at the L2), summed afterwards.
+constexpr int DTAB_PARTS = 64;
+
 __global__ void __launch_bounds__(AGG_THREADS)
 pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__ P,
                          const float* __restrict__ tab, const float* __restrict__ A,
                          const int* __restrict__ rowptr, const int* __restrict__ col_src,
                          const uint8_t* __restrict__ col_code, int64_t n, int C, int F,
-                         float* __restrict__ dP, float* __restrict__ dq, float* dtab) {
-    extern __shared__ float s_dtab[];
-    if (SMEM_TAB) {
-        for (int k = threadIdx.x; k < GNN_NUM_BOND_CODES * C; k += blockDim.x) s_dtab[k] = 0.f;
-        __syncthreads();
-    }
+                         float* __restrict__ dP, float* __restrict__ dq, float* __restrict__ dtab_parts) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * AGG_WARPS;
-    const int64_t ldp = 2 * (int64_t)C;
+    const int ldp = 2 * C;
+    float* dtab = dtab_parts + (size_t)(blockIdx.x % DTAB_PARTS) * GNN_NUM_BOND_CODES * C;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t node = warp0; node < n; node += nwarps) {
-        const int beg = rowptr[node], end = rowptr[node + 1];
+        const int rp = __ldg(rowptr + node + (lane & 1));
+        const int beg = __shfl_sync(GNN_FULL_MASK, rp, 0), end = __shfl_sync(GNN_FULL_MASK, rp, 1);
         const int cnt = end - beg;
-        const float inv_cnt = cnt > 0 ? 1.0f / (float)cnt : 0.f;
-        // 128 channels at a time (one float4 per lane) keeps the register footprint flat in C
-        for (int c = lane * 4; c < C; c += 128) {
+        int my_src = 0, my_code = 0;
+        if (lane < cnt) {
+            my_src = __ldg(col_src + beg + lane) * ldp + C;
+            my_code = (int)__ldg(col_code + beg + lane) * C;
+        }
+        for (int cb = 0; cb < C; cb += 128) {                  // warp-uniform trip count (shuffles inside)
+            const int c = cb + lane * 4;
+            const bool live = c < C;
             if (cnt == 0) {
-                st4(dP + node * ldp + c, make_float4(0.f, 0.f, 0.f, 0.f));
+                if (live) st4(dP + node * ldp + c, zero);
                 continue;
             }
-            float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 mn = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX);
-            float4 mx = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-            float4 nmin = make_float4(0.f, 0.f, 0.f, 0.f), nmax = nmin;
-            // pass 1: statistics + tie counts (same update order as the forward kernel)
-            for (int s = beg; s < end; ++s) {
-                const int src = __ldg(col_src + s);
-                const int code = __ldg(col_code + s);
-                const float inv_k = 1.0f / (float)(s - beg + 1);
-                float4 q = add4(ldg4(P + (int64_t)src * ldp + C + c), ldg4(tab + (int64_t)code * C + c));
-#define UPD(X)                                                     \
-    {                                                              \
-        float d = q.X - mean.X;                                    \
-        mean.X = fmaf(d, inv_k, mean.X);                           \
-        if (q.X < mn.X) { mn.X = q.X; nmin.X = 1.f; }              \
-        else if (q.X == mn.X) nmin.X += 1.f;                       \
-        if (q.X > mx.X) { mx.X = q.X; nmax.X = 1.f; }              \
-        else if (q.X == mx.X) nmax.X += 1.f;                       \
+            const float* pbase = P + c;
+            const float* tbase = tab + c;
+            const int m = min(cnt, 32);
+            // ---- pass 1: shifted sum, min / max with tie counts
+            float4 q0 = zero, s1 = zero, mn = zero, mx = zero, nmin = zero, nmax = zero;
+            for (int k = 0; k < cnt; ++k) {
+                int so, co;
+                if (k < 32) {
+                    so = __shfl_sync(GNN_FULL_MASK, my_src, k);
+                    co = __shfl_sync(GNN_FULL_MASK, my_code, k);
+                } else {
+                    so = __ldg(col_src + beg + k) * ldp + C;
+                    co = (int)__ldg(col_code + beg + k) * C;
+                }
+                const float4 q = live ? add4(ldg4(pbase + so), ldg4(tbase + co)) : zero;
+                if (k == 0) {
+                    q0 = q; mn = q; mx = q;
+                    nmin = make_float4(1.f, 1.f, 1.f, 1.f);
+                    nmax = nmin;
+                } else {
+#define UPD(X)                                                      \
+    {                                                               \
+        s1.X += q.X - q0.X;                                         \
+        if (q.X < mn.X) { mn.X = q.X; nmin.X = 1.f; }               \
+        else if (q.X == mn.X) nmin.X += 1.f;                        \
+        if (q.X > mx.X) { mx.X = q.X; nmax.X = 1.f; }               \
+        else if (q.X == mx.X) nmax.X += 1.f;                        \
     }
-                UPD(x) UPD(y) UPD(z) UPD(w)
+                    UPD(x) UPD(y) UPD(z) UPD(w)
 #undef UPD
+                }
             }
-            const int t = c / F, f = c - t * F;
-            const int64_t off = node * (4 * (int64_t)C) + (int64_t)t * 4 * F + f;
-            const float4 g_mean = ldg4(gA + off), g_min = ldg4(gA + off + F), g_max = ldg4(gA + off + 2 * F),
-                         g_std = ldg4(gA + off + 3 * F);
-            const float4 sd = ldg4(A + off + 3 * F);
-            st4(dP + node * ldp + c, make_float4(g_mean.x + g_min.x + g_max.x, g_mean.y + g_min.y + g_max.y,
-                                                 g_mean.z + g_min.z + g_max.z, g_mean.w + g_min.w + g_max.w));
-            float4 cm, cmin, cmax, cs;
+            (void)m;
+            const float inv_cnt = __frcp_rn((float)cnt);
+            const float4 mean = make_float4(fmaf(s1.x, inv_cnt, q0.x), fmaf(s1.y, inv_cnt, q0.y),
+                                            fmaf(s1.z, inv_cnt, q0.z), fmaf(s1.w, inv_cnt, q0.w));
+            float4 cm = zero, cmin = zero, cmax = zero, cs = zero;
+            if (live) {
+                const int t = c / F, f = c - t * F;
+                const int64_t off = node * (4 * (int64_t)C) + (int64_t)t * 4 * F + f;
+                const float4 g_mean = ldg4(gA + off), g_min = ldg4(gA + off + F), g_max = ldg4(gA + off + 2 * F),
+                             g_std = ldg4(gA + off + 3 * F);
+                const float4 sd = ldg4(A + off + 3 * F);
+                st4(dP + node * ldp + c, make_float4(g_mean.x + g_min.x + g_max.x, g_mean.y + g_min.y + g_max.y,
+                                                     g_mean.z + g_min.z + g_max.z, g_mean.w + g_min.w + g_max.w));
 #define COEF(X)                                              \
     cm.X = g_mean.X * inv_cnt;                               \
     cmin.X = g_min.X / nmin.X;                               \
     cmax.X = g_max.X / nmax.X;                               \
     cs.X = sd.X > 0.f ? g_std.X * inv_cnt / sd.X : 0.f;
-            COEF(x) COEF(y) COEF(z) COEF(w)
+                COEF(x) COEF(y) COEF(z) COEF(w)
 #undef COEF
-            // pass 2: per-slot gradient (rows are L1/L2 hits from pass 1)
-            for (int s = beg; s < end; ++s) {
-                const int src = __ldg(col_src + s);
-                const int code = __ldg(col_code + s);
-                float4 q = add4(ldg4(P + (int64_t)src * ldp + C + c), ldg4(tab + (int64_t)code * C + c));
-                float4 g;
+            }
+            // ---- pass 2: per-slot gradient (rows are L1/L2 hits from pass 1)
+            for (int k = 0; k < cnt; ++k) {
+                int so, co;
+                if (k < 32) {
+                    so = __shfl_sync(GNN_FULL_MASK, my_src, k);
+                    co = __shfl_sync(GNN_FULL_MASK, my_code, k);
+                } else {
+                    so = __ldg(col_src + beg + k) * ldp + C;
+                    co = (int)__ldg(col_code + beg + k) * C;
+                }
+                if (live) {
+                    const float4 q = add4(ldg4(pbase + so), ldg4(tbase + co));
+                    float4 g;
 #define GRAD(X) \
     g.X = cm.X + (q.X == mn.X ? cmin.X : 0.f) + (q.X == mx.X ? cmax.X : 0.f) + cs.X * (q.X - mean.X);
-                GRAD(x) GRAD(y) GRAD(z) GRAD(w)
+                    GRAD(x) GRAD(y) GRAD(z) GRAD(w)
 #undef GRAD
-                st4(dq + (int64_t)s * C + c, g);
-                float* dt = (SMEM_TAB ? s_dtab : dtab) + code * C + c;
-                atomicAdd(dt, g.x);
-                atomicAdd(dt + 1, g.y);
-                atomicAdd(dt + 2, g.z);
-                atomicAdd(dt + 3, g.w);
+                    st4(dq + (int64_t)(beg + k) * C + c, g);
+                    atomicAdd(reinterpret_cast<float4*>(dtab + co + c), g);     // RED.E.ADD.F32x4
+                }
             }
         }
     }
-    if (SMEM_TAB) {
-        __syncthreads();
-        for (int k = threadIdx.x; k < GNN_NUM_BOND_CODES * C; k += blockDim.x) {
-            float v = s_dtab[k];
-            if (v != 0.f) atomicAdd(dtab + k, v);
-        }
+}
+
+// dtab_accum[k] += sum over the partial tables; the partial tables are cleared for the next call
+__global__ void dtab_reduce_kernel(float* __restrict__ parts, int total, float* __restrict__ dtab_accum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int p = 0; p < DTAB_PARTS; ++p) {
+        acc += parts[(size_t)p * total + i];
+        parts[(size_t)p * total + i] = 0.f;
     }
+    dtab_accum[i] += acc;
+}
+
+extern "C" int64_t gnn_pna_aggregate_bwd_workspace_bytes(int towers, int F) {
+    return (int64_t)DTAB_PARTS * GNN_NUM_BOND_CODES * towers * F * (int64_t)sizeof(float);
 }
 
 extern "C" int gnn_pna_aggregate_bwd(const float* gA, const float* P, const float* tab, const float* A,
                                      const int32_t* rowptr, const int32_t* col_src, const uint8_t* col_code,
                                      int64_t n, int towers, int F, float* dP, float* dq, float* dtab_accum,
-                                     void* stream) {
+                                     void* zeroed_workspace, int64_t workspace_bytes, void* stream) {
     if (n < 0 || towers < 1 || F < 4 || (F & 3)) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
+    if (workspace_bytes < gnn_pna_aggregate_bwd_workspace_bytes(towers, F)) return GNN_ERR_WORKSPACE;
     const int C = towers * F;
+    if ((int64_t)n * 2 * C >= (1ll << 31)) return GNN_ERR_TOO_LARGE;    // 32-bit row offsets
     cudaStream_t st = gnn_stream(stream);
-    const size_t smem = (size_t)GNN_NUM_BOND_CODES * C * sizeof(float);
     int64_t blocks = gnn_ceil_div(n, AGG_WARPS);
-    if (smem <= 200 * 1024) {
-        auto kern = pna_aggregate_bwd_kernel<true>;
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return (int)e;
-        }
-        int per_sm = (int)((220 * 1024) / (smem + 1024));
-        if (per_sm < 1) per_sm = 1;
-        if (per_sm > 4) per_sm = 4;
-        int64_t cap = (int64_t)gnn_sm_count() * per_sm;
-        if (blocks > cap) blocks = cap;
-        kern<<<(unsigned)blocks, AGG_THREADS, smem, st>>>(gA, P, tab, A, rowptr, col_src, col_code, n, C, F, dP, dq,
-                                                          dtab_accum);
-    } else {
-        int64_t cap = (int64_t)gnn_sm_count() * 8;
-        if (blocks > cap) blocks = cap;
-        pna_aggregate_bwd_kernel<false><<<(unsigned)blocks, AGG_THREADS, 0, st>>>(gA, P, tab, A, rowptr, col_src,
-                                                                                  col_code, n, C, F, dP, dq, dtab_accum);
-    }
+    int64_t cap = (int64_t)gnn_sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    float* parts = reinterpret_cast<float*>(zeroed_workspace);
+    pna_aggregate_bwd_kernel<<<(unsigned)blocks, AGG_THREADS, 0, st>>>(gA, P, tab, A, rowptr, col_src, col_code, n, C, F,
+                                                                       dP, dq, parts);
+    const int total = GNN_NUM_BOND_CODES * C;
+    dtab_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(parts, total, dtab_accum);
     return gnn_launch_status();
 }
 

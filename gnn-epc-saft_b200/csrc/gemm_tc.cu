@@ -24,12 +24,11 @@ constexpr int BM = 128;          // UMMA M (cta_group::1), one TMEM lane per row
 constexpr int ROW_BYTES = 128;   // bytes of K per row per k-block (32 tf32 or 64 bf16) = one SWIZZLE_128B row
 constexpr int CHUNKS = ROW_BYTES / 16;
 // warp roles of the persistent CTA
-constexpr int EPI_WARPS = 4;                 // warps 0-3: TMEM -> registers -> smem -> coalesced global
-constexpr int MMA_WARP = 4;                  // warp 4: one elected lane issues tcgen05.mma
+constexpr int EPI_WARPS = 8;                 // warps 0-7: TMEM -> registers -> global (warp w: lane quarter w & 3, column half w >> 2)
+constexpr int MMA_WARP = 8;                  // warp 8: one elected lane issues tcgen05.mma
 constexpr int PROD_GROUPS = 4;               // warps 5-20: four producer groups take k-blocks round-robin
 constexpr int PROD_GROUP_THREADS = 128;
 constexpr int THREADS = (EPI_WARPS + 1) * 32 + PROD_GROUPS * PROD_GROUP_THREADS;   // 416
-constexpr int STG_COLS = 32, STG_LD = 36;    // epilogue staging block per warp: 32 rows x 32 columns (+pad)
 enum { MODE_TF32X3 = 0, MODE_BF16 = 1 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -57,7 +56,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
@@ -106,15 +105,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// fp32 -> tf32 hi + tf32 lo, both rounded to nearest (cvt.rna): v = hi + lo + O(2^-22 |v|)
+// fp32 -> tf32 hi + lo.  hi = x rounded to nearest (ties away) on a 10-bit mantissa with two integer ops
+// (cvt.rna.tf32.f32 expands to a long special-case sequence on this target); lo = x - hi is exact in fp32 and the
+// tensor core reads its top 19 bits:  x = hi + lo + O(2^-21 |x|).
 __device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
     hi = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-    lo = make_float4(tf32_rn(v.x - hi.x), tf32_rn(v.y - hi.y), tf32_rn(v.z - hi.z), tf32_rn(v.w - hi.w));
+    lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout):
@@ -470,6 +469,7 @@ struct Geom {
     int N, BN, splits, groups, m_tiles, n_tiles, stages;
     uint32_t tmem_cols;
     ColSum colsum;
+    unsigned long long* prof;    // optional cycle counters (debug): see gnn_tc_set_profile_buffer
 };
 
 // ------------------------------------------------------------------ operand producers
@@ -555,37 +555,52 @@ __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_
 
 // K-major A tile from a segmented operand: 128 rows (nodes m0..) x one k-block of columns.  Thread p owns the
 // 16-byte chunk c = p & 7 of rows r0 + 16 i: every load is a 128-bit coalesced access (8 lanes = 128 contiguous
-// bytes of one row), all eight are issued before the first conversion, smem offsets are compile-time strides.
-template <int MODE>
+// bytes of one row), all eight are issued before the first conversion, addresses advance by a constant stride and
+// smem offsets are compile-time strides.  Full tiles take a branch-free path.
+template <int MODE, bool SCALED>
 __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes,
                                               int64_t m0, int64_t kbase, int64_t k_end, int p) {
     constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
     const int c = p & 7, r0 = p >> 3;
     const int64_t k = kbase + c * EPC;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    SegRef s0 = k < k_end ? seg_resolve(op, k, grp) : SegRef{nullptr, 0, -1};
-    SegRef s1 = (MODE == MODE_BF16 && k + 4 < k_end) ? seg_resolve(op, k + 4, grp) : SegRef{nullptr, 0, -1};
+    const SegRef s0 = k < k_end ? seg_resolve(op, k, grp) : SegRef{nullptr, 0, -1};
+    const SegRef s1 = (MODE == MODE_BF16 && k + 4 < k_end) ? seg_resolve(op, k + 4, grp) : SegRef{nullptr, 0, -1};
     const int64_t row0 = m0 + r0;
     const uint32_t off0 = (uint32_t)r0 * ROW_BYTES + (uint32_t)((c ^ (r0 & 7)) << 4);   // (r0 + 16 i) & 7 == r0 & 7
+    const float* q0 = s0.ptr != nullptr ? s0.ptr + row0 * s0.ld : nullptr;
+    const float* q1 = s1.ptr != nullptr ? s1.ptr + row0 * s1.ld : nullptr;
+    const int64_t st0 = 16 * s0.ld, st1 = 16 * s1.ld;
+    const bool full = m0 + BM <= op.rows;
     float4 v[8], w[MODE == MODE_BF16 ? 8 : 1];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int64_t row = row0 + 16 * i;
-        v[i] = (s0.ptr != nullptr && row < op.rows) ? ldg4(s0.ptr + row * s0.ld) : zero;
-        if (MODE == MODE_BF16) w[i] = (s1.ptr != nullptr && row < op.rows) ? ldg4(s1.ptr + row * s1.ld) : zero;
-    }
-    if (s0.scale >= 0 || (MODE == MODE_BF16 && s1.scale >= 0)) {
+    if (full) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int64_t row = row0 + 16 * i;
-            if (row < op.rows) {
-                if (s0.scale >= 0) {
-                    const float f = __ldg(op.scal + 2 * row + s0.scale);
-                    v[i] = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
-                }
-                if (MODE == MODE_BF16 && s1.scale >= 0) {
-                    const float f = __ldg(op.scal + 2 * row + s1.scale);
-                    w[i] = make_float4(w[i].x * f, w[i].y * f, w[i].z * f, w[i].w * f);
+            v[i] = q0 != nullptr ? ldg4(q0 + i * st0) : zero;
+            if (MODE == MODE_BF16) w[i] = q1 != nullptr ? ldg4(q1 + i * st1) : zero;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const bool ok = row0 + 16 * i < op.rows;
+            v[i] = (ok && q0 != nullptr) ? ldg4(q0 + i * st0) : zero;
+            if (MODE == MODE_BF16) w[i] = (ok && q1 != nullptr) ? ldg4(q1 + i * st1) : zero;
+        }
+    }
+    if (SCALED) {
+        if (s0.scale >= 0 || (MODE == MODE_BF16 && s1.scale >= 0)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t row = row0 + 16 * i;
+                if (row < op.rows) {
+                    if (s0.scale >= 0) {
+                        const float f = __ldg(op.scal + 2 * row + s0.scale);
+                        v[i] = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
+                    }
+                    if (MODE == MODE_BF16 && s1.scale >= 0) {
+                        const float f = __ldg(op.scal + 2 * row + s1.scale);
+                        w[i] = make_float4(w[i].x * f, w[i].y * f, w[i].z * f, w[i].w * f);
+                    }
                 }
             }
         }
@@ -601,14 +616,15 @@ __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uin
 // MN-major tile from a segmented operand (weight gradients: the reduction index is the node).
 // R = MN extent of the tile in {32, 64, 128, 256}, KB K-rows (nodes kbase..).  Layout: [K group][MN group of
 // 128 B][KR rows x 128 B], KR = 4 K rows per atom for tf32 (SWIZZLE_128B_BASE32B: 32-byte chunks XOR (k & 3)),
-// 8 for bf16 (16-byte chunks XOR (k & 7)).  Thread p owns one 16-byte MN chunk and walks nodes: plain coalesced
-// vector copies, no transposition.
-template <int MODE>
+// 8 for bf16 (16-byte chunks XOR (k & 7)).  Thread p owns one 16-byte MN chunk and walks nodes with a constant
+// pointer stride: plain coalesced vector copies, no transposition.
+template <int MODE, bool SCALED>
 __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes, int R,
                                                int64_t mn0, int64_t kbase, int64_t k_end, int p, float4* colacc = nullptr) {
     constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
     constexpr int KB = MODE == MODE_TF32X3 ? 32 : 64;
     constexpr int KR = MODE == MODE_TF32X3 ? 4 : 8;
+    constexpr int KR_SHIFT = MODE == MODE_TF32X3 ? 2 : 3;
     constexpr uint32_t ATOM = KR * 128;
     const int cpr = R / EPC;                                     // chunks per K row: power of two, 4..64
     const int ch = p & (cpr - 1), kk0 = p / cpr, step = PROD_GROUP_THREADS / cpr;
@@ -617,24 +633,37 @@ __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, ui
     const int64_t col = mn0 + (int64_t)ch * EPC;
     const SegRef s0 = seg_resolve(op, col, grp);
     const SegRef s1 = MODE == MODE_BF16 ? seg_resolve(op, col + 4, grp) : SegRef{nullptr, 0, -1};
-    const int mg = ch >> 3, c8 = ch & 7;
+    const int c8 = ch & 7;
+    const uint32_t mg_off = (uint32_t)(ch >> 3) * ATOM;
     const int64_t lim = k_end < op.rows ? k_end : op.rows;
-    for (int kb0 = kk0; kb0 < KB; kb0 += 8 * step) {
+    const bool full = kbase + KB <= lim;
+    const float* q0 = s0.ptr != nullptr ? s0.ptr + (kbase + kk0) * s0.ld : nullptr;
+    const float* q1 = s1.ptr != nullptr ? s1.ptr + (kbase + kk0) * s1.ld : nullptr;
+    const int64_t st0 = (int64_t)step * s0.ld, st1 = (int64_t)step * s1.ld;
+    for (int j0 = 0; kk0 + j0 * step < KB; j0 += 8) {
         float4 v[8], w[MODE == MODE_BF16 ? 8 : 1];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int kk = kb0 + i * step;
-            const int64_t k = kbase + kk;
-            const bool ok = kk < KB && k < lim;
-            v[i] = (ok && s0.ptr != nullptr) ? ldg4(s0.ptr + k * s0.ld) : zero;
-            if (MODE == MODE_BF16) w[i] = (ok && s1.ptr != nullptr) ? ldg4(s1.ptr + k * s1.ld) : zero;
-            if (ok && s0.scale >= 0) {
-                const float f = __ldg(op.scal + 2 * k + s0.scale);
-                v[i] = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
-            }
-            if (MODE == MODE_BF16 && ok && s1.scale >= 0) {
-                const float f = __ldg(op.scal + 2 * k + s1.scale);
-                w[i] = make_float4(w[i].x * f, w[i].y * f, w[i].z * f, w[i].w * f);
+            const int kk = kk0 + (j0 + i) * step;
+            const bool ok = kk < KB && (full || kbase + kk < lim);
+            v[i] = (ok && q0 != nullptr) ? ldg4(q0 + (j0 + i) * st0) : zero;
+            if (MODE == MODE_BF16) w[i] = (ok && q1 != nullptr) ? ldg4(q1 + (j0 + i) * st1) : zero;
+        }
+        if (SCALED) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int kk = kk0 + (j0 + i) * step;
+                const int64_t k = kbase + kk;
+                if (kk < KB && k < lim) {
+                    if (s0.scale >= 0) {
+                        const float f = __ldg(op.scal + 2 * k + s0.scale);
+                        v[i] = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
+                    }
+                    if (MODE == MODE_BF16 && s1.scale >= 0) {
+                        const float f = __ldg(op.scal + 2 * k + s1.scale);
+                        w[i] = make_float4(w[i].x * f, w[i].y * f, w[i].z * f, w[i].w * f);
+                    }
+                }
             }
         }
         if (colacc != nullptr) {                                  // running column sums (bias gradient)
@@ -648,12 +677,12 @@ __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, ui
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int kk = kb0 + i * step;
+            const int kk = kk0 + (j0 + i) * step;
             if (kk < KB) {
                 const int kr = kk & (KR - 1);
                 const uint32_t swz = MODE == MODE_TF32X3 ? (uint32_t)((((c8 >> 1) ^ kr) << 5) | ((c8 & 1) << 4))
                                                          : (uint32_t)((c8 ^ kr) << 4);
-                const uint32_t off = (uint32_t)(kk / KR) * kgs + (uint32_t)mg * ATOM + (uint32_t)kr * 128u + swz;
+                const uint32_t off = (uint32_t)(kk >> KR_SHIFT) * kgs + mg_off + (uint32_t)kr * 128u + swz;
                 if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, off, v[i]);
                 else put_chunk_bf16(tile, off, v[i], w[MODE == MODE_BF16 ? i : 0]);
             }
@@ -683,7 +712,7 @@ pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t*
     produce_tile<MODE>(bl, tile, b_plane, BN, (int64_t)nt * BN, (int64_t)kb * KB_ELEMS, K, threadIdx.x);
 }
 
-template <int MODE, bool PACKED, bool MN_MAJOR, class BL, class EP>
+template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b) {
     extern __shared__ uint8_t smem_raw[];
@@ -694,11 +723,11 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
     constexpr int PARTS = MODE == MODE_TF32X3 ? 2 : 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int BN = g.BN, NS = g.stages;
+    const long long kernel_t0 = g.prof ? clock64() : 0;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_plane = BM * ROW_BYTES, b_plane = (uint32_t)BN * ROW_BYTES;
     const uint32_t stage_bytes = PARTS * (a_plane + b_plane);        // multiple of 1024 (BN % 16 == 0)
-    float* stg_all = reinterpret_cast<float*>(smem + (size_t)NS * stage_bytes);
 
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, g.tmem_cols);
     if (tid == 0) {
@@ -731,7 +760,10 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
 
     if (warp < EPI_WARPS) {
         // =============================== epilogue ===============================
-        float* stg = stg_all + warp * (32 * STG_LD);
+        // thread = one accumulator row (TMEM lane); warp w reads lane quarter w & 3 and the 16-column chunks
+        // c = (w >> 2), (w >> 2) + 2, ...; values go straight from registers to global memory (each lane writes
+        // 64 contiguous bytes of its row per chunk)
+        const int q = warp & 3, half = warp >> 2;
         uint32_t t = 0;
         for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) {
             int64_t m0, k_begin, k_end;
@@ -740,56 +772,48 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             EP ep = ep0;
             ep.set_group(grp);
             const uint32_t b = t & 1, tuse = t >> 1;
+            const long long et0 = g.prof ? clock64() : 0;
             mbar_wait(&tmem_full_bar[b], tuse & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + b * (uint32_t)BN + ((uint32_t)(warp * 32) << 16);
-            const int64_t m_thread = m0 + warp * 32 + lane;
+            const long long et1 = g.prof ? clock64() : 0;
+            const uint32_t taddr = tmem_base + b * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+            const int64_t m = m0 + q * 32 + lane;
+            const bool row_ok = m < g.M;
             const int out_cols = EP::kCombine3 ? BN / 3 : BN;          // columns that are written out
             float amp = 0.f, att = 0.f;
             if constexpr (EP::kCombine3) {
-                if (m_thread < g.M) ep.scalers(m_thread, amp, att);
+                if (row_ok) ep.scalers(m, amp, att);
             }
-            for (int cb = 0; cb < out_cols; cb += STG_COLS) {
-                // thread = one row: 32 columns of the block into the staging tile
+            long long ld_cyc = 0;
+            for (int col = half * 16; col < out_cols; col += 32) {
+                float v[16];
+                const long long lt0 = g.prof ? clock64() : 0;
+                tmem_ld16(taddr + col, v);
+                if (g.prof) ld_cyc += clock64() - lt0;
+                if constexpr (EP::kCombine3) {
+                    float d1[16], d2[16];
+                    tmem_ld16(taddr + out_cols + col, d1);
+                    tmem_ld16(taddr + 2 * out_cols + col, d2);
 #pragma unroll
-                for (int h = 0; h < STG_COLS / 16; ++h) {
-                    const int col = cb + h * 16;
-                    float v[16];
-                    if (col < out_cols) {
-                        tmem_ld16(taddr + col, v);
-                        if constexpr (EP::kCombine3) {
-                            float d1[16], d2[16];
-                            tmem_ld16(taddr + out_cols + col, d1);
-                            tmem_ld16(taddr + 2 * out_cols + col, d2);
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) v[j] = v[j] + amp * d1[j] + att * d2[j];
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        *reinterpret_cast<float4*>(stg + lane * STG_LD + h * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 16; ++j) v[j] = v[j] + amp * d1[j] + att * d2[j];
                 }
-                __syncwarp();
-                // write-out: 8 lanes per row (128 contiguous bytes), 4 rows per pass
-                const int cq = (lane & 7) * 4, rsub = lane >> 3;
-#pragma unroll 2
-                for (int rr = 0; rr < 32; rr += 4) {
-                    const int r = rr + rsub;
-                    const int64_t m = m0 + warp * 32 + r;
-                    const int col = cb + cq;
-                    if (m < g.M && col < out_cols) {
-                        float4 v = *reinterpret_cast<const float4*>(stg + r * STG_LD + cq);
-                        if constexpr (EP::kCombine3) ep.emit4(m, (int)(n0 / 3) + col, g.N, v);
-                        else if (n0 + col < g.N) ep.emit4(m, n0 + col, g.N, v);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 v4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if constexpr (EP::kCombine3) ep.emit4(m, (int)(n0 / 3) + col + j, g.N, v4);
+                        else if (n0 + col + j < g.N) ep.emit4(m, n0 + col + j, g.N, v4);
                     }
                 }
-                __syncwarp();
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[b]);
+            if (g.prof && tid == 0) {
+                atomicAdd(g.prof + 6, (unsigned long long)(et1 - et0));             // epilogue waiting for the accumulator
+                atomicAdd(g.prof + 7, (unsigned long long)(clock64() - et1));       // epilogue work
+                atomicAdd(g.prof + 8, 1ull);
+                atomicAdd(g.prof + 11, (unsigned long long)ld_cyc);                 // ... of which first tcgen05.ld + wait per chunk
+            }
         }
     } else if (warp == MMA_WARP) {
         // =============================== MMA issuer ===============================
@@ -806,8 +830,13 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             const uint32_t tmem_d = tmem_base + b * (uint32_t)BN;
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 const uint32_t s = it % NS, use = it / NS;
+                const long long mt0 = g.prof ? clock64() : 0;
                 mbar_wait(&full_bar[s], use & 1);
                 tc_fence_after();
+                if (g.prof && lane == 0) {
+                    atomicAdd(g.prof + 4, (unsigned long long)(clock64() - mt0));   // MMA warp waiting for operands
+                    atomicAdd(g.prof + 5, 1ull);
+                }
                 if (lane == 0) {
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + a_plane;
                     const uint32_t b_hi = a_hi + PARTS * a_plane, b_lo = b_hi + b_plane;
@@ -868,7 +897,9 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 if ((int)(it % NS) != pg) continue;                // group pg owns ring stage pg (see below)
                 const uint32_t s = it % NS, use = it / NS;
+                const long long pt0 = g.prof ? clock64() : 0;
                 if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+                const long long pt1 = g.prof ? clock64() : 0;
                 uint8_t* stage = smem + (size_t)s * stage_bytes;
                 const int64_t kbase = k_begin + (int64_t)kb * KB_ELEMS;
                 if constexpr (PACKED) {
@@ -879,16 +910,23 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         mbar_expect_tx(&full_bar[s], bytes);
                         bulk_g2s(stage + PARTS * a_plane, packed_b + tile_idx * bytes, bytes, &full_bar[s]);
                     }
-                    produce_a_seg<MODE>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
+                    produce_a_seg<MODE, SCALED>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
                 } else if constexpr (MN_MAJOR) {
-                    produce_mn_seg<MODE>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p, do_colsum ? colacc : nullptr);
-                    produce_mn_seg<MODE>(bl, grp, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
+                    produce_mn_seg<MODE, SCALED>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p, do_colsum ? colacc : nullptr);
+                    produce_mn_seg<MODE, false>(bl, grp, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
                 } else {
-                    produce_a_seg<MODE>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
+                    produce_a_seg<MODE, SCALED>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
                     produce_tile<MODE>(bl, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
                 }
+                const long long pt2 = g.prof ? clock64() : 0;
                 fence_async_smem();                                 // generic-proxy writes -> async (tensor core) proxy
                 mbar_arrive(&full_bar[s]);
+                if (g.prof && p == 0) {
+                    atomicAdd(g.prof + 0, (unsigned long long)(pt1 - pt0));     // wait for a free stage
+                    atomicAdd(g.prof + 1, (unsigned long long)(pt2 - pt1));     // load + convert + store
+                    atomicAdd(g.prof + 2, (unsigned long long)(clock64() - pt2));   // fence + arrive
+                    atomicAdd(g.prof + 3, 1ull);
+                }
             }
             if constexpr (MN_MAJOR) {
                 if (do_colsum && pg < NS) {                         // flush this thread's column chunk
@@ -912,13 +950,18 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, g.tmem_cols);
+    if (g.prof && tid == 0) {
+        atomicAdd(g.prof + 9, (unsigned long long)(clock64() - kernel_t0));
+        atomicAdd(g.prof + 10, 1ull);
+    }
 }
 
 // ------------------------------------------------------------------ host side
 static const size_t kSmemLimit = 232448;     // 227 KB opt-in maximum per CTA
+static unsigned long long* g_prof = nullptr; // debug only: per-role cycle counters of the next launches
 
 // BL: K-major weight functor (packed through pack_ws when possible) or, for MN_MAJOR, a SegOperand
-template <int MODE, bool MN_MAJOR = false, class BL, class EP>
+template <int MODE, bool MN_MAJOR = false, bool SCALED = false, class BL, class EP>
 static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN, int64_t K, int64_t k_chunk, int splits,
                   int groups, cudaStream_t st, void* pack_ws = nullptr, int64_t pack_ws_bytes = 0,
                   ColSum colsum = ColSum{nullptr, 0, 0, 0, 1}) {
@@ -927,7 +970,7 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
     constexpr int parts = MODE == MODE_TF32X3 ? 2 : 1;
     constexpr int kb_elems = MODE == MODE_TF32X3 ? 32 : 64;
     const size_t stage_bytes = (size_t)parts * (BM + BN) * ROW_BYTES;
-    const size_t fixed = 4 * 32 * STG_LD * sizeof(float) + 1024 + 256;
+    const size_t fixed = 1024 + 256;
     int stages = (int)((kSmemLimit - fixed) / stage_bytes);
     if (stages > PROD_GROUPS) stages = PROD_GROUPS;      // one producer group per ring stage
     if (stages < 2) return GNN_ERR_UNSUPPORTED;
@@ -941,12 +984,13 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
     while ((int)cols < 2 * BN) cols <<= 1;
     g.tmem_cols = cols;
     g.colsum = colsum;
+    g.prof = g_prof;
     const size_t smem = (size_t)stages * stage_bytes + fixed;
     int64_t grid = g.num_items < gnn_sm_count() ? g.num_items : gnn_sm_count();
 
     if constexpr (MN_MAJOR) {
         if ((BN & (BN - 1)) != 0 || BN < (MODE == MODE_TF32X3 ? 32 : 64)) return GNN_ERR_UNSUPPORTED;   // whole 128-byte groups
-        auto kern = gemm_tc_kernel<MODE, false, true, BL, EP>;
+        auto kern = gemm_tc_kernel<MODE, false, true, SCALED, BL, EP>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, nullptr);
@@ -960,12 +1004,12 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             dim3 pgrid((unsigned)num_kb, (unsigned)g.n_tiles, (unsigned)groups);
             pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
                                                                           reinterpret_cast<uint8_t*>(pack_ws));
-            auto kern = gemm_tc_kernel<MODE, true, false, BL, EP>;
+            auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws));
         } else {
-            auto kern = gemm_tc_kernel<MODE, false, false, BL, EP>;
+            auto kern = gemm_tc_kernel<MODE, false, false, SCALED, BL, EP>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, nullptr);
@@ -1149,7 +1193,7 @@ extern "C" int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const f
         EStore ep{gA, (int64_t)towers * 4 * F, 4 * (int64_t)F, nullptr, 0, 0, 0, is_vec(gA, 0)};
         const int BN = pick_bn(4 * F);
         int rc;
-        DISPATCH_MODE(precision, rc = (launch<MODE>(aop, bl, ep, n, 4 * F, BN, 3 * (int64_t)F_out, 3 * (int64_t)F_out, 1,
+        DISPATCH_MODE(precision, rc = (launch<MODE, false, true>(aop, bl, ep, n, 4 * F, BN, 3 * (int64_t)F_out, 3 * (int64_t)F_out, 1,
                                                     towers, st, pack_ws, pack_ws_bytes)));
         if (rc) return rc;
     }
@@ -1262,7 +1306,7 @@ extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const floa
             const int BN = pick_bn_mn(4 * F, MODE);
             const int64_t tiles = gnn_ceil_div(4 * F, BN) * gnn_ceil_div(3 * FoP, BM) * towers;
             splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
-            rc = (launch<MODE, true>(aop, bop, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st, nullptr, 0,
+            rc = (launch<MODE, true, true>(aop, bop, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st, nullptr, 0,
                                      ColSum{dbpost, bpost_tower_stride, 0, dbpost ? F_out : 0, F_out}));
         });
         if (rc) return rc;
@@ -1285,5 +1329,13 @@ extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const floa
         });
         if (rc) return rc;
     }
+    return 0;
+}
+
+// debug: 16 x uint64 device buffer that receives per-role cycle counters of subsequent tensor-core GEMM launches
+// (NULL disables).  [0] producer wait-for-stage, [1] produce, [2] fence+arrive, [3] #k-blocks (per group leader),
+// [4] MMA wait-for-operands, [5] #k-blocks, [6] epilogue wait, [7] epilogue work, [8] #items, [9] CTA cycles, [10] #CTAs
+extern "C" int gnn_tc_set_profile_buffer(void* buf) {
+    tc::g_prof = reinterpret_cast<unsigned long long*>(buf);
     return 0;
 }

@@ -211,6 +211,14 @@ class _Workspace:
             self.buf[(key, device)] = t
         return t
 
+    def get_zeroed(self, key, nbytes, device):
+        """Scratch whose users leave it all-zero (so it is cleared only when (re)allocated)."""
+        t = self.buf.get((key, device))
+        if t is None or t.numel() < nbytes:
+            t = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self.buf[(key, device)] = t
+        return t
+
 
 _WS = _Workspace()
 PACK_WS_BYTES = 4 << 20
@@ -651,8 +659,10 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
         dP = torch.empty(n, 2 * C, **f32)
         if pp.pre_layers == 1:
             dq = torch.empty(max(g.ep, 1), C, **f32)
+            nb = _lib.query("gnn_pna_aggregate_bwd_workspace_bytes", T, F)
+            zws = _WS.get_zeroed("aggbwd", nb, dev)         # kept all-zero by the kernel pair itself
             _c("gnn_pna_aggregate_bwd", gA, rec.P, sv.tab[l], rec.A, g.rowptr, g.col_src, g.col_code, n, T, F, dP,
-               dq, dtab[l])
+               dq, dtab[l], zws, zws.numel())
         else:
             hs = rec.hs
             dm = torch.empty(max(g.ep, 1), C, **f32)

@@ -126,11 +126,14 @@ int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int32_t* rowpt
                           int towers, int F, float* A, void* stream);
 /* Backward: gA [N,towers,4,F] -> dP[:, 0:C] (dst part), dq [E',C] per CSR slot and
  * dtab_accum [60,C] (+=, caller zeroes).  min/max gradients are split evenly over ties
- * (torch scatter_reduce amin/amax semantics). */
+ * (torch scatter_reduce amin/amax semantics).  `zeroed_workspace` holds partial bond-code
+ * tables; it must be all-zero on entry and is all-zero again on exit. */
+int64_t gnn_pna_aggregate_bwd_workspace_bytes(int towers, int F);
 int gnn_pna_aggregate_bwd(const float* gA, const float* P, const float* tab, const float* A,
                           const int32_t* rowptr, const int32_t* col_src,
                           const uint8_t* col_code, int64_t num_nodes, int towers, int F,
-                          float* dP, float* dq, float* dtab_accum, void* stream);
+                          float* dP, float* dq, float* dtab_accum, void* zeroed_workspace,
+                          int64_t workspace_bytes, void* stream);
 /* dP[:, C:2C][j] = sum over out-edges of j of dq[slot] (deterministic order) */
 int gnn_scatter_src_bwd(const float* dq, const int32_t* srcptr, const int32_t* src_slot,
                         int64_t num_nodes, int C, float* dP, void* stream);
@@ -226,6 +229,10 @@ int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const
                           int64_t num_nodes, int F, int F_out, int towers, float* dwpost,
                           int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride,
                           int precision, void* stream);
+
+/* Debug aid: 16 x uint64 device buffer that receives per-role cycle counters (producers / MMA issuer /
+ * epilogue) of subsequent tensor-core GEMM launches; NULL disables.  Process-global, not for production. */
+int gnn_tc_set_profile_buffer(void* buf);
 
 /* Fused projection stage of PNAConv (pre_nns[t][0], first two thirds of its input), all towers in one
  * launch.  wpre / bpre point at tower 0 of the layer, towers are *_tower_stride floats apart.

@@ -222,8 +222,12 @@ def _agg_grad(q, ga_row, sd, towers, f):
     return dq, g_mean + g_min + g_max
 
 
+def gnn_pna_aggregate_bwd_workspace_bytes(towers, f):
+    return 256
+
+
 def gnn_pna_aggregate_bwd(gA, P, tab, A, rowptr, col_src, col_code, n, towers, f, dP, dq, dtab_accum,
-                          stream=None):
+                          workspace=None, workspace_bytes=0, stream=None):
     c = towers * f
     for i, (b, e) in enumerate(_segments(rowptr, n)):
         if e == b:

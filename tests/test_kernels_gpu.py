@@ -219,12 +219,15 @@ def test_aggregate_fwd_bwd(n, e, T, F, loops, quant):
     gA = torch.randn(n, T * 4 * F)
     dP, dq, dtab = torch.zeros(n, 2 * C), torch.zeros(max(ep, 1), C), torch.zeros(60, C)
     # feed the CUDA forward's A to both sides so that only the backward arithmetic is compared
+    nb = _lib.query("gnn_pna_aggregate_bwd_workspace_bytes", T, F)
+    zws = torch.zeros(nb, dtype=torch.uint8)
     cpu, gpu = run_both("gnn_pna_aggregate_bwd", gA, P, tab, A_gpu, ref["rowptr"], ref["col_src"], ref["col_code"], n,
-                        T, F, dP, dq, dtab)
-    close(gpu[-3][:, :C], cpu[-3][:, :C], 1e-5, "dPdst")
-    close(gpu[-2][:ep], cpu[-2][:ep], 2e-5, "dq")
-    close(gpu[-1], cpu[-1], 1e-4, "dtab")
-    dq_gpu = gpu[-2].cpu()
+                        T, F, dP, dq, dtab, zws, nb)
+    close(gpu[-5][:, :C], cpu[-5][:, :C], 1e-5, "dPdst")
+    close(gpu[-4][:ep], cpu[-4][:ep], 2e-5, "dq")
+    close(gpu[-3], cpu[-3], 1e-4, "dtab")
+    assert int(gpu[-2].count_nonzero()) == 0, "workspace must be left all-zero"
+    dq_gpu = gpu[-4].cpu()
     dP2 = torch.zeros(n, 2 * C)
     cpu, gpu = run_both("gnn_scatter_src_bwd", dq_gpu, ref["srcptr"], ref["src_slot"], n, C, dP2)
     close(gpu[-1][:, C:], cpu[-1][:, C:], 1e-5, "dPsrc")
