@@ -97,72 +97,115 @@ __device__ __forceinline__ void seg_finish(const SegStat& st, int cnt, float4 pd
     store_aggregates(A, node, C, F, c, mean, add4(st.mn, pd), add4(st.mx, pd), sd);
 }
 
-// one warp per destination node, 128 channels per pass; the gather of edge k+1 is in flight while edge k
-// is accumulated (software pipelining), indices come from one lane-parallel load + shuffles.
+// one warp per destination node, NCHUNK x 128 channels; the gather of edge k+1 is in flight while edge k is
+// accumulated (software pipelining), indices come from one lane-parallel load + shuffles, and everything that
+// does not depend on the node (channel -> tower/feature split, column pointers) is hoisted out of the node loop.
+// Measured on B200 (tools/agg_probe.py, ncu): the kernel is bound by instruction issue / the per-node dependent
+// chain rather than by DRAM; variants tried and rejected: 8-node edge streams per warp (register pressure),
+// higher occupancy via register caps (spills), cross-node index prefetch, two nodes per warp.
+template <int NCHUNK>
 __global__ void __launch_bounds__(AGG_THREADS, 4)
 pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ tab,
                          const int* __restrict__ rowptr, const int* __restrict__ col_src,
-                         const uint8_t* __restrict__ col_code, int64_t n, int C, int F, float* __restrict__ A) {
+                         const uint8_t* __restrict__ col_code, int n, int C, int F, float* __restrict__ A) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t)blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * AGG_WARPS;
-    const int ldp = 2 * C;
-    for (int64_t node = warp0; node < n; node += nwarps) {
+    const int warp0 = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * AGG_WARPS;
+    const int ldp = 2 * C, lda = 4 * C;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cj[NCHUNK], aoff[NCHUNK];
+    bool live[NCHUNK];
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+        cj[j] = j * 128 + lane * 4;
+        live[j] = cj[j] < C;
+        const int t = cj[j] / F;
+        aoff[j] = t * 4 * F + (cj[j] - t * F);            // A[node][t][agg][f]
+    }
+    for (int node = warp0; node < n; node += nwarps) {
         const int rp = __ldg(rowptr + node + (lane & 1));
         const int beg = __shfl_sync(GNN_FULL_MASK, rp, 0), end = __shfl_sync(GNN_FULL_MASK, rp, 1);
         const int cnt = end - beg;
-        // row offsets of the first 32 in-edges (all of them for molecular graphs), pre-scaled
-        int my_src = 0, my_code = 0;
+        int my_src = 0, my_code = 0;                      // pre-scaled element offsets of the first 32 in-edges
         if (lane < cnt) {
             my_src = __ldg(col_src + beg + lane) * ldp + C;
             my_code = (int)__ldg(col_code + beg + lane) * C;
         }
-        for (int cb = 0; cb < C; cb += 128) {                  // warp-uniform trip count (shuffles inside)
-            const int c = cb + lane * 4;
-            const bool live = c < C;
-            const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        float* const arow = A + (size_t)node * lda;
+        const float* const prow = P + (size_t)node * ldp;
+        const int m = min(cnt, 32);
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            float* const out = arow + aoff[j];
             if (cnt == 0) {
-                if (live) store_aggregates(A, node, C, F, c, zero, zero, zero, zero);
+                if (live[j]) {
+                    st4_stream(out, zero);
+                    st4_stream(out + F, zero);
+                    st4_stream(out + 2 * F, zero);
+                    st4_stream(out + 3 * F, zero);
+                }
                 continue;
             }
-            const float* pbase = P + c;
-            const float* tbase = tab + c;
-            const float4 pd = live ? ldg4(pbase + node * ldp) : zero;
-            const int m = min(cnt, 32);
-            // edge 0 defines the shift
+            const float* const pbase = P + cj[j];
+            const float* const tbase = tab + cj[j];
+            const float4 pd = live[j] ? ldg4(prow + cj[j]) : zero;
             int so = __shfl_sync(GNN_FULL_MASK, my_src, 0), co = __shfl_sync(GNN_FULL_MASK, my_code, 0);
-            float4 pn = live ? ldg4(pbase + so) : zero, tn = live ? ldg4(tbase + co) : zero;
-            SegStat st;
+            float4 pn = live[j] ? ldg4(pbase + so) : zero, tn = live[j] ? ldg4(tbase + co) : zero;
+            // edge 0 defines the shift q0
+            float4 q0, s1 = zero, s2 = zero, mn, mx;
             {
-                const float4 pc = pn, tc_ = tn;
+                const float4 pc = pn, tcur = tn;
                 if (1 < m) {
                     so = __shfl_sync(GNN_FULL_MASK, my_src, 1);
                     co = __shfl_sync(GNN_FULL_MASK, my_code, 1);
-                    if (live) {
+                    if (live[j]) {
                         pn = ldg4(pbase + so);
                         tn = ldg4(tbase + co);
                     }
                 }
-                seg_first(st, add4(pc, tc_));
+                q0 = add4(pc, tcur);
+                mn = q0;
+                mx = q0;
             }
             for (int k = 1; k < m; ++k) {
-                const float4 pc = pn, tc_ = tn;
+                const float4 pc = pn, tcur = tn;
                 if (k + 1 < m) {                                           // warp-uniform: prefetch the next edge
                     so = __shfl_sync(GNN_FULL_MASK, my_src, k + 1);
                     co = __shfl_sync(GNN_FULL_MASK, my_code, k + 1);
-                    if (live) {
+                    if (live[j]) {
                         pn = ldg4(pbase + so);
                         tn = ldg4(tbase + co);
                     }
                 }
-                seg_add(st, add4(pc, tc_));
+                const float4 q = add4(pc, tcur);
+                const float dx = q.x - q0.x, dy = q.y - q0.y, dz = q.z - q0.z, dw = q.w - q0.w;
+                s1 = make_float4(s1.x + dx, s1.y + dy, s1.z + dz, s1.w + dw);
+                s2 = make_float4(fmaf(dx, dx, s2.x), fmaf(dy, dy, s2.y), fmaf(dz, dz, s2.z), fmaf(dw, dw, s2.w));
+                mn = make_float4(fminf(mn.x, q.x), fminf(mn.y, q.y), fminf(mn.z, q.z), fminf(mn.w, q.w));
+                mx = make_float4(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z), fmaxf(mx.w, q.w));
             }
-            // in-degree > 32 (never for molecules): plain loop over the remaining slots
-            for (int s = beg + 32; s < end; ++s) {
+            for (int s = beg + 32; s < end; ++s) {         // in-degree > 32 (never for molecules)
                 const int so2 = __ldg(col_src + s) * ldp + C, co2 = (int)__ldg(col_code + s) * C;
-                if (live) seg_add(st, add4(ldg4(pbase + so2), ldg4(tbase + co2)));
+                if (live[j]) {
+                    const float4 q = add4(ldg4(pbase + so2), ldg4(tbase + co2));
+                    const float dx = q.x - q0.x, dy = q.y - q0.y, dz = q.z - q0.z, dw = q.w - q0.w;
+                    s1 = make_float4(s1.x + dx, s1.y + dy, s1.z + dz, s1.w + dw);
+                    s2 = make_float4(fmaf(dx, dx, s2.x), fmaf(dy, dy, s2.y), fmaf(dz, dz, s2.z), fmaf(dw, dw, s2.w));
+                    mn = make_float4(fminf(mn.x, q.x), fminf(mn.y, q.y), fminf(mn.z, q.z), fminf(mn.w, q.w));
+                    mx = make_float4(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z), fmaxf(mx.w, q.w));
+                }
             }
-            if (live) seg_finish(st, cnt, pd, A, node, C, F, c);
+            if (live[j]) {
+                const float inv = __frcp_rn((float)cnt);
+                const float4 m1 = make_float4(s1.x * inv, s1.y * inv, s1.z * inv, s1.w * inv);
+                st4_stream(out, make_float4(q0.x + m1.x + pd.x, q0.y + m1.y + pd.y, q0.z + m1.z + pd.z, q0.w + m1.w + pd.w));
+                st4_stream(out + F, add4(mn, pd));
+                st4_stream(out + 2 * F, add4(mx, pd));
+                st4_stream(out + 3 * F, make_float4(pna_std_fast(fmaf(-m1.x, m1.x, s2.x * inv)),
+                                                    pna_std_fast(fmaf(-m1.y, m1.y, s2.y * inv)),
+                                                    pna_std_fast(fmaf(-m1.z, m1.z, s2.z * inv)),
+                                                    pna_std_fast(fmaf(-m1.w, m1.w, s2.w * inv))));
+            }
         }
     }
 }
@@ -186,7 +229,16 @@ extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int
     int64_t blocks = gnn_ceil_div(n, AGG_WARPS);
     int64_t cap = (int64_t)gnn_sm_count() * 48;
     if (blocks > cap) blocks = cap;
-    pna_aggregate_fwd_kernel<<<(unsigned)blocks, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, n, C, F, A);
+    const int chunks = (C + 127) / 128;
+#define LAUNCH_FWD(CH) pna_aggregate_fwd_kernel<CH><<<(unsigned)blocks, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, (int)n, C, F, A)
+    switch (chunks) {
+        case 1: LAUNCH_FWD(1); break;
+        case 2: LAUNCH_FWD(2); break;
+        case 3: case 4: LAUNCH_FWD(4); break;
+        case 5: case 6: case 7: case 8: LAUNCH_FWD(8); break;
+        default: return GNN_ERR_UNSUPPORTED;
+    }
+#undef LAUNCH_FWD
     return gnn_launch_status();
 }
 
