@@ -34,8 +34,10 @@ NUM_BATCHES = 4          # distinct batches cycled through, so nothing is reused
 METRIC = "molecular graphs/sec (train step: fwd+bwd+AdamW, fp32)"
 
 # kernels launched per C-ABI call (lower bounds where the count depends on sizes)
-KERNELS_PER_CALL = {"gnn_build_csr": 13, "gnn_graph_ptr_from_batch": 1, "gnn_bn_stats": 2, "gnn_bn_act_bwd": 3,
-                    "gnn_pna_post_dgrad": 3, "gnn_bond_table_bwd": 3, "gnn_fill_zero": 1}
+KERNELS_PER_CALL = {"gnn_build_csr": 11, "gnn_bn_stats": 2, "gnn_bn_act_bwd": 3, "gnn_bond_table_bwd": 3,
+                    "gnn_pna_aggregate_bwd": 2, "gnn_tc_linear_fwd": 2, "gnn_tc_linear_dgrad": 2,
+                    "gnn_tc_pna_post_fwd": 2, "gnn_tc_pna_post_dgrad": 2, "gnn_tc_pna_post_wgrad": 2,
+                    "gnn_tc_pna_proj_fwd": 2, "gnn_tc_pna_dx_dgrad": 2}
 
 
 def peaks():
@@ -157,10 +159,27 @@ def run_reference(args, rank):
                                        "the PyG op sequence; torch_geometric is not installable here)"},
             "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
+
+
+def _emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else a library prints (e.g. NCCL's version
+    banner) was redirected to stderr by _quiet_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -215,15 +234,15 @@ def main():
         return float(t.item())
 
     # ---------------- device-resident throughput (`value`)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                      # samples clocks from the warm-up through the timed region
     for i in range(args.warmup):
         engine.step(dev_batches[i % NUM_BATCHES])
     prof = M.KernelProfiler(watch=["gnn_pna_aggregate_fwd", "gnn_pna_aggregate_bwd"])
     M.set_profiler(prof)
     calls0 = M.ABI_CALLS
-    sampler = ClockSampler(local_rank)
     sync_all()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     loss = None
@@ -308,7 +327,7 @@ def main():
                 "gpu_launches": int(launches_per_step * args.steps), "abi_calls_per_step": calls_per_step,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernel_shares": shares,
                 "final_loss": final_loss}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
