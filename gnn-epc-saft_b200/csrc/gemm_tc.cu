@@ -50,6 +50,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 256-bit global store (STG.E.256): one full 32-byte sector per lane per instruction
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     const uint32_t addr = smem_u32(bar);
@@ -310,9 +316,31 @@ struct EStore {     // Y[m, n] = act(v + bias[n]) (+ Y)
     int64_t bias_group_stride;
     int act, accumulate, vec;
     static constexpr int kCombine3 = 0;
+    static constexpr int kWide = 1;
     __device__ __forceinline__ void set_group(int g) {
         y += (int64_t)g * y_group_stride;
         if (bias) bias += (int64_t)g * bias_group_stride;
+    }
+    // 16 consecutive columns as two 256-bit stores (rows 32-byte aligned, no read-modify-write)
+    __device__ __forceinline__ bool wide_ok(int n, int N) const {
+        return vec && !accumulate && n + 15 < N && ((ldy | y_group_stride) & 7) == 0 &&
+               ((reinterpret_cast<uintptr_t>(y) | (uintptr_t)(n * 4)) & 31) == 0;
+    }
+    __device__ __forceinline__ void store16(int64_t m, int n, float* v) const {
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 b = ldg4(bias + n + j);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+        }
+        if (act) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        float* dst = y + m * ldy + n;
+        st_global_v8(dst, v);
+        st_global_v8(dst + 8, v + 8);
     }
     __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
         float* dst = y + m * ldy + n;
@@ -342,7 +370,8 @@ struct EStore {     // Y[m, n] = act(v + bias[n]) (+ Y)
         }
     }
 };
-struct EAtomic {    // dW[m, n] += v
+struct EAtomic {
+    static constexpr int kWide = 0;    // dW[m, n] += v
     float* y;
     int64_t ldy, y_group_stride;
     int vec;
@@ -363,6 +392,7 @@ struct EAtomic {    // dW[m, n] += v
 // post forward: O[i, t*F_out + o] = act(D[i, o] + amp_i D[i, FoP+o] + att_i D[i, 2FoP+o] + b_t[o]);
 // the kernel combines the three scaler groups, emit4 adds bias / activation and stores.
 struct EPostCombine {
+    static constexpr int kWide = 0;
     float* O;
     const float* scal;
     const float* bias;
@@ -395,6 +425,7 @@ struct EPostCombine {
 };
 // post wgrad (A part): D[(s,o), r] -> dWpost_t[o, F + s*4F + r]  (rows are s*FoP + o); F % 4 == 0
 struct EPostWgrad {
+    static constexpr int kWide = 0;
     float* dw;
     int64_t tower_stride;
     int F, F_out, FoP, vec;
@@ -417,6 +448,25 @@ struct EPostWgrad {
 
 // fused projection forward: P[i, n] = acc + (n < C ? bpre_{t}[f] : 0), n = part*C + t*F + f
 struct EProjStore {
+    static constexpr int kWide = 1;
+    __device__ __forceinline__ bool wide_ok(int n, int N) const {
+        return n + 15 < N && (F & 15) == 0 && (reinterpret_cast<uintptr_t>(P) & 31) == 0;
+    }
+    __device__ __forceinline__ void store16(int64_t m, int n, float* v) const {
+        const int C = towers * F;
+        if (n < C) {                                       // F % 16 == 0: the 16 columns share one tower
+            const int t = n / F, f = n - t * F;
+            const float* b = bias + (int64_t)t * bias_tower_stride + f;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const float4 bb = ldg4(b + j);
+                v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            }
+        }
+        float* dst = P + m * (2 * (int64_t)C) + n;
+        st_global_v8(dst, v);
+        st_global_v8(dst + 8, v + 8);
+    }
     float* P;
     const float* bias;
     int64_t bias_tower_stride;
@@ -435,6 +485,7 @@ struct EProjStore {
 };
 // fused projection weight gradient: D[(part,t,f), kk] -> dWpre_t[f, part*F + kk]
 struct EProjWgrad {
+    static constexpr int kWide = 0;
     float* dw;
     int64_t tower_stride;
     int F, towers;
@@ -798,11 +849,20 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     for (int j = 0; j < 16; ++j) v[j] = v[j] + amp * d1[j] + att * d2[j];
                 }
                 if (row_ok) {
+                    bool done = false;
+                    if constexpr (EP::kWide) {
+                        if (ep.wide_ok(n0 + col, g.N)) {
+                            ep.store16(m, n0 + col, v);
+                            done = true;
+                        }
+                    }
+                    if (!done) {
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 v4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if constexpr (EP::kCombine3) ep.emit4(m, (int)(n0 / 3) + col + j, g.N, v4);
-                        else if (n0 + col + j < g.N) ep.emit4(m, n0 + col + j, g.N, v4);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float4 v4 = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if constexpr (EP::kCombine3) ep.emit4(m, (int)(n0 / 3) + col + j, g.N, v4);
+                            else if (n0 + col + j < g.N) ep.emit4(m, n0 + col + j, g.N, v4);
+                        }
                     }
                 }
             }
