@@ -24,11 +24,17 @@ constexpr int BM = 128;          // UMMA M (cta_group::1), one TMEM lane per row
 constexpr int ROW_BYTES = 128;   // bytes of K per row per k-block (32 tf32 or 64 bf16) = one SWIZZLE_128B row
 constexpr int CHUNKS = ROW_BYTES / 16;
 // warp roles of the persistent CTA
-constexpr int EPI_WARPS = 8;                 // warps 0-7: TMEM -> registers -> global (warp w: lane quarter w & 3, column half w >> 2)
-constexpr int MMA_WARP = 8;                  // warp 8: one elected lane issues tcgen05.mma
+// epilogue warps 0..EW-1: TMEM -> registers -> global (warp w: lane quarter w & 3, column phase w >> 2).
+// Weight-gradient (MN-major) launches have one light epilogue per CTA and register-hungry producers: 4 warps
+// there, the first of which also issues the MMAs (20 warps = 5 per SM sub-partition -> 96 registers per
+// thread); 8 epilogue warps + a dedicated MMA warp elsewhere (25 warps -> 72 registers).
+__host__ __device__ constexpr int epi_warps(bool mn_major) { return mn_major ? 4 : 8; }
+                                             // warp EW: one elected lane issues tcgen05.mma
 constexpr int PROD_GROUPS = 4;               // warps 5-20: four producer groups take k-blocks round-robin
 constexpr int PROD_GROUP_THREADS = 128;
-constexpr int THREADS = (EPI_WARPS + 1) * 32 + PROD_GROUPS * PROD_GROUP_THREADS;   // 416
+__host__ __device__ constexpr int cta_threads(bool mn_major) {
+    return (epi_warps(mn_major) + (mn_major ? 0 : 1)) * 32 + PROD_GROUPS * PROD_GROUP_THREADS;
+}
 enum { MODE_TF32X3 = 0, MODE_BF16 = 1 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -83,6 +89,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ bool elect_one() {     // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 template <int MODE>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
@@ -518,6 +529,7 @@ struct ColSum {
 struct Geom {
     int64_t M, K, k_chunk, num_items;
     int N, BN, splits, groups, m_tiles, n_tiles, stages;
+    int kb_rows;                 // K rows (nodes) per ring stage: KB_ELEMS, or half of it for wide MN-major tiles
     uint32_t tmem_cols;
     ColSum colsum;
     unsigned long long* prof;    // optional cycle counters (debug): see gnn_tc_set_profile_buffer
@@ -671,9 +683,9 @@ __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uin
 // pointer stride: plain coalesced vector copies, no transposition.
 template <int MODE, bool SCALED>
 __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes, int R,
-                                               int64_t mn0, int64_t kbase, int64_t k_end, int p, float4* colacc = nullptr) {
+                                               int64_t mn0, int64_t kbase, int64_t k_end, int p, float4* colacc = nullptr,
+                                               int KB = MODE == MODE_TF32X3 ? 32 : 64) {
     constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
-    constexpr int KB = MODE == MODE_TF32X3 ? 32 : 64;
     constexpr int KR = MODE == MODE_TF32X3 ? 4 : 8;
     constexpr int KR_SHIFT = MODE == MODE_TF32X3 ? 2 : 3;
     constexpr uint32_t ATOM = KR * 128;
@@ -741,6 +753,83 @@ __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, ui
     }
 }
 
+// TF32X3 weight-gradient producer: both MN-major operands of one k-block in a single load phase.
+// A thread owns one 16-byte column chunk of A and one of B (resolved once per work item into an MnPlan) and
+// walks node rows kk0, kk0 + step, ...; all NA + NB loads are issued before the first conversion so that
+// one k-block costs one memory round trip, and every address / swizzled offset is a precomputed base plus a
+// compile-time multiple of a precomputed stride (the producers are instruction-issue bound).
+struct MnPlan {
+    const float* q;        // (node kk0, this thread's column chunk) or nullptr for padding columns
+    const float* sc;       // &scal[2 * kk0 + scale] or nullptr
+    int64_t row_ld;        // elements per node row
+    int64_t step_ld;       // step * row_ld
+    int kk0, step;
+    uint32_t off0, off1, dk2;   // smem offset of row i: off[i & 1] + (i >> 1) * dk2
+};
+__device__ __forceinline__ uint32_t mn_off_tf32(int kk, int c8, uint32_t mg_off, uint32_t kgs) {
+    const int kr = kk & 3;
+    return (uint32_t)(kk >> 2) * kgs + mg_off + (uint32_t)kr * 128u + (uint32_t)((((c8 >> 1) ^ kr) << 5) | ((c8 & 1) << 4));
+}
+__device__ __forceinline__ MnPlan mn_plan(const SegOperand& op, int grp, int R, int64_t mn0, int p) {
+    const int cpr = R >> 2, ch = p & (cpr - 1);
+    const SegRef r = seg_resolve(op, mn0 + (int64_t)ch * 4, grp);
+    MnPlan pl;
+    pl.kk0 = p / cpr;
+    pl.step = PROD_GROUP_THREADS / cpr;                       // 2 (256 columns), 4, 8 or 16 (32 columns)
+    pl.row_ld = r.ld;
+    pl.step_ld = (int64_t)pl.step * r.ld;
+    pl.q = r.ptr != nullptr ? r.ptr + (int64_t)pl.kk0 * r.ld : nullptr;
+    pl.sc = (r.ptr != nullptr && r.scale >= 0) ? op.scal + 2 * pl.kk0 + r.scale : nullptr;
+    const uint32_t mg_off = (uint32_t)(ch >> 3) * 512u, kgs = (uint32_t)(cpr >> 3) * 512u;
+    pl.off0 = mn_off_tf32(pl.kk0, ch & 7, mg_off, kgs);
+    pl.off1 = mn_off_tf32(pl.kk0 + pl.step, ch & 7, mg_off, kgs);
+    pl.dk2 = mn_off_tf32(pl.kk0 + 2 * pl.step, ch & 7, mg_off, kgs) - pl.off0;
+    return pl;
+}
+template <bool SCALED, int NA, int NB>
+__device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnPlan& pb, uint8_t* a_tile, uint32_t a_plane,
+                                                     uint8_t* b_tile, uint32_t b_plane, int64_t kbase, int64_t lim,
+                                                     float4* colacc) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 va[NA], vb[NB];
+    float f[NA];
+    const float* qa = pa.q != nullptr ? pa.q + kbase * pa.row_ld : nullptr;
+    const float* qb = pb.q != nullptr ? pb.q + kbase * pb.row_ld : nullptr;
+    const float* qs = (SCALED && pa.sc != nullptr) ? pa.sc + 2 * kbase : nullptr;
+    const int64_t left = lim - kbase;                       // valid node rows from kbase on
+    if (left >= (int64_t)NA * pa.step) {                    // whole k-block in range: no per-row predicates
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            va[i] = qa != nullptr ? ldg4(qa + i * pa.step_ld) : zero;
+            if (SCALED) f[i] = qs != nullptr ? __ldg(qs + i * 2 * pa.step) : 1.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) vb[i] = qb != nullptr ? ldg4(qb + i * pb.step_ld) : zero;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const bool ok = pa.kk0 + i * pa.step < left;
+            va[i] = (ok && qa != nullptr) ? ldg4(qa + i * pa.step_ld) : zero;
+            if (SCALED) f[i] = (ok && qs != nullptr) ? __ldg(qs + i * 2 * pa.step) : 1.f;
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const bool ok = pb.kk0 + i * pb.step < left;
+            vb[i] = (ok && qb != nullptr) ? ldg4(qb + i * pb.step_ld) : zero;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        if (SCALED) va[i] = make_float4(va[i].x * f[i], va[i].y * f[i], va[i].z * f[i], va[i].w * f[i]);
+        if (colacc != nullptr)
+            colacc[0] = make_float4(colacc[0].x + va[i].x, colacc[0].y + va[i].y, colacc[0].z + va[i].z, colacc[0].w + va[i].w);
+        put_chunk_tf32<MODE_TF32X3>(a_tile, a_plane, ((i & 1) ? pa.off1 : pa.off0) + (uint32_t)(i >> 1) * pa.dk2, va[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+        put_chunk_tf32<MODE_TF32X3>(b_tile, b_plane, ((i & 1) ? pb.off1 : pb.off0) + (uint32_t)(i >> 1) * pb.dk2, vb[i]);
+}
+
 // ------------------------------------------------------------------ the kernel
 // Persistent, warp-specialised: work item = (m tile, n tile, group, k split).
 //   producers (4 groups x 4 warps): global -> registers -> (tf32 hi/lo | bf16) -> SWIZZLE_128B smem ring
@@ -764,7 +853,7 @@ pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t*
 }
 
 template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(cta_threads(MN_MAJOR), 1)
 gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar[2], tmem_empty_bar[2];
@@ -772,13 +861,17 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
 
     constexpr int KB_ELEMS = MODE == MODE_TF32X3 ? 32 : 64;
     constexpr int PARTS = MODE == MODE_TF32X3 ? 2 : 1;
+    constexpr int EPI_WARPS = epi_warps(MN_MAJOR), MMA_WARP = MN_MAJOR ? 0 : EPI_WARPS;
+    constexpr int PROD_WARP0 = MN_MAJOR ? EPI_WARPS : EPI_WARPS + 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int BN = g.BN, NS = g.stages;
     const long long kernel_t0 = g.prof ? clock64() : 0;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_plane = BM * ROW_BYTES, b_plane = (uint32_t)BN * ROW_BYTES;
-    const uint32_t stage_bytes = PARTS * (a_plane + b_plane);        // multiple of 1024 (BN % 16 == 0)
+    const int KBR = MN_MAJOR ? g.kb_rows : KB_ELEMS;                 // K rows per ring stage
+    const uint32_t kdiv = MN_MAJOR ? (uint32_t)(KB_ELEMS / g.kb_rows) : 1u;
+    const uint32_t a_plane = BM * ROW_BYTES / kdiv, b_plane = (uint32_t)BN * ROW_BYTES / kdiv;
+    const uint32_t stage_bytes = PARTS * (a_plane + b_plane);        // multiple of 1024
 
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, g.tmem_cols);
     if (tid == 0) {
@@ -809,14 +902,13 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
         k_end = min(g.K, k_begin + g.k_chunk);
     };
 
-    if (warp < EPI_WARPS) {
-        // =============================== epilogue ===============================
-        // thread = one accumulator row (TMEM lane); warp w reads lane quarter w & 3 and the 16-column chunks
-        // c = (w >> 2), (w >> 2) + 2, ...; values go straight from registers to global memory (each lane writes
-        // 64 contiguous bytes of its row per chunk)
+    // =============================== epilogue (one work item) ===============================
+    // thread = one accumulator row (TMEM lane); warp w reads lane quarter w & 3 and the 16-column chunks
+    // c = (w >> 2), (w >> 2) + EPI_WARPS / 4, ...; values go straight from registers to global memory (each lane
+    // writes 64 contiguous bytes of its row per chunk)
+    auto epi_item = [&](int64_t item, uint32_t t) {
         const int q = warp & 3, half = warp >> 2;
-        uint32_t t = 0;
-        for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) {
+        {
             int64_t m0, k_begin, k_end;
             int n0, grp;
             decode(item, m0, n0, grp, k_begin, k_end);
@@ -836,7 +928,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 if (row_ok) ep.scalers(m, amp, att);
             }
             long long ld_cyc = 0;
-            for (int col = half * 16; col < out_cols; col += 32) {
+            for (int col = half * 16; col < out_cols; col += 4 * EPI_WARPS) {
                 float v[16];
                 const long long lt0 = g.prof ? clock64() : 0;
                 tmem_ld16(taddr + col, v);
@@ -873,17 +965,18 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 atomicAdd(g.prof + 7, (unsigned long long)(clock64() - et1));       // epilogue work
                 atomicAdd(g.prof + 8, 1ull);
                 atomicAdd(g.prof + 11, (unsigned long long)ld_cyc);                 // ... of which first tcgen05.ld + wait per chunk
+                if (t == 0) atomicAdd(g.prof + 14, (unsigned long long)(et1 - kernel_t0));       // first item: accumulator ready
             }
         }
-    } else if (warp == MMA_WARP) {
-        // =============================== MMA issuer ===============================
-        const uint32_t idesc = instr_desc(MODE, BN, MN_MAJOR ? 1 : 0);
-        uint32_t it = 0, t = 0;
-        for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) {
+    };
+    // =============================== MMA issue (one work item, one warp) ===============================
+    const uint32_t idesc = instr_desc(MODE, BN, MN_MAJOR ? 1 : 0);
+    auto mma_item = [&](int64_t item, uint32_t t, uint32_t& it) {
+        {
             int64_t m0, k_begin, k_end;
             int n0, grp;
             decode(item, m0, n0, grp, k_begin, k_end);
-            const int num_kb = (int)((k_end - k_begin + KB_ELEMS - 1) / KB_ELEMS);
+            const int num_kb = (int)((k_end - k_begin + KBR - 1) / KBR);
             const uint32_t b = t & 1, tuse = t >> 1;
             if (tuse > 0) mbar_wait(&tmem_empty_bar[b], (tuse - 1) & 1);     // epilogue drained this accumulator
             tc_fence_after();
@@ -897,11 +990,13 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     atomicAdd(g.prof + 4, (unsigned long long)(clock64() - mt0));   // MMA warp waiting for operands
                     atomicAdd(g.prof + 5, 1ull);
                 }
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + a_plane;
                     const uint32_t b_hi = a_hi + PARTS * a_plane, b_lo = b_hi + b_plane;
+                    const int ksteps = (CHUNKS / 2) / (int)kdiv;
 #pragma unroll
                     for (int j = 0; j < CHUNKS / 2; ++j) {       // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
+                        if (j >= ksteps) break;
                         const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
                         uint64_t dah, dal, dbh, dbl;
                         if (MN_MAJOR) {
@@ -935,14 +1030,35 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 }
                 __syncwarp();
             }
+            if (g.prof && lane == 0 && t == 0) atomicAdd(g.prof + 13, (unsigned long long)(clock64() - kernel_t0));   // first item: all MMAs issued
+        }
+    };
+
+    if constexpr (MN_MAJOR) {
+        // weight gradients: warp 0 issues the MMAs of an item and then joins warps 1-3 in its epilogue
+        if (warp < EPI_WARPS) {
+            uint32_t it = 0, t = 0;
+            for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) {
+                if (warp == 0) mma_item(item, t, it);
+                epi_item(item, t);
+            }
         }
     } else {
+        if (warp < EPI_WARPS) {
+            uint32_t t = 0;
+            for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) epi_item(item, t);
+        } else if (warp == MMA_WARP) {
+            uint32_t it = 0, t = 0;
+            for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) mma_item(item, t, it);
+        }
+    }
+    if (warp >= PROD_WARP0) {
         // =============================== producers ===============================
         // NS (<= PROD_GROUPS) groups are active and group pg owns ring stage pg: a group then only ever waits
         // for the MMAs of its own previous k-block, so it can never run two mbarrier phases ahead (a parity
         // wait cannot tell phase n from phase n-2).  Groups pg >= NS idle.
-        const int pg = (warp - (EPI_WARPS + 1)) >> 2;            // producer group 0..3
-        const int p = tid - (EPI_WARPS + 1) * 32 - pg * PROD_GROUP_THREADS;
+        const int pg = (warp - PROD_WARP0) >> 2;                 // producer group 0..3
+        const int p = tid - PROD_WARP0 * 32 - pg * PROD_GROUP_THREADS;
         const int total_kb = (int)((g.K + KB_ELEMS - 1) / KB_ELEMS);      // packed images exist only without split-K
         uint32_t it = 0;
         for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x) {
@@ -951,17 +1067,23 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             decode(item, m0, n0, grp, k_begin, k_end);
             BL bl = bl0;
             if constexpr (!MN_MAJOR) bl.set_group(grp);
-            const int num_kb = (int)((k_end - k_begin + KB_ELEMS - 1) / KB_ELEMS);
+            const int num_kb = (int)((k_end - k_begin + KBR - 1) / KBR);
             float4 colacc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
             const bool do_colsum = MN_MAJOR && g.colsum.base != nullptr && n0 == 0;
+            MnPlan pa{}, pb{};
+            if constexpr (MN_MAJOR && MODE == MODE_TF32X3) {
+                pa = mn_plan(aop, grp, BM, m0, p);
+                pb = mn_plan(bl, grp, BN, (int64_t)n0, p);
+            }
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
                 if ((int)(it % NS) != pg) continue;                // group pg owns ring stage pg (see below)
                 const uint32_t s = it % NS, use = it / NS;
                 const long long pt0 = g.prof ? clock64() : 0;
+                if (g.prof && p == 0 && it == 0) atomicAdd(g.prof + 12, (unsigned long long)(pt0 - kernel_t0));   // set-up until the first k-block
                 if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
                 const long long pt1 = g.prof ? clock64() : 0;
                 uint8_t* stage = smem + (size_t)s * stage_bytes;
-                const int64_t kbase = k_begin + (int64_t)kb * KB_ELEMS;
+                const int64_t kbase = k_begin + (int64_t)kb * KBR;
                 if constexpr (PACKED) {
                     // the weight operand was pre-packed as the smem image: one TMA bulk copy per k-block
                     if (p == 0) {
@@ -971,9 +1093,20 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         bulk_g2s(stage + PARTS * a_plane, packed_b + tile_idx * bytes, bytes, &full_bar[s]);
                     }
                     produce_a_seg<MODE, SCALED>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
+                } else if constexpr (MN_MAJOR && MODE == MODE_TF32X3) {
+                    // loads per thread: A (128 columns) KBR / 4 rows; B (BN columns) KBR * BN / 512 rows
+                    const int64_t lim = k_end < aop.rows ? k_end : aop.rows;
+                    uint8_t* bt = stage + PARTS * a_plane;
+                    float4* ca = do_colsum ? colacc : nullptr;
+                    if (BN == 256) produce_mn_pair_tf32<SCALED, 4, 8>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
+                    else if (BN == 128) produce_mn_pair_tf32<SCALED, 4, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
+                    else if (BN == 64) produce_mn_pair_tf32<SCALED, 8, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
+                    else produce_mn_pair_tf32<SCALED, 8, 2>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
                 } else if constexpr (MN_MAJOR) {
-                    produce_mn_seg<MODE, SCALED>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p, do_colsum ? colacc : nullptr);
-                    produce_mn_seg<MODE, false>(bl, grp, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
+                    produce_mn_seg<MODE, SCALED>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p,
+                                                 do_colsum ? colacc : nullptr, KBR);
+                    produce_mn_seg<MODE, false>(bl, grp, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p,
+                                                nullptr, KBR);
                 } else {
                     produce_a_seg<MODE, SCALED>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
                     produce_tile<MODE>(bl, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
@@ -989,20 +1122,33 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 }
             }
             if constexpr (MN_MAJOR) {
-                if (do_colsum && pg < NS) {                         // flush this thread's column chunk
+                if (do_colsum) {
+                    // bias gradient: reduce the per-thread column sums of this item across the 512 producer
+                    // threads in shared memory, then one global atomic per column (the target is a handful of
+                    // addresses shared by every CTA: per-thread atomics would serialise in one L2 slice)
                     constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
-                    const int cpr = BM / EPC;
-                    const int col0 = (int)m0 + (p & (cpr - 1)) * EPC;
+                    constexpr int CPR = BM / EPC;
+                    __shared__ float cs_stage[PROD_GROUPS * PROD_GROUP_THREADS * EPC];
+                    const int pp = pg * PROD_GROUP_THREADS + p;
                     const float e[8] = {colacc[0].x, colacc[0].y, colacc[0].z, colacc[0].w,
                                         colacc[1].x, colacc[1].y, colacc[1].z, colacc[1].w};
 #pragma unroll
-                    for (int j = 0; j < EPC; ++j) {
-                        const int col = col0 + j;
-                        if (col < g.colsum.ncols && e[j] != 0.f)
+                    for (int j = 0; j < EPC; ++j) cs_stage[pp * EPC + j] = e[j];
+                    asm volatile("bar.sync 1, %0;" ::"n"(PROD_GROUPS * PROD_GROUP_THREADS) : "memory");
+                    if (pp < BM) {
+                        const int col = (int)m0 + pp;
+                        float t = 0.f;
+#pragma unroll
+                        for (int gq = 0; gq < PROD_GROUPS; ++gq)
+#pragma unroll
+                            for (int k0 = 0; k0 < PROD_GROUP_THREADS / CPR; ++k0)
+                                t += cs_stage[(gq * PROD_GROUP_THREADS + k0 * CPR + pp / EPC) * EPC + pp % EPC];
+                        if (col < g.colsum.ncols && t != 0.f)
                             atomicAdd(g.colsum.base + (int64_t)grp * g.colsum.group_stride +
                                           (int64_t)(col / g.colsum.tower_cols) * g.colsum.tower_stride +
-                                          col % g.colsum.tower_cols, e[j]);
+                                          col % g.colsum.tower_cols, t);
                     }
+                    asm volatile("bar.sync 1, %0;" ::"n"(PROD_GROUPS * PROD_GROUP_THREADS) : "memory");
                 }
             }
         }
@@ -1029,8 +1175,10 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
     if (BN % 16 != 0 || BN < 16 || BN > 256) return GNN_ERR_UNSUPPORTED;
     constexpr int parts = MODE == MODE_TF32X3 ? 2 : 1;
     constexpr int kb_elems = MODE == MODE_TF32X3 ? 32 : 64;
-    const size_t stage_bytes = (size_t)parts * (BM + BN) * ROW_BYTES;
-    const size_t fixed = 1024 + 256;
+    // wide MN-major TF32X3 tiles use half-height k-blocks: 4 ring stages (one per producer group) still fit
+    const int kb_rows = (MN_MAJOR && MODE == MODE_TF32X3 && BN >= 128) ? kb_elems / 2 : kb_elems;
+    const size_t stage_bytes = (size_t)parts * (BM + BN) * ROW_BYTES * kb_rows / kb_elems;
+    const size_t fixed = 1024 + 256 + (MN_MAJOR ? PROD_GROUPS * PROD_GROUP_THREADS * (MODE == MODE_TF32X3 ? 16 : 32) : 0);
     int stages = (int)((kSmemLimit - fixed) / stage_bytes);
     if (stages > PROD_GROUPS) stages = PROD_GROUPS;      // one producer group per ring stage
     if (stages < 2) return GNN_ERR_UNSUPPORTED;
@@ -1040,6 +1188,7 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
     g.n_tiles = EP::kCombine3 ? N / BN : (int)gnn_ceil_div(N, BN);
     g.num_items = (int64_t)g.m_tiles * g.n_tiles * groups * splits;
     g.stages = stages;
+    g.kb_rows = kb_rows;
     uint32_t cols = 32;
     while ((int)cols < 2 * BN) cols <<= 1;
     g.tmem_cols = cols;
@@ -1053,7 +1202,7 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
         auto kern = gemm_tc_kernel<MODE, false, true, SCALED, BL, EP>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, nullptr);
+        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr);
     } else {
         // weights (B) are packed once per call when a workspace is given and the M loop re-uses them
         const int num_kb = (int)gnn_ceil_div(K, kb_elems);
@@ -1067,12 +1216,12 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws));
+            kern<<<(unsigned)grid, cta_threads(false), smem, st>>>(aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws));
         } else {
             auto kern = gemm_tc_kernel<MODE, false, false, SCALED, BL, EP>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            kern<<<(unsigned)grid, THREADS, smem, st>>>(aop, bl, ep, g, nullptr);
+            kern<<<(unsigned)grid, cta_threads(false), smem, st>>>(aop, bl, ep, g, nullptr);
         }
     }
     return gnn_launch_status();

@@ -8,11 +8,11 @@
 #include <math.h>
 
 constexpr int RED_TX = 32, RED_TY = 8;          // column-reduction block: 32 columns x 8 row phases
-constexpr int RED_ROWS_PER_CTA = 512;
+constexpr int RED_ROWS_PER_CTA = 256;
 
 static int red_ctas(int64_t rows) {
     int64_t c = gnn_ceil_div(rows, RED_ROWS_PER_CTA);
-    int64_t cap = (int64_t)gnn_sm_count() * 4;
+    int64_t cap = (int64_t)gnn_sm_count() * 8;
     if (c > cap) c = cap;
     if (c < 1) c = 1;
     return (int)c;
@@ -77,21 +77,93 @@ bn_partial_kernel(const float* __restrict__ Y, const float* __restrict__ dOut, c
     }
 }
 
+// vectorised variant for C in {4, 8, ..., 1024} with 256 % (C/4) == 0: 16-byte loads, TX = C/4 threads per row
+template <int MODE>
+__global__ void __launch_bounds__(256)
+bn_partial4_kernel(const float* __restrict__ Y, const float* __restrict__ dOut, const float* __restrict__ stats,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int C, int relu,
+                   double* __restrict__ partial) {
+    extern __shared__ double sred[];                 // [256][8]
+    const int TX = C >> 2, TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c = tx * 4;
+    const int64_t chunk = ceil_div_dev(rows, gridDim.x);
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, ga = mu, be = mu;
+    if (MODE == 1) {
+        mu = ldg4(stats + c);
+        rs = ldg4(stats + C + c);
+        ga = ldg4(gamma + c);
+        be = ldg4(beta + c);
+    }
+    for (int64_t r = r0 + ty; r < r1; r += TY) {
+        const float4 y = ldg4(Y + r * C + c);
+        if (MODE == 0) {
+            a[0] += y.x; a[1] += y.y; a[2] += y.z; a[3] += y.w;
+            a[4] += (double)y.x * y.x; a[5] += (double)y.y * y.y; a[6] += (double)y.z * y.z; a[7] += (double)y.w * y.w;
+        } else {
+            float4 dz = ldg4(dOut + r * C + c);
+            const float4 yh = make_float4((y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w);
+            if (relu) {
+                if (!(fmaf(ga.x, yh.x, be.x) > 0.f)) dz.x = 0.f;
+                if (!(fmaf(ga.y, yh.y, be.y) > 0.f)) dz.y = 0.f;
+                if (!(fmaf(ga.z, yh.z, be.z) > 0.f)) dz.z = 0.f;
+                if (!(fmaf(ga.w, yh.w, be.w) > 0.f)) dz.w = 0.f;
+            }
+            a[0] += dz.x; a[1] += dz.y; a[2] += dz.z; a[3] += dz.w;
+            a[4] += (double)dz.x * yh.x; a[5] += (double)dz.y * yh.y; a[6] += (double)dz.z * yh.z; a[7] += (double)dz.w * yh.w;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sred[threadIdx.x * 8 + k] = a[k];
+    __syncthreads();
+    if (ty == 0) {
+        for (int k = 0; k < 8; ++k) {
+            double t = 0.0;
+            for (int j = 0; j < TY; ++j) t += sred[(j * TX + tx) * 8 + k];
+            partial[((int64_t)blockIdx.x * 2 + (k >> 2)) * C + c + (k & 3)] = t;
+        }
+    }
+}
+
+static bool bn_vec_ok(int C) { return (C & 3) == 0 && C >= 4 && C <= 1024 && (256 % (C >> 2)) == 0; }
+
+// Sum the per-CTA partials of one column; launched with dim3(32, 8): threadIdx.y strides the parts.  Returns the
+// totals in thread y == 0 (other threads get garbage and must not write).
+__device__ __forceinline__ void reduce_parts(const double* __restrict__ partial, int nparts, int C, int c, double& s,
+                                             double& ss) {
+    __shared__ double r0[8][33], r1[8][33];
+    double a = 0.0, b = 0.0;
+    if (c < C)
+        for (int p = threadIdx.y; p < nparts; p += 8) {
+            a += partial[((int64_t)p * 2 + 0) * C + c];
+            b += partial[((int64_t)p * 2 + 1) * C + c];
+        }
+    r0[threadIdx.y][threadIdx.x] = a;
+    r1[threadIdx.y][threadIdx.x] = b;
+    __syncthreads();
+    s = ss = 0.0;
+    if (threadIdx.y == 0)
+        for (int k = 0; k < 8; ++k) {
+            s += r0[k][threadIdx.x];
+            ss += r1[k][threadIdx.x];
+        }
+}
+
 __global__ void bn_stats_finalize_kernel(const double* __restrict__ partial, int nparts, int64_t rows, int C,
                                          int training, float eps, float momentum, float* running_mean,
                                          float* running_var, int64_t* num_batches_tracked, float* stats) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0, ss = 0.0;
+    if (training) reduce_parts(partial, nparts, C, c, s, ss);
+    if (threadIdx.y != 0) return;
     if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
     if (!training) {
         stats[c] = running_mean[c];
         stats[C + c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
         return;
-    }
-    double s = 0.0, ss = 0.0;
-    for (int p = 0; p < nparts; ++p) {
-        s += partial[((int64_t)p * 2 + 0) * C + c];
-        ss += partial[((int64_t)p * 2 + 1) * C + c];
     }
     double mean = s / (double)rows;
     double var = ss / (double)rows - mean * mean;
@@ -115,10 +187,15 @@ extern "C" int gnn_bn_stats(const float* Y, int64_t rows, int C, int training, f
     cudaStream_t st = gnn_stream(stream);
     double* partial = reinterpret_cast<double*>(workspace);
     int parts = red_ctas(rows);
-    if (training)
-        bn_partial_kernel<0><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, nullptr, nullptr, nullptr, nullptr, rows, C, 0,
-                                                                      partial);
-    bn_stats_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, parts, rows, C, training, eps, momentum,
+    if (training) {
+        if (bn_vec_ok(C))
+            bn_partial4_kernel<0><<<parts, 256, 256 * 8 * sizeof(double), st>>>(Y, nullptr, nullptr, nullptr, nullptr,
+                                                                                rows, C, 0, partial);
+        else
+            bn_partial_kernel<0><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, nullptr, nullptr, nullptr, nullptr, rows, C,
+                                                                          0, partial);
+    }
+    bn_stats_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, parts, rows, C, training, eps, momentum,
                                                               running_mean, running_var, num_batches_tracked, stats);
     return gnn_launch_status();
 }
@@ -184,12 +261,9 @@ extern "C" int gnn_bn_act_fwd(const float* Y, const float* stats, const float* g
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int nparts, int C, float* sums,
                                        float* dgamma, float* dbeta) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, sy = 0.0;
-    for (int p = 0; p < nparts; ++p) {
-        s += partial[((int64_t)p * 2 + 0) * C + c];
-        sy += partial[((int64_t)p * 2 + 1) * C + c];
-    }
+    double s, sy;
+    reduce_parts(partial, nparts, C, c, s, sy);
+    if (threadIdx.y != 0 || c >= C) return;
     sums[c] = (float)s;
     sums[C + c] = (float)sy;
     if (dbeta) dbeta[c] += (float)s;
@@ -215,6 +289,35 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dOut, const fl
     }
 }
 
+__global__ void bn_act_bwd_apply4_kernel(const float* __restrict__ dOut, const float* __restrict__ Y,
+                                         const float* __restrict__ stats, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, const float* __restrict__ sums,
+                                         int64_t rows, int C, int relu, int training, float* __restrict__ dY) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t total4 = rows * C / 4;
+    const int C4 = C >> 2;
+    const float inv_n = 1.0f / (float)rows;
+    for (; i < total4; i += stride) {
+        const int c = (int)(i % C4) * 4;
+        const float4 mu = ldg4(stats + c), rs = ldg4(stats + C + c), ga = ldg4(gamma + c), be = ldg4(beta + c);
+        const float4 s0 = ldg4(sums + c), s1 = ldg4(sums + C + c);
+        const float4 y = ldg4(Y + 4 * i);
+        float4 dz = ldg4(dOut + 4 * i);
+        float4 o;
+#define BWD(X)                                                                      \
+    {                                                                               \
+        const float yh = (y.X - mu.X) * rs.X;                                       \
+        if (relu && !(fmaf(ga.X, yh, be.X) > 0.f)) dz.X = 0.f;                      \
+        const float v = training ? (dz.X - s0.X * inv_n - yh * s1.X * inv_n) : dz.X; \
+        o.X = ga.X * rs.X * v;                                                      \
+    }
+        BWD(x) BWD(y) BWD(z) BWD(w)
+#undef BWD
+        st4(dY + 4 * i, o);
+    }
+}
+
 extern "C" int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* stats, const float* gamma,
                               const float* beta, int64_t rows, int C, int relu, int training, float* dY,
                               float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, void* stream) {
@@ -225,10 +328,18 @@ extern "C" int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* st
     int parts = red_ctas(rows);
     double* partial = reinterpret_cast<double*>(workspace);
     float* sums = reinterpret_cast<float*>(partial + (int64_t)parts * 2 * C);
-    bn_partial_kernel<1><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, dOut, stats, gamma, beta, rows, C, relu, partial);
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, parts, C, sums, dgamma, dbeta);
-    bn_act_bwd_apply_kernel<<<ew_grid(rows * C, 256), 256, 0, st>>>(dOut, Y, stats, gamma, beta, sums, rows, C, relu,
-                                                                    training, dY);
+    if (bn_vec_ok(C))
+        bn_partial4_kernel<1><<<parts, 256, 256 * 8 * sizeof(double), st>>>(Y, dOut, stats, gamma, beta, rows, C, relu,
+                                                                            partial);
+    else
+        bn_partial_kernel<1><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, dOut, stats, gamma, beta, rows, C, relu, partial);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, parts, C, sums, dgamma, dbeta);
+    if ((C & 3) == 0)
+        bn_act_bwd_apply4_kernel<<<ew_grid(rows * C / 4, 256), 256, 0, st>>>(dOut, Y, stats, gamma, beta, sums, rows, C,
+                                                                             relu, training, dY);
+    else
+        bn_act_bwd_apply_kernel<<<ew_grid(rows * C, 256), 256, 0, st>>>(dOut, Y, stats, gamma, beta, sums, rows, C, relu,
+                                                                        training, dY);
     return gnn_launch_status();
 }
 

@@ -29,7 +29,8 @@ def report(name, fn, reps=5):
     kb, mk, it, ct = max(p[3], 1), max(p[5], 1), max(p[8], 1), max(p[10], 1)
     print(f"{name:28s} {us:8.1f} us/call | per k-block (cycles): wait_stage {p[0]/kb:8.0f} produce {p[1]/kb:8.0f} "
           f"arrive {p[2]/kb:6.0f} | mma wait {p[4]/mk:8.0f} | per item: epi wait {p[6]/it:9.0f} epi work {p[7]/it:8.0f} "
-          f"(tmem ld {p[11]/it:6.0f}) | CTA cycles {p[9]/ct:9.0f} ({p[9]/ct/1.9e3:.1f} us) kblocks/CTA {p[5]/ct:.1f}")
+          f"(tmem ld {p[11]/it:6.0f}) | CTA cycles {p[9]/ct:9.0f} ({p[9]/ct/1.9e3:.1f} us) kblocks/CTA {p[5]/ct:.1f} | first item: "
+          f"start {p[12]/ct:7.0f} mma issued {p[13]/ct:8.0f} acc ready {p[14]/ct:8.0f}")
 
 
 n = 102263
@@ -53,3 +54,12 @@ gA = torch.empty(n, T * 4 * F, device=dev)
 report("post_dgrad gA", lambda: _lib.call("gnn_tc_pna_post_dgrad", O, scal, wpost, wts, n, F, Fo, T, None, gA, 0, ws, ws.numel(), st()))
 dwp = torch.zeros(T * wts, device=dev)
 report("post_wgrad (2 launches)", lambda: _lib.call("gnn_tc_pna_post_wgrad", O, x, A, scal, n, F, Fo, T, dwp, wts, dwp[Fo * 13 * F:], wts, 0, st()))
+C = T * F
+wpre_ts = F * 3 * F + F                      # per-tower pre-NN weight [F, 3F] + bias [F]
+wpre = torch.randn(T * wpre_ts, device=dev) * 0.1
+P = torch.empty(n, 2 * C, device=dev)
+report("proj_fwd", lambda: _lib.call("gnn_tc_pna_proj_fwd", x, wpre, wpre_ts, wpre[F * 3 * F:], wpre_ts, n, F, T, P, 0, ws, ws.numel(), st()))
+dx = torch.empty(n, F, device=dev)
+report("dx_dgrad", lambda: _lib.call("gnn_tc_pna_dx_dgrad", P, O, wpre, wpre_ts, wpost, wts, n, F, Fo, T, 0, dx, 0, ws, ws.numel(), st()))
+dwpre = torch.zeros(T * wpre_ts, device=dev)
+report("proj_wgrad", lambda: _lib.call("gnn_tc_pna_proj_wgrad", P, x, n, F, T, dwpre, wpre_ts, dwpre[F * 3 * F:], wpre_ts, 0, st()))
