@@ -102,7 +102,12 @@ __device__ __forceinline__ void seg_finish(const SegStat& st, int cnt, float4 pd
 // does not depend on the node (channel -> tower/feature split, column pointers) is hoisted out of the node loop.
 // Measured on B200 (tools/agg_probe.py, ncu): the kernel is bound by instruction issue / the per-node dependent
 // chain rather than by DRAM; variants tried and rejected: 8-node edge streams per warp (register pressure),
-// higher occupancy via register caps (spills), cross-node index prefetch, two nodes per warp.
+// higher occupancy via register caps (spills), cross-node index prefetch, two nodes per warp, and a streamed
+// variant (contiguous node range per warp, source rows through a 16-row cp.async ring in shared memory 12 rows
+// ahead, indices read 32 at a time): bit-identical output and the same 79-80 us, i.e. the kernel is not bound by
+// latency hiding.  Stores alone (209 MB) take 43 us in the same harness, a torch fill of that size 41 us; in the
+// training step the 105 MB of P written by the projection GEMM are still dirty in L2 and are evicted by this
+// kernel's stores, so DRAM sees ~314 MB of writes per launch.
 template <int NCHUNK>
 __global__ void __launch_bounds__(AGG_THREADS, 4)
 pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ tab,
@@ -349,7 +354,8 @@ pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__
     g.X = cm.X + (q.X == mn.X ? cmin.X : 0.f) + (q.X == mx.X ? cmax.X : 0.f) + cs.X * (q.X - mean.X);
                     GRAD(x) GRAD(y) GRAD(z) GRAD(w)
 #undef GRAD
-                    st4(dq + (int64_t)(beg + k) * C + c, g);
+                    if (dq != nullptr) st4(dq + (int64_t)(beg + k) * C + c, g);
+                    else atomicAdd(reinterpret_cast<float4*>(dP + so + c), g);  // dPsrc[src] += g  (so = src*2C + C)
                     atomicAdd(reinterpret_cast<float4*>(dtab + co + c), g);     // RED.E.ADD.F32x4
                 }
             }
@@ -388,6 +394,10 @@ extern "C" int gnn_pna_aggregate_bwd(const float* gA, const float* P, const floa
     int64_t cap = (int64_t)gnn_sm_count() * 32;
     if (blocks > cap) blocks = cap;
     float* parts = reinterpret_cast<float*>(zeroed_workspace);
+    if (dq == nullptr) {       // source gradients accumulate atomically into dP[:, C:2C]
+        cudaError_t e = cudaMemset2DAsync(dP + C, 2 * (size_t)C * sizeof(float), 0, (size_t)C * sizeof(float), (size_t)n, st);
+        if (e != cudaSuccess) return (int)e;
+    }
     pna_aggregate_bwd_kernel<<<(unsigned)blocks, AGG_THREADS, 0, st>>>(gA, P, tab, A, rowptr, col_src, col_code, n, C, F,
                                                                        dP, dq, parts);
     const int total = GNN_NUM_BOND_CODES * C;

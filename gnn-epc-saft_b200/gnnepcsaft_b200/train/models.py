@@ -22,6 +22,10 @@ from .. import _lib
 from ..data.graph import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS, NUM_BOND_CODES
 
 TOWERS = 2  # reference models.py:76
+# Source-node gradient scatter: two passes with a fixed summation order (default; also the faster one on B200:
+# 191 + 48 us per layer) or, with GNN_B200_ATOMIC_SCATTER=1, 128-bit atomic adds inside the aggregate backward
+# kernel (no per-slot buffer, 248 us per layer).
+DETERMINISTIC_SCATTER = os.environ.get("GNN_B200_ATOMIC_SCATTER", "0") != "1"
 DEFAULT_MATMUL = "tf32x3"
 
 
@@ -658,7 +662,9 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
         # aggregation + message
         dP = torch.empty(n, 2 * C, **f32)
         if pp.pre_layers == 1:
-            dq = torch.empty(max(g.ep, 1), C, **f32)
+            # default: per-slot gradients dq, summed per source node by gnn_scatter_src_bwd; dq = None makes the
+            # kernel accumulate them atomically into dP[:, C:] instead
+            dq = torch.empty(max(g.ep, 1), C, **f32) if DETERMINISTIC_SCATTER else None
             nb = _lib.query("gnn_pna_aggregate_bwd_workspace_bytes", T, F)
             zws = _WS.get_zeroed("aggbwd", nb, dev)         # kept all-zero by the kernel pair itself
             _c("gnn_pna_aggregate_bwd", gA, rec.P, sv.tab[l], rec.A, g.rowptr, g.col_src, g.col_code, n, T, F, dP,
@@ -679,7 +685,8 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
                 dm = dprev
             dq = dm
             _c("gnn_edge_hidden_bwd", dq, g.rowptr, g.col_code, n, C, dP, dtab[l])
-        _c("gnn_scatter_src_bwd", dq, g.srcptr, g.src_slot, n, C, dP)
+        if dq is not None:
+            _c("gnn_scatter_src_bwd", dq, g.srcptr, g.src_slot, n, C, dP)
         # projections
         if fused_dx:
             pre0 = conv.pre_nns[0][0]

@@ -120,14 +120,17 @@ int gnn_bond_table_bwd(const float* dtab, const float* bond_tables, const float*
  *   q_e = Psrc[src_e] + tab[code_e];   m_e = Pdst[dst_e] + q_e
  * Output A [N, towers, 4, F]: mean, min, max (of m) and std (of q; shift invariant), with
  * empty segments -> 0 and std = sqrt(max(var,1e-5)) masked to 0 when <= sqrt(1e-5).
- * One warp per destination node, single pass, Welford variance. */
+ * One warp per destination node, single pass, variance from sums shifted by the first message. */
 int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int32_t* rowptr,
                           const int32_t* col_src, const uint8_t* col_code, int64_t num_nodes,
                           int towers, int F, float* A, void* stream);
 /* Backward: gA [N,towers,4,F] -> dP[:, 0:C] (dst part), dq [E',C] per CSR slot and
  * dtab_accum [60,C] (+=, caller zeroes).  min/max gradients are split evenly over ties
  * (torch scatter_reduce amin/amax semantics).  `zeroed_workspace` holds partial bond-code
- * tables; it must be all-zero on entry and is all-zero again on exit. */
+ * tables; it must be all-zero on entry and is all-zero again on exit.
+ * dq == NULL: the per-slot gradients are not materialised; dP[:, C:2C] (source part) is
+ * cleared and receives dq_e at row src_e through 128-bit atomic adds (summation order
+ * not fixed), which replaces the gnn_scatter_src_bwd pass. */
 int64_t gnn_pna_aggregate_bwd_workspace_bytes(int towers, int F);
 int gnn_pna_aggregate_bwd(const float* gA, const float* P, const float* tab, const float* A,
                           const int32_t* rowptr, const int32_t* col_src,

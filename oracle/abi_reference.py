@@ -229,6 +229,8 @@ def gnn_pna_aggregate_bwd_workspace_bytes(towers, f):
 def gnn_pna_aggregate_bwd(gA, P, tab, A, rowptr, col_src, col_code, n, towers, f, dP, dq, dtab_accum,
                           workspace=None, workspace_bytes=0, stream=None):
     c = towers * f
+    if dq is None:
+        dP[:n, c:2 * c] = 0
     for i, (b, e) in enumerate(_segments(rowptr, n)):
         if e == b:
             dP[i, :c] = 0
@@ -236,7 +238,10 @@ def gnn_pna_aggregate_bwd(gA, P, tab, A, rowptr, col_src, col_code, n, towers, f
         q = P[col_src[b:e].long(), c:] + tab[col_code[b:e].long()]
         sd = A[i].view(towers, 4, f)[:, 3].reshape(-1)
         d, dpd = _agg_grad(q, gA[i], sd, towers, f)
-        dq[b:e] = d
+        if dq is None:
+            dP[:, c:2 * c].index_add_(0, col_src[b:e].long(), d)
+        else:
+            dq[b:e] = d
         dP[i, :c] = dpd
         dtab_accum.index_add_(0, col_code[b:e].long(), d)
 

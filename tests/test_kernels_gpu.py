@@ -231,6 +231,16 @@ def test_aggregate_fwd_bwd(n, e, T, F, loops, quant):
     dP2 = torch.zeros(n, 2 * C)
     cpu, gpu = run_both("gnn_scatter_src_bwd", dq_gpu, ref["srcptr"], ref["src_slot"], n, C, dP2)
     close(gpu[-1][:, C:], cpu[-1][:, C:], 1e-5, "dPsrc")
+    dPsrc_two_pass = gpu[-1][:, C:].cpu()
+    # dq = NULL: source gradients accumulate atomically inside the kernel (no dq buffer, no second pass)
+    dP3, dtab3 = torch.full((n, 2 * C), 7.0), torch.zeros(60, C)
+    cpu, gpu = run_both("gnn_pna_aggregate_bwd", gA, P, tab, A_gpu, ref["rowptr"], ref["col_src"], ref["col_code"], n,
+                        T, F, dP3, None, dtab3, zws, nb)
+    close(gpu[-5][:, :C], cpu[-5][:, :C], 1e-5, "dPdst (atomic variant)")
+    close(gpu[-5][:, C:], cpu[-5][:, C:], 2e-5, "dPsrc (atomic variant)")
+    close(gpu[-5][:, C:], dPsrc_two_pass, 2e-5, "dPsrc atomic vs two-pass")
+    close(gpu[-3], cpu[-3], 1e-4, "dtab (atomic variant)")
+    assert int(gpu[-2].count_nonzero()) == 0
 
 
 def test_general_message_path():
