@@ -256,7 +256,7 @@ extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int
 // partial tables in global memory with native 128-bit reductions (RED.E.ADD.F32x4 at the L2), summed afterwards.
 constexpr int DTAB_PARTS = 64;
 
-__global__ void __launch_bounds__(AGG_THREADS)
+__global__ void __launch_bounds__(AGG_THREADS, 3)
 pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__ P,
                          const float* __restrict__ tab, const float* __restrict__ A,
                          const int* __restrict__ rowptr, const int* __restrict__ col_src,
@@ -287,6 +287,17 @@ pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__
             const float* pbase = P + c;
             const float* tbase = tab + c;
             const int m = min(cnt, 32);
+            // gradient rows of this node: requested before pass 1, used after it
+            float4 g_mean = zero, g_min = zero, g_max = zero, g_std = zero, sd = zero;
+            if (live) {
+                const int t = c / F, f = c - t * F;
+                const int64_t off = node * (4 * (int64_t)C) + (int64_t)t * 4 * F + f;
+                g_mean = ldg4(gA + off);
+                g_min = ldg4(gA + off + F);
+                g_max = ldg4(gA + off + 2 * F);
+                g_std = ldg4(gA + off + 3 * F);
+                sd = ldg4(A + off + 3 * F);
+            }
             // ---- pass 1: shifted sum, min / max with tie counts
             float4 q0 = zero, s1 = zero, mn = zero, mx = zero, nmin = zero, nmax = zero;
             for (int k = 0; k < cnt; ++k) {
@@ -304,13 +315,13 @@ pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__
                     nmin = make_float4(1.f, 1.f, 1.f, 1.f);
                     nmax = nmin;
                 } else {
-#define UPD(X)                                                      \
-    {                                                               \
-        s1.X += q.X - q0.X;                                         \
-        if (q.X < mn.X) { mn.X = q.X; nmin.X = 1.f; }               \
-        else if (q.X == mn.X) nmin.X += 1.f;                        \
-        if (q.X > mx.X) { mx.X = q.X; nmax.X = 1.f; }               \
-        else if (q.X == mx.X) nmax.X += 1.f;                        \
+#define UPD(X)                                                              \
+    {                                                                       \
+        s1.X += q.X - q0.X;                                                 \
+        nmin.X = q.X < mn.X ? 1.f : (q.X == mn.X ? nmin.X + 1.f : nmin.X);  \
+        mn.X = fminf(mn.X, q.X);                                            \
+        nmax.X = q.X > mx.X ? 1.f : (q.X == mx.X ? nmax.X + 1.f : nmax.X);  \
+        mx.X = fmaxf(mx.X, q.X);                                            \
     }
                     UPD(x) UPD(y) UPD(z) UPD(w)
 #undef UPD
@@ -322,18 +333,13 @@ pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__
                                             fmaf(s1.z, inv_cnt, q0.z), fmaf(s1.w, inv_cnt, q0.w));
             float4 cm = zero, cmin = zero, cmax = zero, cs = zero;
             if (live) {
-                const int t = c / F, f = c - t * F;
-                const int64_t off = node * (4 * (int64_t)C) + (int64_t)t * 4 * F + f;
-                const float4 g_mean = ldg4(gA + off), g_min = ldg4(gA + off + F), g_max = ldg4(gA + off + 2 * F),
-                             g_std = ldg4(gA + off + 3 * F);
-                const float4 sd = ldg4(A + off + 3 * F);
                 st4(dP + node * ldp + c, make_float4(g_mean.x + g_min.x + g_max.x, g_mean.y + g_min.y + g_max.y,
                                                      g_mean.z + g_min.z + g_max.z, g_mean.w + g_min.w + g_max.w));
 #define COEF(X)                                              \
     cm.X = g_mean.X * inv_cnt;                               \
-    cmin.X = g_min.X / nmin.X;                               \
-    cmax.X = g_max.X / nmax.X;                               \
-    cs.X = sd.X > 0.f ? g_std.X * inv_cnt / sd.X : 0.f;
+    cmin.X = g_min.X * __frcp_rn(nmin.X);                    \
+    cmax.X = g_max.X * __frcp_rn(nmax.X);                    \
+    cs.X = sd.X > 0.f ? g_std.X * inv_cnt * __frcp_rn(sd.X) : 0.f;
                 COEF(x) COEF(y) COEF(z) COEF(w)
 #undef COEF
             }
