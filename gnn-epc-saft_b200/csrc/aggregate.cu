@@ -369,17 +369,28 @@ pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__
     }
 }
 
-// dtab_accum[k] += sum over the partial tables; the partial tables are cleared for the next call
-__global__ void dtab_reduce_kernel(float* __restrict__ parts, int total, float* __restrict__ dtab_accum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+// dtab_accum[k] += sum over the partial tables; the partial tables are cleared for the next call.
+// block (32 outputs, 8 part phases): every thread sums DTAB_PARTS / 8 partials with independent loads
+__global__ void __launch_bounds__(256)
+dtab_reduce_kernel(float* __restrict__ parts, int total, float* __restrict__ dtab_accum) {
+    __shared__ float red[8][33];
+    const int i = blockIdx.x * 32 + threadIdx.x;
     float acc = 0.f;
-#pragma unroll 8
-    for (int p = 0; p < DTAB_PARTS; ++p) {
-        acc += parts[(size_t)p * total + i];
-        parts[(size_t)p * total + i] = 0.f;
+    if (i < total) {
+#pragma unroll
+        for (int p = threadIdx.y; p < DTAB_PARTS; p += 8) {
+            acc += parts[(size_t)p * total + i];
+            parts[(size_t)p * total + i] = 0.f;
+        }
     }
-    dtab_accum[i] += acc;
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && i < total) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        dtab_accum[i] += t;
+    }
 }
 
 extern "C" int64_t gnn_pna_aggregate_bwd_workspace_bytes(int towers, int F) {
@@ -407,7 +418,7 @@ extern "C" int gnn_pna_aggregate_bwd(const float* gA, const float* P, const floa
     pna_aggregate_bwd_kernel<<<(unsigned)blocks, AGG_THREADS, 0, st>>>(gA, P, tab, A, rowptr, col_src, col_code, n, C, F,
                                                                        dP, dq, parts);
     const int total = GNN_NUM_BOND_CODES * C;
-    dtab_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(parts, total, dtab_accum);
+    dtab_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(parts, total, dtab_accum);
     return gnn_launch_status();
 }
 

@@ -839,17 +839,22 @@ __device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnP
 //             arrive tmem_empty[b]   (two accumulator buffers in TMEM: epilogue of item i overlaps item i+1)
 // grid (k-blocks, n tiles, groups): writes the B operand of every (group, n tile, k-block) as the exact
 // shared-memory image (SWIZZLE_128B, hi/lo planes) so that the GEMM can fetch it with one TMA bulk copy
+constexpr int PACK_ROWS = 32;
 template <int MODE, class BL>
 __global__ void __launch_bounds__(PROD_GROUP_THREADS)
 pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t* __restrict__ out) {
     constexpr int KB_ELEMS = MODE == MODE_TF32X3 ? 32 : 64;
     constexpr int PARTS = MODE == MODE_TF32X3 ? 2 : 1;
-    const int kb = blockIdx.x, nt = blockIdx.y, grp = blockIdx.z;
+    // blockIdx.x = k-block * row_splits + row split: a CTA writes PACK_ROWS rows (whole 8-row swizzle atoms) of a tile
+    const int row_splits = (BN + PACK_ROWS - 1) / PACK_ROWS;
+    const int kb = blockIdx.x / row_splits, r_begin = (blockIdx.x % row_splits) * PACK_ROWS;
+    const int nt = blockIdx.y, grp = blockIdx.z;
     BL bl = bl0;
     bl.set_group(grp);
     const uint32_t b_plane = (uint32_t)BN * ROW_BYTES;
-    uint8_t* tile = out + ((size_t)(grp * n_tiles + nt) * num_kb + kb) * (size_t)(PARTS * b_plane);
-    produce_tile<MODE>(bl, tile, b_plane, BN, (int64_t)nt * BN, (int64_t)kb * KB_ELEMS, K, threadIdx.x);
+    uint8_t* tile = out + ((size_t)(grp * n_tiles + nt) * num_kb + kb) * (size_t)(PARTS * b_plane) + (size_t)(r_begin / 8) * 1024;
+    const int rows = BN - r_begin < PACK_ROWS ? BN - r_begin : PACK_ROWS;
+    produce_tile<MODE>(bl, tile, b_plane, rows, (int64_t)nt * BN + r_begin, (int64_t)kb * KB_ELEMS, K, threadIdx.x);
 }
 
 template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP>
@@ -1210,7 +1215,7 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
         const bool packed = pack_ws != nullptr && splits == 1 && g.m_tiles >= 2 && pack_bytes <= pack_ws_bytes &&
                             (reinterpret_cast<uintptr_t>(pack_ws) & 127) == 0;
         if (packed) {
-            dim3 pgrid((unsigned)num_kb, (unsigned)g.n_tiles, (unsigned)groups);
+            dim3 pgrid((unsigned)(num_kb * ((BN + PACK_ROWS - 1) / PACK_ROWS)), (unsigned)g.n_tiles, (unsigned)groups);
             pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
                                                                           reinterpret_cast<uint8_t*>(pack_ws));
             auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP>;

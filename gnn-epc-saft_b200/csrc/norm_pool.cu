@@ -129,14 +129,16 @@ bn_partial4_kernel(const float* __restrict__ Y, const float* __restrict__ dOut, 
 
 static bool bn_vec_ok(int C) { return (C & 3) == 0 && C >= 4 && C <= 1024 && (256 % (C >> 2)) == 0; }
 
-// Sum the per-CTA partials of one column; launched with dim3(32, 8): threadIdx.y strides the parts.  Returns the
-// totals in thread y == 0 (other threads get garbage and must not write).
+// Sum the per-CTA partials of one column; launched with dim3(32, FIN_TY): threadIdx.y strides the parts.  Returns
+// the totals in thread y == 0 (other threads get garbage and must not write).
+constexpr int FIN_TY = 32;
 __device__ __forceinline__ void reduce_parts(const double* __restrict__ partial, int nparts, int C, int c, double& s,
                                              double& ss) {
-    __shared__ double r0[8][33], r1[8][33];
+    __shared__ double r0[FIN_TY][33], r1[FIN_TY][33];
     double a = 0.0, b = 0.0;
     if (c < C)
-        for (int p = threadIdx.y; p < nparts; p += 8) {
+#pragma unroll 4
+        for (int p = threadIdx.y; p < nparts; p += FIN_TY) {
             a += partial[((int64_t)p * 2 + 0) * C + c];
             b += partial[((int64_t)p * 2 + 1) * C + c];
         }
@@ -145,7 +147,8 @@ __device__ __forceinline__ void reduce_parts(const double* __restrict__ partial,
     __syncthreads();
     s = ss = 0.0;
     if (threadIdx.y == 0)
-        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int k = 0; k < FIN_TY; ++k) {
             s += r0[k][threadIdx.x];
             ss += r1[k][threadIdx.x];
         }
@@ -195,7 +198,7 @@ extern "C" int gnn_bn_stats(const float* Y, int64_t rows, int C, int training, f
             bn_partial_kernel<0><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, nullptr, nullptr, nullptr, nullptr, rows, C,
                                                                           0, partial);
     }
-    bn_stats_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, parts, rows, C, training, eps, momentum,
+    bn_stats_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_TY), 0, st>>>(partial, parts, rows, C, training, eps, momentum,
                                                               running_mean, running_var, num_batches_tracked, stats);
     return gnn_launch_status();
 }
@@ -333,7 +336,7 @@ extern "C" int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* st
                                                                             partial);
     else
         bn_partial_kernel<1><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, dOut, stats, gamma, beta, rows, C, relu, partial);
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st>>>(partial, parts, C, sums, dgamma, dbeta);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_TY), 0, st>>>(partial, parts, C, sums, dgamma, dbeta);
     if ((C & 3) == 0)
         bn_act_bwd_apply4_kernel<<<ew_grid(rows * C / 4, 256), 256, 0, st>>>(dOut, Y, stats, gamma, beta, sums, rows, C,
                                                                              relu, training, dY);
