@@ -269,6 +269,15 @@ def main():
     roofline = {"kernel": "pna_aggregate_fwd_kernel<1>", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": agg_ms, "launches_timed": cnt}
+    # DRAM bytes per launch of the same kernel on the same workload from the committed ncu --set full capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_agg_fwd_traffic.json")) as fh:
+            tr = json.load(fh)
+        if tr.get("workload_nodes") == int(n_nodes):
+            roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            roofline["traffic_source"] = "profiles/r1_agg_fwd_traffic.json (ncu --set full, per launch)"
+    except (OSError, ValueError, KeyError):
+        pass
     btot, bcnt = agg.get("gnn_pna_aggregate_bwd", (0.0, 0))
     roofline["bwd_avg_launch_ms"] = btot / max(bcnt, 1)
 
