@@ -35,7 +35,11 @@ constexpr int PROD_GROUP_THREADS = 128;
 __host__ __device__ constexpr int cta_threads(bool mn_major) {
     return (epi_warps(mn_major) + (mn_major ? 0 : 1)) * 32 + PROD_GROUPS * PROD_GROUP_THREADS;
 }
-enum { MODE_TF32X3 = 0, MODE_BF16 = 1 };
+// MODE_TF32X3: three tf32 MMAs per K step.  MODE_TF32C: the hi*hi product on the tf32 path plus ONE bf16 MMA whose
+// doubled K carries both cross terms ([lo | hi] x [hi ; lo], operands rounded to bf16): two instructions instead of
+// three at ~2^-19 relative error per product.  MODE_BF16: one bf16 MMA.
+enum { MODE_TF32X3 = 0, MODE_BF16 = 1, MODE_TF32C = 2 };
+__host__ __device__ constexpr bool tf32_like(int mode) { return mode != MODE_BF16; }
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,7 +101,7 @@ __device__ __forceinline__ bool elect_one() {     // one lane of the (converged)
 }
 template <int MODE>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    if (MODE == MODE_TF32X3)
+    if (tf32_like(MODE))
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
@@ -155,7 +159,7 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int chunk) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32, a/b format, K-major both, N>>3, M>>4
 __host__ __device__ inline uint32_t instr_desc(int mode, int n, int mn_major) {
-    uint32_t fmt = mode == MODE_TF32X3 ? 2u : 1u;   // TF32 = 2, BF16 = 1
+    uint32_t fmt = mode == MODE_BF16 ? 1u : 2u;     // TF32 = 2, BF16 = 1
     uint32_t major = mn_major ? ((1u << 15) | (1u << 16)) : 0u;   // a_major / b_major: 0 = K, 1 = MN
     return (1u << 4) | (fmt << 7) | (fmt << 10) | major | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -544,6 +548,30 @@ __device__ __forceinline__ void put_chunk_tf32(uint8_t* tile, uint32_t plane_byt
     *reinterpret_cast<float4*>(tile + off) = hi;
     *reinterpret_cast<float4*>(tile + plane_bytes + off) = lo;
 }
+// four fp32 -> four bf16 by truncation: one PRMT per pair (the cvt.rn.bf16x2 path made the producers the
+// bottleneck); the operands of the correction MMA only need ~8 bits
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+    return make_uint2(__byte_perm(__float_as_uint(v.x), __float_as_uint(v.y), 0x7632),
+                      __byte_perm(__float_as_uint(v.z), __float_as_uint(v.w), 0x7632));
+}
+// MODE_TF32C: hi goes to the tf32 plane at `off`; the second plane is a bf16 tile whose K is doubled: part 0 at
+// `coff0`, part 1 at `coff1` (8-byte half chunks).  A operands store (lo, hi), B operands (hi, lo), so that the bf16
+// MMA over the doubled K sums lo_a*hi_b + hi_a*lo_b.
+template <bool IS_B>
+__device__ __forceinline__ void put_chunk_tf32c(uint8_t* tile, uint32_t plane_bytes, uint32_t off, uint32_t coff0,
+                                                uint32_t coff1, float4 v) {
+    float4 hi, lo;
+    split_tf32(v, hi, lo);
+    *reinterpret_cast<float4*>(tile + off) = hi;
+    *reinterpret_cast<uint2*>(tile + plane_bytes + coff0) = pack_bf16x4(IS_B ? hi : lo);
+    *reinterpret_cast<uint2*>(tile + plane_bytes + coff1) = pack_bf16x4(IS_B ? lo : hi);
+}
+// K-major tiles: correction-plane offset of the 4-element chunk c (0..7) of `row`, part 0 / 1.  The two parts of
+// eight consecutive K values share one 32-byte MMA slice (16-byte chunk 2*(c>>1) + part): any K order works as long
+// as A and B agree, and this one lets a warp's 8-byte stores (4 rows x 64 B) cover all 32 banks.
+__device__ __forceinline__ uint32_t sw128_coff(int row, int c, int part) {
+    return (uint32_t)row * ROW_BYTES + (uint32_t)((((c >> 1) * 2 + part) ^ (row & 7)) << 4) + (uint32_t)(c & 1) * 8u;
+}
 __device__ __forceinline__ void put_chunk_bf16(uint8_t* tile, uint32_t off, float4 a, float4 b) {
     __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
     __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
@@ -564,13 +592,13 @@ __device__ __forceinline__ float4 mask_k(float4 v, int64_t k, int64_t k_end) {  
 template <int MODE, class L>
 __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_t plane_bytes, int rows, int64_t row0,
                                              int64_t kbase, int64_t k_end, int p) {
-    constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;     // elements per 16-byte chunk
+    constexpr int EPC = tf32_like(MODE) ? 4 : 8;     // elements per 16-byte chunk
     if (!L::kTransposed) {
         // 8 lanes sweep the 8 chunks of a row (128 contiguous bytes in memory), 16 rows per pass.
         // All loads of the tile (up to 8 rows per thread) are issued before the first conversion.
         const int c = p & 7, r0 = p >> 3;
         const int64_t k = kbase + c * EPC;
-        constexpr int NB = MODE == MODE_TF32X3 ? 8 : 4;        // rows per thread per batch (register budget)
+        constexpr int NB = tf32_like(MODE) ? 8 : 4;        // rows per thread per batch (register budget)
         for (int rb = 0; rb < rows; rb += 16 * NB) {
             float4 v[NB], w[MODE == MODE_BF16 ? NB : 1];
 #pragma unroll
@@ -587,13 +615,15 @@ __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_
                 const int r = rb + r0 + 16 * i;
                 if (r < rows) {
                     if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, sw128_offset(r, c), v[i]);
+                    else if (MODE == MODE_TF32C)
+                        put_chunk_tf32c<true>(tile, plane_bytes, sw128_offset(r, c), sw128_coff(r, c, 0), sw128_coff(r, c, 1), v[i]);
                     else put_chunk_bf16(tile, sw128_offset(r, c), v[i], w[MODE == MODE_BF16 ? i : 0]);
                 }
             }
         }
     } else {
         // lanes run along rows (the contiguous dimension of a transposed operand); each thread owns whole rows
-        constexpr int NB = MODE == MODE_TF32X3 ? CHUNKS : CHUNKS / 2;
+        constexpr int NB = tf32_like(MODE) ? CHUNKS : CHUNKS / 2;
         for (int r = p; r < rows; r += PROD_GROUP_THREADS) {
 #pragma unroll
             for (int cb = 0; cb < CHUNKS; cb += NB) {
@@ -609,6 +639,9 @@ __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, sw128_offset(r, cb + i), v[i]);
+                    else if (MODE == MODE_TF32C)
+                        put_chunk_tf32c<true>(tile, plane_bytes, sw128_offset(r, cb + i), sw128_coff(r, cb + i, 0),
+                                              sw128_coff(r, cb + i, 1), v[i]);
                     else put_chunk_bf16(tile, sw128_offset(r, cb + i), v[i], w[MODE == MODE_BF16 ? i : 0]);
                 }
             }
@@ -623,7 +656,7 @@ __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_
 template <int MODE, bool SCALED>
 __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes,
                                               int64_t m0, int64_t kbase, int64_t k_end, int p) {
-    constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
+    constexpr int EPC = tf32_like(MODE) ? 4 : 8;
     const int c = p & 7, r0 = p >> 3;
     const int64_t k = kbase + c * EPC;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -631,6 +664,7 @@ __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uin
     const SegRef s1 = (MODE == MODE_BF16 && k + 4 < k_end) ? seg_resolve(op, k + 4, grp) : SegRef{nullptr, 0, -1};
     const int64_t row0 = m0 + r0;
     const uint32_t off0 = (uint32_t)r0 * ROW_BYTES + (uint32_t)((c ^ (r0 & 7)) << 4);   // (r0 + 16 i) & 7 == r0 & 7
+    const uint32_t coff0 = sw128_coff(r0, c, 0), coff1 = sw128_coff(r0, c, 1);
     const float* q0 = s0.ptr != nullptr ? s0.ptr + row0 * s0.ld : nullptr;
     const float* q1 = s1.ptr != nullptr ? s1.ptr + row0 * s1.ld : nullptr;
     const int64_t st0 = 16 * s0.ld, st1 = 16 * s1.ld;
@@ -672,6 +706,9 @@ __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uin
     for (int i = 0; i < 8; ++i) {
         const uint32_t off = off0 + (uint32_t)i * (16 * ROW_BYTES);
         if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, off, v[i]);
+        else if (MODE == MODE_TF32C)
+            put_chunk_tf32c<false>(tile, plane_bytes, off, coff0 + (uint32_t)i * (16 * ROW_BYTES),
+                                   coff1 + (uint32_t)i * (16 * ROW_BYTES), v[i]);
         else put_chunk_bf16(tile, off, v[i], w[MODE == MODE_BF16 ? i : 0]);
     }
 }
@@ -684,10 +721,10 @@ __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uin
 template <int MODE, bool SCALED>
 __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes, int R,
                                                int64_t mn0, int64_t kbase, int64_t k_end, int p, float4* colacc = nullptr,
-                                               int KB = MODE == MODE_TF32X3 ? 32 : 64) {
-    constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
-    constexpr int KR = MODE == MODE_TF32X3 ? 4 : 8;
-    constexpr int KR_SHIFT = MODE == MODE_TF32X3 ? 2 : 3;
+                                               int KB = tf32_like(MODE) ? 32 : 64) {
+    constexpr int EPC = tf32_like(MODE) ? 4 : 8;
+    constexpr int KR = tf32_like(MODE) ? 4 : 8;
+    constexpr int KR_SHIFT = tf32_like(MODE) ? 2 : 3;
     constexpr uint32_t ATOM = KR * 128;
     const int cpr = R / EPC;                                     // chunks per K row: power of two, 4..64
     const int ch = p & (cpr - 1), kk0 = p / cpr, step = PROD_GROUP_THREADS / cpr;
@@ -743,10 +780,10 @@ __device__ __forceinline__ void produce_mn_seg(const SegOperand& op, int grp, ui
             const int kk = kk0 + (j0 + i) * step;
             if (kk < KB) {
                 const int kr = kk & (KR - 1);
-                const uint32_t swz = MODE == MODE_TF32X3 ? (uint32_t)((((c8 >> 1) ^ kr) << 5) | ((c8 & 1) << 4))
+                const uint32_t swz = tf32_like(MODE) ? (uint32_t)((((c8 >> 1) ^ kr) << 5) | ((c8 & 1) << 4))
                                                          : (uint32_t)((c8 ^ kr) << 4);
                 const uint32_t off = (uint32_t)(kk >> KR_SHIFT) * kgs + mg_off + (uint32_t)kr * 128u + swz;
-                if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, off, v[i]);
+                if (tf32_like(MODE)) put_chunk_tf32<MODE>(tile, plane_bytes, off, v[i]);
                 else put_chunk_bf16(tile, off, v[i], w[MODE == MODE_BF16 ? i : 0]);
             }
         }
@@ -765,7 +802,15 @@ struct MnPlan {
     int64_t step_ld;       // step * row_ld
     int kk0, step;
     uint32_t off0, off1, dk2;   // smem offset of row i: off[i & 1] + (i >> 1) * dk2
+    int ch;                     // 4-column chunk index inside the tile (MODE_TF32C correction plane)
+    uint32_t kgs16;             // bytes between 8-row K groups of the bf16 correction plane
 };
+// bf16 MN-major tile (8-row atoms, 16-byte swizzle): byte offset of the 4-column half chunk ch4 in K row kk2
+__device__ __forceinline__ uint32_t mn_coff_bf16(int kk2, int ch4, uint32_t kgs16) {
+    const int kr = kk2 & 7, c16 = ch4 >> 1;
+    return (uint32_t)(kk2 >> 3) * kgs16 + (uint32_t)(c16 >> 3) * 1024u + (uint32_t)kr * 128u +
+           (uint32_t)(((c16 & 7) ^ kr) << 4) + (uint32_t)(ch4 & 1) * 8u;
+}
 __device__ __forceinline__ uint32_t mn_off_tf32(int kk, int c8, uint32_t mg_off, uint32_t kgs) {
     const int kr = kk & 3;
     return (uint32_t)(kk >> 2) * kgs + mg_off + (uint32_t)kr * 128u + (uint32_t)((((c8 >> 1) ^ kr) << 5) | ((c8 & 1) << 4));
@@ -784,12 +829,15 @@ __device__ __forceinline__ MnPlan mn_plan(const SegOperand& op, int grp, int R, 
     pl.off0 = mn_off_tf32(pl.kk0, ch & 7, mg_off, kgs);
     pl.off1 = mn_off_tf32(pl.kk0 + pl.step, ch & 7, mg_off, kgs);
     pl.dk2 = mn_off_tf32(pl.kk0 + 2 * pl.step, ch & 7, mg_off, kgs) - pl.off0;
+    pl.ch = ch;
+    pl.kgs16 = (uint32_t)(R >> 6) * 1024u;
     return pl;
 }
-template <bool SCALED, int NA, int NB>
+template <int MODE, bool SCALED, int NA, int NB>
 __device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnPlan& pb, uint8_t* a_tile, uint32_t a_plane,
                                                      uint8_t* b_tile, uint32_t b_plane, int64_t kbase, int64_t lim,
                                                      float4* colacc) {
+    constexpr int KBR = NA * 4;                              // K rows (nodes) of this k-block: A has step 4
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 va[NA], vb[NB];
     float f[NA];
@@ -823,11 +871,26 @@ __device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnP
         if (SCALED) va[i] = make_float4(va[i].x * f[i], va[i].y * f[i], va[i].z * f[i], va[i].w * f[i]);
         if (colacc != nullptr)
             colacc[0] = make_float4(colacc[0].x + va[i].x, colacc[0].y + va[i].y, colacc[0].z + va[i].z, colacc[0].w + va[i].w);
-        put_chunk_tf32<MODE_TF32X3>(a_tile, a_plane, ((i & 1) ? pa.off1 : pa.off0) + (uint32_t)(i >> 1) * pa.dk2, va[i]);
+        const uint32_t off = ((i & 1) ? pa.off1 : pa.off0) + (uint32_t)(i >> 1) * pa.dk2;
+        if (MODE == MODE_TF32C) {
+            const int kk = pa.kk0 + i * pa.step;
+            put_chunk_tf32c<false>(a_tile, a_plane, off, mn_coff_bf16(kk, pa.ch, pa.kgs16),
+                                   mn_coff_bf16(KBR + kk, pa.ch, pa.kgs16), va[i]);
+        } else {
+            put_chunk_tf32<MODE_TF32X3>(a_tile, a_plane, off, va[i]);
+        }
     }
 #pragma unroll
-    for (int i = 0; i < NB; ++i)
-        put_chunk_tf32<MODE_TF32X3>(b_tile, b_plane, ((i & 1) ? pb.off1 : pb.off0) + (uint32_t)(i >> 1) * pb.dk2, vb[i]);
+    for (int i = 0; i < NB; ++i) {
+        const uint32_t off = ((i & 1) ? pb.off1 : pb.off0) + (uint32_t)(i >> 1) * pb.dk2;
+        if (MODE == MODE_TF32C) {
+            const int kk = pb.kk0 + i * pb.step;
+            put_chunk_tf32c<true>(b_tile, b_plane, off, mn_coff_bf16(kk, pb.ch, pb.kgs16),
+                                  mn_coff_bf16(KBR + kk, pb.ch, pb.kgs16), vb[i]);
+        } else {
+            put_chunk_tf32<MODE_TF32X3>(b_tile, b_plane, off, vb[i]);
+        }
+    }
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -843,8 +906,8 @@ constexpr int PACK_ROWS = 32;
 template <int MODE, class BL>
 __global__ void __launch_bounds__(PROD_GROUP_THREADS)
 pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t* __restrict__ out) {
-    constexpr int KB_ELEMS = MODE == MODE_TF32X3 ? 32 : 64;
-    constexpr int PARTS = MODE == MODE_TF32X3 ? 2 : 1;
+    constexpr int KB_ELEMS = tf32_like(MODE) ? 32 : 64;
+    constexpr int PARTS = tf32_like(MODE) ? 2 : 1;
     // blockIdx.x = k-block * row_splits + row split: a CTA writes PACK_ROWS rows (whole 8-row swizzle atoms) of a tile
     const int row_splits = (BN + PACK_ROWS - 1) / PACK_ROWS;
     const int kb = blockIdx.x / row_splits, r_begin = (blockIdx.x % row_splits) * PACK_ROWS;
@@ -864,8 +927,8 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
 
-    constexpr int KB_ELEMS = MODE == MODE_TF32X3 ? 32 : 64;
-    constexpr int PARTS = MODE == MODE_TF32X3 ? 2 : 1;
+    constexpr int KB_ELEMS = tf32_like(MODE) ? 32 : 64;
+    constexpr int PARTS = tf32_like(MODE) ? 2 : 1;
     constexpr int EPI_WARPS = epi_warps(MN_MAJOR), MMA_WARP = MN_MAJOR ? 0 : EPI_WARPS;
     constexpr int PROD_WARP0 = MN_MAJOR ? EPI_WARPS : EPI_WARPS + 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -976,6 +1039,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
     };
     // =============================== MMA issue (one work item, one warp) ===============================
     const uint32_t idesc = instr_desc(MODE, BN, MN_MAJOR ? 1 : 0);
+    const uint32_t idesc16 = instr_desc(MODE_BF16, BN, MN_MAJOR ? 1 : 0);      // correction MMAs of MODE_TF32C
     auto mma_item = [&](int64_t item, uint32_t t, uint32_t& it) {
         {
             int64_t m0, k_begin, k_end;
@@ -987,7 +1051,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + b * (uint32_t)BN;
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const uint32_t s = it % NS, use = it / NS;
+                const uint32_t s = it % NS, use = it / NS;          // warp-uniform, one warp: cheap enough
                 const long long mt0 = g.prof ? clock64() : 0;
                 mbar_wait(&full_bar[s], use & 1);
                 tc_fence_after();
@@ -999,6 +1063,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + a_plane;
                     const uint32_t b_hi = a_hi + PARTS * a_plane, b_lo = b_hi + b_plane;
                     const int ksteps = (CHUNKS / 2) / (int)kdiv;
+                    uint64_t corr_a[CHUNKS / 2], corr_b[CHUNKS / 2];
 #pragma unroll
                     for (int j = 0; j < CHUNKS / 2; ++j) {       // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
                         if (j >= ksteps) break;
@@ -1006,10 +1071,10 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         uint64_t dah, dal, dbh, dbl;
                         if (MN_MAJOR) {
                             // one MMA spans two K groups (tf32: 2 x 4 rows, bf16: 2 x 8 rows) linked by the stride offset
-                            constexpr uint32_t ATOM = MODE == MODE_TF32X3 ? 512 : 1024;
-                            constexpr uint32_t LT = MODE == MODE_TF32X3 ? 1 : 2;
-                            const uint32_t a_kgs = (BM * (MODE == MODE_TF32X3 ? 4 : 2) / 128) * ATOM;
-                            const uint32_t b_kgs = ((uint32_t)BN * (MODE == MODE_TF32X3 ? 4 : 2) / 128) * ATOM;
+                            constexpr uint32_t ATOM = tf32_like(MODE) ? 512 : 1024;
+                            constexpr uint32_t LT = tf32_like(MODE) ? 1 : 2;
+                            const uint32_t a_kgs = (BM * (tf32_like(MODE) ? 4 : 2) / 128) * ATOM;
+                            const uint32_t b_kgs = ((uint32_t)BN * (tf32_like(MODE) ? 4 : 2) / 128) * ATOM;
                             const uint32_t ao = j * 2 * a_kgs, bo = j * 2 * b_kgs;
                             dah = smem_desc_sw128_mn(a_hi + ao, ATOM, a_kgs, LT);
                             dal = smem_desc_sw128_mn(a_lo + ao, ATOM, a_kgs, LT);
@@ -1026,9 +1091,28 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                             umma<MODE>(tmem_d, dal, dbh, idesc, first);
                             umma<MODE>(tmem_d, dah, dbl, idesc, 1u);
                             umma<MODE>(tmem_d, dah, dbh, idesc, 1u);
+                        } else if (MODE == MODE_TF32C) {
+                            // hi*hi on the tf32 path, then one bf16 MMA over the K-doubled correction planes
+                            uint64_t dac, dbc;
+                            if (MN_MAJOR) {
+                                const uint32_t a_kgs16 = (BM * 2 / 128) * 1024u, b_kgs16 = ((uint32_t)BN * 2 / 128) * 1024u;
+                                dac = smem_desc_sw128_mn(a_lo + j * 2 * a_kgs16, 1024u, a_kgs16, 2u);
+                                dbc = smem_desc_sw128_mn(b_lo + j * 2 * b_kgs16, 1024u, b_kgs16, 2u);
+                            } else {
+                                dac = dal;
+                                dbc = dbl;
+                            }
+                            umma<MODE>(tmem_d, dah, dbh, idesc, first);
+                            corr_a[j] = dac;
+                            corr_b[j] = dbc;
                         } else {
                             umma<MODE>(tmem_d, dah, dbh, idesc, first);
                         }
+                    }
+                    if (MODE == MODE_TF32C) {      // the bf16 MMAs of the k-block go out together: one kind switch per k-block
+#pragma unroll
+                        for (int j = 0; j < CHUNKS / 2; ++j)
+                            if (j < ksteps) umma<MODE_BF16>(tmem_d, corr_a[j], corr_b[j], idesc16, 1u);
                     }
                     umma_commit(&empty_bar[s]);                       // smem stage reusable once these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full_bar[b]);
@@ -1065,7 +1149,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
         const int pg = (warp - PROD_WARP0) >> 2;                 // producer group 0..3
         const int p = tid - PROD_WARP0 * 32 - pg * PROD_GROUP_THREADS;
         const int total_kb = (int)((g.K + KB_ELEMS - 1) / KB_ELEMS);      // packed images exist only without split-K
-        uint32_t it = 0;
+        uint32_t it_mod = 0, my_use = 0;          // running k-block index modulo NS; k-blocks this group has produced
         for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x) {
             int64_t m0, k_begin, k_end;
             int n0, grp;
@@ -1076,15 +1160,19 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             float4 colacc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
             const bool do_colsum = MN_MAJOR && g.colsum.base != nullptr && n0 == 0;
             MnPlan pa{}, pb{};
-            if constexpr (MN_MAJOR && MODE == MODE_TF32X3) {
+            if constexpr (MN_MAJOR && tf32_like(MODE)) {
                 pa = mn_plan(aop, grp, BM, m0, p);
                 pb = mn_plan(bl, grp, BN, (int64_t)n0, p);
             }
-            for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                if ((int)(it % NS) != pg) continue;                // group pg owns ring stage pg (see below)
-                const uint32_t s = it % NS, use = it / NS;
+            // group pg owns ring stage pg: it produces the k-blocks whose running index is pg modulo NS
+            int kb_first = pg - (int)it_mod;
+            if (kb_first < 0) kb_first += NS;
+            if (pg >= NS) kb_first = num_kb;                       // fewer stages than groups: the extra groups idle
+            it_mod = (it_mod + (uint32_t)num_kb) % (uint32_t)NS;
+            for (int kb = kb_first; kb < num_kb; kb += NS, ++my_use) {
+                const uint32_t s = (uint32_t)pg, use = my_use;
                 const long long pt0 = g.prof ? clock64() : 0;
-                if (g.prof && p == 0 && it == 0) atomicAdd(g.prof + 12, (unsigned long long)(pt0 - kernel_t0));   // set-up until the first k-block
+                if (g.prof && p == 0 && pg == 0 && my_use == 0) atomicAdd(g.prof + 12, (unsigned long long)(pt0 - kernel_t0));   // set-up until the first k-block
                 if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
                 const long long pt1 = g.prof ? clock64() : 0;
                 uint8_t* stage = smem + (size_t)s * stage_bytes;
@@ -1098,15 +1186,15 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         bulk_g2s(stage + PARTS * a_plane, packed_b + tile_idx * bytes, bytes, &full_bar[s]);
                     }
                     produce_a_seg<MODE, SCALED>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
-                } else if constexpr (MN_MAJOR && MODE == MODE_TF32X3) {
+                } else if constexpr (MN_MAJOR && tf32_like(MODE)) {
                     // loads per thread: A (128 columns) KBR / 4 rows; B (BN columns) KBR * BN / 512 rows
                     const int64_t lim = k_end < aop.rows ? k_end : aop.rows;
                     uint8_t* bt = stage + PARTS * a_plane;
                     float4* ca = do_colsum ? colacc : nullptr;
-                    if (BN == 256) produce_mn_pair_tf32<SCALED, 4, 8>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
-                    else if (BN == 128) produce_mn_pair_tf32<SCALED, 4, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
-                    else if (BN == 64) produce_mn_pair_tf32<SCALED, 8, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
-                    else produce_mn_pair_tf32<SCALED, 8, 2>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
+                    if (BN == 256) produce_mn_pair_tf32<MODE, SCALED, 4, 8>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
+                    else if (BN == 128) produce_mn_pair_tf32<MODE, SCALED, 4, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
+                    else if (BN == 64) produce_mn_pair_tf32<MODE, SCALED, 8, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
+                    else produce_mn_pair_tf32<MODE, SCALED, 8, 2>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
                 } else if constexpr (MN_MAJOR) {
                     produce_mn_seg<MODE, SCALED>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p,
                                                  do_colsum ? colacc : nullptr, KBR);
@@ -1131,7 +1219,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     // bias gradient: reduce the per-thread column sums of this item across the 512 producer
                     // threads in shared memory, then one global atomic per column (the target is a handful of
                     // addresses shared by every CTA: per-thread atomics would serialise in one L2 slice)
-                    constexpr int EPC = MODE == MODE_TF32X3 ? 4 : 8;
+                    constexpr int EPC = tf32_like(MODE) ? 4 : 8;
                     constexpr int CPR = BM / EPC;
                     __shared__ float cs_stage[PROD_GROUPS * PROD_GROUP_THREADS * EPC];
                     const int pp = pg * PROD_GROUP_THREADS + p;
@@ -1178,12 +1266,12 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
                   ColSum colsum = ColSum{nullptr, 0, 0, 0, 1}) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     if (BN % 16 != 0 || BN < 16 || BN > 256) return GNN_ERR_UNSUPPORTED;
-    constexpr int parts = MODE == MODE_TF32X3 ? 2 : 1;
-    constexpr int kb_elems = MODE == MODE_TF32X3 ? 32 : 64;
+    constexpr int parts = tf32_like(MODE) ? 2 : 1;
+    constexpr int kb_elems = tf32_like(MODE) ? 32 : 64;
     // wide MN-major TF32X3 tiles use half-height k-blocks: 4 ring stages (one per producer group) still fit
-    const int kb_rows = (MN_MAJOR && MODE == MODE_TF32X3 && BN >= 128) ? kb_elems / 2 : kb_elems;
+    const int kb_rows = (MN_MAJOR && tf32_like(MODE) && BN >= 128) ? kb_elems / 2 : kb_elems;
     const size_t stage_bytes = (size_t)parts * (BM + BN) * ROW_BYTES * kb_rows / kb_elems;
-    const size_t fixed = 1024 + 256 + (MN_MAJOR ? PROD_GROUPS * PROD_GROUP_THREADS * (MODE == MODE_TF32X3 ? 16 : 32) : 0);
+    const size_t fixed = 1024 + 256 + (MN_MAJOR ? PROD_GROUPS * PROD_GROUP_THREADS * (tf32_like(MODE) ? 16 : 32) : 0);
     int stages = (int)((kSmemLimit - fixed) / stage_bytes);
     if (stages > PROD_GROUPS) stages = PROD_GROUPS;      // one producer group per ring stage
     if (stages < 2) return GNN_ERR_UNSUPPORTED;
@@ -1237,7 +1325,7 @@ static int pick_bn(int n) {
     return bn > 256 ? 256 : bn;
 }
 static int pick_bn_mn(int n, int mode) {          // MN-major tiles: (32 tf32 only) / 64 / 128 / 256 columns
-    int bn = mode == MODE_TF32X3 ? 32 : 64;
+    int bn = mode == MODE_TF32X3 ? 32 : 64;       // 16-bit MN-major tiles need whole 128-byte rows (64 columns)
     while (bn < n && bn < 256) bn <<= 1;
     return bn;
 }
@@ -1272,6 +1360,7 @@ using namespace tc;
 #define DISPATCH_MODE(precision, CALL)                         \
     do {                                                       \
         if ((precision) == 0) { constexpr int MODE = MODE_TF32X3; CALL; } \
+        else if ((precision) == 1) { constexpr int MODE = MODE_TF32C; CALL; } \
         else if ((precision) == 2) { constexpr int MODE = MODE_BF16; CALL; } \
         else return GNN_ERR_BAD_ARG;                           \
     } while (0)
@@ -1321,7 +1410,7 @@ extern "C" int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X
     DISPATCH_MODE(precision, {
         const int BN = pick_bn_mn(K, MODE);
         const int64_t tiles = gnn_ceil_div(N, BM) * gnn_ceil_div(K, BN);
-        splitk(M, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
+        splitk(M, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
         return (launch<MODE, true>(aop, bop, ep, N, K, BN, M, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
                                    ColSum{db, 0, 0, db ? N : 0, N}));
     });
@@ -1489,7 +1578,7 @@ extern "C" int gnn_tc_pna_proj_wgrad(const float* dP, const float* x, int64_t n,
     DISPATCH_MODE(precision, {
         const int BN = pick_bn_mn(F, MODE);
         const int64_t tiles = gnn_ceil_div(2 * C, BM) * gnn_ceil_div(F, BN);
-        splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
+        splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
         return (launch<MODE, true>(aop, bop, ep, 2 * C, F, BN, n, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
                                    ColSum{dbpre, 0, bpre_tower_stride, dbpre ? C : 0, F}));
     });
@@ -1519,7 +1608,7 @@ extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const floa
         DISPATCH_MODE(precision, {
             const int BN = pick_bn_mn(4 * F, MODE);
             const int64_t tiles = gnn_ceil_div(4 * F, BN) * gnn_ceil_div(3 * FoP, BM) * towers;
-            splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
+            splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
             rc = (launch<MODE, true, true>(aop, bop, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st, nullptr, 0,
                                      ColSum{dbpost, bpost_tower_stride, 0, dbpost ? F_out : 0, F_out}));
         });
@@ -1538,7 +1627,7 @@ extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const floa
         DISPATCH_MODE(precision, {
             const int BN = pick_bn_mn(F, MODE);
             const int64_t tiles = gnn_ceil_div(F, BN) * towers;
-            splitk(n, tiles, MODE == MODE_TF32X3 ? 32 : 64, k_chunk, splits);
+            splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
             rc = (launch<MODE, true>(aop, bop, ep, F_out, F, BN, n, k_chunk, splits, towers, st));
         });
         if (rc) return rc;

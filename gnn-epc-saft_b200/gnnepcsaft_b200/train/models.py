@@ -148,7 +148,7 @@ def _c(name, *args):
 
 
 # dense-stage dispatch: which kernel family runs the Linear layers
-MATMUL_MODES = {"simt": -1, "tf32x3": 0, "bf16": 2}
+MATMUL_MODES = {"simt": -1, "tf32x3": 0, "tf32c": 1, "bf16": 2}
 
 
 def _al(t, *dims):
@@ -311,6 +311,7 @@ class PNAPCSAFT(nn.Module):
         self._arena_offsets: List[int] = []
         self._row_off = None
         # dense stages: "tf32x3" = tcgen05 with fp32 operands split into tf32 hi+lo (fp32-level accuracy),
+        # "tf32c" = tf32 hi*hi + one K-doubled bf16 MMA for the cross terms (2 instead of 3 MMAs, ~2e-6 per product),
         # "bf16" = tcgen05 bf16 operands / fp32 accumulate (torch "medium" matmul precision, which the
         # reference itself sets at train.py:319), "simt" = plain fp32 FMA kernels
         self.matmul_precision = os.environ.get("GNN_B200_MATMUL", DEFAULT_MATMUL)

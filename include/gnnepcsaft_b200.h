@@ -201,7 +201,9 @@ int gnn_pna_post_wgrad(const float* dO, const float* x, const float* A, const fl
 /* ---------------------------------------------------------------- dense stages (tcgen05 / TMEM)
  * The same contractions on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
  * `precision`: 0 = TF32x3 (fp32 operands split into tf32 hi+lo, 3 MMAs: fp32-level accuracy, the
- * parity path), 2 = BF16 operands, fp32 accumulate (the reference's own
+ * parity path), 1 = TF32+BF16C (the hi*hi product on the tf32 path plus one bf16 MMA whose doubled K
+ * carries both cross terms: 2 MMAs, ~2^-19 relative error per product, still inside the 1e-5 parity
+ * bar), 2 = BF16 operands, fp32 accumulate (the reference's own
  * torch.set_float32_matmul_precision("medium"), train.py:319).  Semantics equal the gnn_linear_* /
  * gnn_pna_post_* entry points above (bias gradients are column sums taken by the operand producers of the
  * weight-gradient kernels; gnn_colsum_accum is the stand-alone version).  Operands must be 128-bit

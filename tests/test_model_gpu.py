@@ -29,7 +29,7 @@ def _errs(y, y32, y64):
 # fp32 parity bars per dense-stage kernel family: both must be within 1e-5 (max-normalised) of the fp32
 # oracle and of the fp64 truth; the exact-fp32 SIMT kernels must additionally be as close to the truth as
 # the fp32 oracle itself (factor 2), TF32x3 (tf32 hi+lo split on the tensor cores) is allowed 1e-5.
-FP32_MODES = ["tf32x3", "simt"]
+FP32_MODES = ["tf32x3", "tf32c", "simt"]
 
 
 def _fp32_bar(mode, e_o):
@@ -208,7 +208,7 @@ def test_full_size_properties_4096_graphs():
     assert float(flat_grads(m)[mask].abs().max()) > 0
 
 
-@pytest.mark.parametrize("precision,fwd_tol,grad_tol", [("tf32x3", 1e-5, 2e-3), ("simt", 1e-5, 2e-3), ("bf16", 3e-2, 3e-1)])
+@pytest.mark.parametrize("precision,fwd_tol,grad_tol", [("tf32x3", 1e-5, 2e-3), ("tf32c", 1e-5, 2e-3), ("simt", 1e-5, 2e-3), ("bf16", 3e-2, 3e-1)])
 @pytest.mark.parametrize("name", ["default", "pre2_post2", "wide_small"])
 def test_tensor_core_dense_stages(name, precision, fwd_tol, grad_tol):
     """Dense stages on tcgen05: TF32x3 must meet the fp32 parity bar; bf16 operands (the reference's
