@@ -37,7 +37,9 @@ METRIC = "molecular graphs/sec (train step: fwd+bwd+AdamW, fp32)"
 KERNELS_PER_CALL = {"gnn_build_csr": 11, "gnn_bn_stats": 2, "gnn_bn_act_bwd": 3, "gnn_bond_table_bwd": 3,
                     "gnn_pna_aggregate_bwd": 2, "gnn_tc_linear_fwd": 2, "gnn_tc_linear_dgrad": 2,
                     "gnn_tc_pna_post_fwd": 2, "gnn_tc_pna_post_dgrad": 2, "gnn_tc_pna_post_wgrad": 2,
-                    "gnn_tc_pna_proj_fwd": 2, "gnn_tc_pna_dx_dgrad": 2}
+                    "gnn_tc_pna_proj_fwd": 2, "gnn_tc_pna_dx_dgrad": 2, "gnn_pna_aggregate_src_bwd": 2,
+                    "gnn_tc_pna_postf_fwd": 2, "gnn_tc_pna_postf_wgrad": 2, "gnn_tc_pna_projsrc_fwd": 2,
+                    "gnn_tc_pna_dxf_dgrad": 2}
 
 
 def peaks():
@@ -239,7 +241,12 @@ def main():
         sampler.start()                      # samples clocks from the warm-up through the timed region
     for i in range(args.warmup):
         engine.step(dev_batches[i % NUM_BATCHES])
-    prof = M.KernelProfiler(watch=["gnn_pna_aggregate_fwd", "gnn_pna_aggregate_bwd"])
+    # the fused message+aggregate kernel: source-only variant when the destination projection is folded into the
+    # post weights (default for this model), [Pdst | Psrc] variant otherwise
+    folded = model._fold_dst(model._matmul_mode())
+    agg_fwd, agg_bwd = (("gnn_pna_aggregate_src_fwd", "gnn_pna_aggregate_src_bwd") if folded else
+                        ("gnn_pna_aggregate_fwd", "gnn_pna_aggregate_bwd"))
+    prof = M.KernelProfiler(watch=[agg_fwd, agg_bwd])
     M.set_profiler(prof)
     calls0 = M.ABI_CALLS
     sync_all()
@@ -263,22 +270,24 @@ def main():
     H, T, F = cfg.hidden_dim, 2, cfg.hidden_dim
     ep = n_edges + n_nodes                       # self-loops are implicit CSR entries
     alg_bytes = 4 * n_nodes * H + 16 * n_nodes * T * F + 5 * ep + 4 * (n_nodes + 1)
-    tot_ms, cnt = agg.get("gnn_pna_aggregate_fwd", (0.0, 0))
+    tot_ms, cnt = agg.get(agg_fwd, (0.0, 0))
     agg_ms = tot_ms / max(cnt, 1)
     achieved = alg_bytes / (agg_ms * 1e-3) / 1e9 if agg_ms > 0 else 0.0
-    roofline = {"kernel": "pna_aggregate_fwd_kernel<1>", "bound": "hbm", "achieved": achieved, "peak": peak,
+    roofline = {"kernel": "pna_aggregate_fwd_kernel<1, %s>" % ("true" if folded else "false"), "abi_call": agg_fwd,
+                "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": agg_ms, "launches_timed": cnt}
     # DRAM bytes per launch of the same kernel on the same workload from the committed ncu --set full capture
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_agg_fwd_traffic.json")) as fh:
+        tname = "r1_agg_src_fwd_traffic.json" if folded else "r1_agg_fwd_traffic.json"
+        with open(os.path.join(ROOT, "profiles", tname)) as fh:
             tr = json.load(fh)
         if tr.get("workload_nodes") == int(n_nodes):
             roofline["traffic"] = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-            roofline["traffic_source"] = "profiles/r1_agg_fwd_traffic.json (ncu --set full, per launch)"
+            roofline["traffic_source"] = f"profiles/{tname} (ncu --set full, per launch)"
     except (OSError, ValueError, KeyError):
         pass
-    btot, bcnt = agg.get("gnn_pna_aggregate_bwd", (0.0, 0))
+    btot, bcnt = agg.get(agg_bwd, (0.0, 0))
     roofline["bwd_avg_launch_ms"] = btot / max(bcnt, 1)
 
     # ---------------- per-kernel share table (separate instrumented pass, not part of any reported time)

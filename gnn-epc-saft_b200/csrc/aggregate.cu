@@ -108,7 +108,9 @@ __device__ __forceinline__ void seg_finish(const SegStat& st, int cnt, float4 pd
 // latency hiding.  Stores alone (209 MB) take 43 us in the same harness, a torch fill of that size 41 us; in the
 // training step the 105 MB of P written by the projection GEMM are still dirty in L2 and are evicted by this
 // kernel's stores, so DRAM sees ~314 MB of writes per launch.
-template <int NCHUNK>
+// SRC_ONLY: P is [n, C] = source projections only and the aggregates are those of the shift-free q (the destination
+// term is folded into the post GEMM's weights, gnn_pna_fold_fwd) - the kernel then reads half as much.
+template <int NCHUNK, bool SRC_ONLY>
 __global__ void __launch_bounds__(AGG_THREADS, 4)
 pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ tab,
                          const int* __restrict__ rowptr, const int* __restrict__ col_src,
@@ -116,7 +118,7 @@ pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ 
     const int lane = threadIdx.x & 31;
     const int warp0 = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
     const int nwarps = gridDim.x * AGG_WARPS;
-    const int ldp = 2 * C, lda = 4 * C;
+    const int ldp = SRC_ONLY ? C : 2 * C, lda = 4 * C, soff = SRC_ONLY ? 0 : C;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     int cj[NCHUNK], aoff[NCHUNK];
     bool live[NCHUNK];
@@ -130,10 +132,12 @@ pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ 
     for (int node = warp0; node < n; node += nwarps) {
         const int rp = __ldg(rowptr + node + (lane & 1));
         const int beg = __shfl_sync(GNN_FULL_MASK, rp, 0), end = __shfl_sync(GNN_FULL_MASK, rp, 1);
-        const int cnt = end - beg;
+        // REDUX result lives in a uniform register: the edge loops below are then provably warp-uniform and the
+        // compiler drops the divergence bookkeeping (BSSY / WARPSYNC) around the shuffles
+        const int cnt = __reduce_max_sync(GNN_FULL_MASK, end - beg);
         int my_src = 0, my_code = 0;                      // pre-scaled element offsets of the first 32 in-edges
         if (lane < cnt) {
-            my_src = __ldg(col_src + beg + lane) * ldp + C;
+            my_src = __ldg(col_src + beg + lane) * ldp + soff;
             my_code = (int)__ldg(col_code + beg + lane) * C;
         }
         float* const arow = A + (size_t)node * lda;
@@ -153,7 +157,7 @@ pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ 
             }
             const float* const pbase = P + cj[j];
             const float* const tbase = tab + cj[j];
-            const float4 pd = live[j] ? ldg4(prow + cj[j]) : zero;
+            const float4 pd = (!SRC_ONLY && live[j]) ? ldg4(prow + cj[j]) : zero;
             int so = __shfl_sync(GNN_FULL_MASK, my_src, 0), co = __shfl_sync(GNN_FULL_MASK, my_code, 0);
             float4 pn = live[j] ? ldg4(pbase + so) : zero, tn = live[j] ? ldg4(tbase + co) : zero;
             // edge 0 defines the shift q0
@@ -190,7 +194,7 @@ pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ 
                 mx = make_float4(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z), fmaxf(mx.w, q.w));
             }
             for (int s = beg + 32; s < end; ++s) {         // in-degree > 32 (never for molecules)
-                const int so2 = __ldg(col_src + s) * ldp + C, co2 = (int)__ldg(col_code + s) * C;
+                const int so2 = __ldg(col_src + s) * ldp + soff, co2 = (int)__ldg(col_code + s) * C;
                 if (live[j]) {
                     const float4 q = add4(ldg4(pbase + so2), ldg4(tbase + co2));
                     const float dx = q.x - q0.x, dy = q.y - q0.y, dz = q.z - q0.z, dw = q.w - q0.w;
@@ -223,9 +227,9 @@ static int agg_grid(int64_t n) {
     return (int)blocks;
 }
 
-extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int32_t* rowptr,
-                                     const int32_t* col_src, const uint8_t* col_code, int64_t n, int towers,
-                                     int F, float* A, void* stream) {
+template <bool SRC_ONLY>
+static int aggregate_fwd_launch(const float* P, const float* tab, const int32_t* rowptr, const int32_t* col_src,
+                                const uint8_t* col_code, int64_t n, int towers, int F, float* A, void* stream) {
     if (n < 0 || towers < 1 || F < 4 || (F & 3)) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
     const int C = towers * F;
@@ -235,7 +239,7 @@ extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int
     int64_t cap = (int64_t)gnn_sm_count() * 48;
     if (blocks > cap) blocks = cap;
     const int chunks = (C + 127) / 128;
-#define LAUNCH_FWD(CH) pna_aggregate_fwd_kernel<CH><<<(unsigned)blocks, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, (int)n, C, F, A)
+#define LAUNCH_FWD(CH) pna_aggregate_fwd_kernel<CH, SRC_ONLY><<<(unsigned)blocks, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, (int)n, C, F, A)
     switch (chunks) {
         case 1: LAUNCH_FWD(1); break;
         case 2: LAUNCH_FWD(2); break;
@@ -247,6 +251,17 @@ extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int
     return gnn_launch_status();
 }
 
+extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int32_t* rowptr,
+                                     const int32_t* col_src, const uint8_t* col_code, int64_t n, int towers,
+                                     int F, float* A, void* stream) {
+    return aggregate_fwd_launch<false>(P, tab, rowptr, col_src, col_code, n, towers, F, A, stream);
+}
+extern "C" int gnn_pna_aggregate_src_fwd(const float* Psrc, const float* tab, const int32_t* rowptr,
+                                         const int32_t* col_src, const uint8_t* col_code, int64_t n, int towers,
+                                         int F, float* A, void* stream) {
+    return aggregate_fwd_launch<true>(Psrc, tab, rowptr, col_src, col_code, n, towers, F, A, stream);
+}
+
 // ------------------------------------------------------------------ backward, factorised message
 // Per destination node: recompute the segment statistics of q (shifted by the first message exactly as in the
 // forward kernel), count ties, then emit
@@ -256,113 +271,143 @@ extern "C" int gnn_pna_aggregate_fwd(const float* P, const float* tab, const int
 // partial tables in global memory with native 128-bit reductions (RED.E.ADD.F32x4 at the L2), summed afterwards.
 constexpr int DTAB_PARTS = 64;
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));     // one MUFU op, max rel. error 2^-23 (no slow-path call)
+    return y;
+}
+
+// statistics of one more message for pass 1 (shifted sum, min / max with tie counts)
+__device__ __forceinline__ void bwd_stat(float q, float q0, float& s1, float& mn, float& mx, float& nmin, float& nmax) {
+    s1 += q - q0;
+    // branch-free: a new extremum resets the count to 1, a tie adds 1 (selects only; the nested ?: form compiled to
+    // per-lane divergent branches)
+    nmin = (q < mn ? 0.f : nmin) + (q <= mn ? 1.f : 0.f);
+    mn = fminf(mn, q);
+    nmax = (q > mx ? 0.f : nmax) + (q >= mx ? 1.f : 0.f);
+    mx = fmaxf(mx, q);
+}
+
+template <bool SRC_ONLY>
 __global__ void __launch_bounds__(AGG_THREADS, 3)
 pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__ P,
                          const float* __restrict__ tab, const float* __restrict__ A,
                          const int* __restrict__ rowptr, const int* __restrict__ col_src,
-                         const uint8_t* __restrict__ col_code, int64_t n, int C, int F,
+                         const uint8_t* __restrict__ col_code, int n, int C, int F,
                          float* __restrict__ dP, float* __restrict__ dq, float* __restrict__ dtab_parts) {
     const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (int64_t)blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
-    const int64_t nwarps = (int64_t)gridDim.x * AGG_WARPS;
-    const int ldp = 2 * C;
+    const int warp0 = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * AGG_WARPS;
+    const int ldp = SRC_ONLY ? C : 2 * C, soff = SRC_ONLY ? 0 : C;
     float* dtab = dtab_parts + (size_t)(blockIdx.x % DTAB_PARTS) * GNN_NUM_BOND_CODES * C;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t node = warp0; node < n; node += nwarps) {
+    for (int node = warp0; node < n; node += nwarps) {
         const int rp = __ldg(rowptr + node + (lane & 1));
         const int beg = __shfl_sync(GNN_FULL_MASK, rp, 0), end = __shfl_sync(GNN_FULL_MASK, rp, 1);
-        const int cnt = end - beg;
+        // REDUX writes a uniform register: the compiler then knows that the edge loops below are warp-uniform
+        // (no divergence bookkeeping around the shuffles)
+        const int cnt = __reduce_max_sync(GNN_FULL_MASK, end - beg);
         int my_src = 0, my_code = 0;
         if (lane < cnt) {
-            my_src = __ldg(col_src + beg + lane) * ldp + C;
+            my_src = __ldg(col_src + beg + lane) * ldp + soff;
             my_code = (int)__ldg(col_code + beg + lane) * C;
         }
+        const int m = min(cnt, 32);
         for (int cb = 0; cb < C; cb += 128) {                  // warp-uniform trip count (shuffles inside)
             const int c = cb + lane * 4;
             const bool live = c < C;
             if (cnt == 0) {
-                if (live) st4(dP + node * ldp + c, zero);
+                if (!SRC_ONLY && live) st4(dP + (size_t)node * ldp + c, zero);
                 continue;
             }
-            const float* pbase = P + c;
-            const float* tbase = tab + c;
-            const int m = min(cnt, 32);
+            const float* pbase = P + (live ? c : 0);           // dead lanes read column 0 (valid memory, results unused)
+            const float* tbase = tab + (live ? c : 0);
             // gradient rows of this node: requested before pass 1, used after it
             float4 g_mean = zero, g_min = zero, g_max = zero, g_std = zero, sd = zero;
             if (live) {
                 const int t = c / F, f = c - t * F;
-                const int64_t off = node * (4 * (int64_t)C) + (int64_t)t * 4 * F + f;
+                const size_t off = (size_t)node * (4 * (size_t)C) + (size_t)t * 4 * F + f;
                 g_mean = ldg4(gA + off);
                 g_min = ldg4(gA + off + F);
                 g_max = ldg4(gA + off + 2 * F);
                 g_std = ldg4(gA + off + 3 * F);
                 sd = ldg4(A + off + 3 * F);
             }
-            // ---- pass 1: shifted sum, min / max with tie counts
-            float4 q0 = zero, s1 = zero, mn = zero, mx = zero, nmin = zero, nmax = zero;
-            for (int k = 0; k < cnt; ++k) {
-                int so, co;
-                if (k < 32) {
-                    so = __shfl_sync(GNN_FULL_MASK, my_src, k);
-                    co = __shfl_sync(GNN_FULL_MASK, my_code, k);
-                } else {
-                    so = __ldg(col_src + beg + k) * ldp + C;
-                    co = (int)__ldg(col_code + beg + k) * C;
-                }
-                const float4 q = live ? add4(ldg4(pbase + so), ldg4(tbase + co)) : zero;
-                if (k == 0) {
-                    q0 = q; mn = q; mx = q;
-                    nmin = make_float4(1.f, 1.f, 1.f, 1.f);
-                    nmax = nmin;
-                } else {
-#define UPD(X)                                                              \
-    {                                                                       \
-        s1.X += q.X - q0.X;                                                 \
-        nmin.X = q.X < mn.X ? 1.f : (q.X == mn.X ? nmin.X + 1.f : nmin.X);  \
-        mn.X = fminf(mn.X, q.X);                                            \
-        nmax.X = q.X > mx.X ? 1.f : (q.X == mx.X ? nmax.X + 1.f : nmax.X);  \
-        mx.X = fmaxf(mx.X, q.X);                                            \
-    }
-                    UPD(x) UPD(y) UPD(z) UPD(w)
-#undef UPD
-                }
+            // ---- pass 1: shifted sum, min / max with tie counts; the row of edge k+1 is in flight while k is used
+            int so = __shfl_sync(GNN_FULL_MASK, my_src, 0), co = __shfl_sync(GNN_FULL_MASK, my_code, 0);
+            float4 pn = ldg4(pbase + so), tn = ldg4(tbase + co);
+            const float4 q0 = add4(pn, tn);
+            float4 s1 = zero, mn = q0, mx = q0;
+            float4 nmin = make_float4(1.f, 1.f, 1.f, 1.f), nmax = nmin;
+            if (1 < m) {
+                so = __shfl_sync(GNN_FULL_MASK, my_src, 1);
+                co = __shfl_sync(GNN_FULL_MASK, my_code, 1);
+                pn = ldg4(pbase + so);
+                tn = ldg4(tbase + co);
             }
-            (void)m;
-            const float inv_cnt = __frcp_rn((float)cnt);
+            for (int k = 1; k < m; ++k) {
+                const float4 q = add4(pn, tn);
+                if (k + 1 < m) {
+                    so = __shfl_sync(GNN_FULL_MASK, my_src, k + 1);
+                    co = __shfl_sync(GNN_FULL_MASK, my_code, k + 1);
+                    pn = ldg4(pbase + so);
+                    tn = ldg4(tbase + co);
+                }
+                bwd_stat(q.x, q0.x, s1.x, mn.x, mx.x, nmin.x, nmax.x);
+                bwd_stat(q.y, q0.y, s1.y, mn.y, mx.y, nmin.y, nmax.y);
+                bwd_stat(q.z, q0.z, s1.z, mn.z, mx.z, nmin.z, nmax.z);
+                bwd_stat(q.w, q0.w, s1.w, mn.w, mx.w, nmin.w, nmax.w);
+            }
+            for (int s = beg + 32; s < end; ++s) {             // in-degree > 32 (never for molecules)
+                const float4 q = add4(ldg4(pbase + __ldg(col_src + s) * ldp + soff), ldg4(tbase + (int)__ldg(col_code + s) * C));
+                bwd_stat(q.x, q0.x, s1.x, mn.x, mx.x, nmin.x, nmax.x);
+                bwd_stat(q.y, q0.y, s1.y, mn.y, mx.y, nmin.y, nmax.y);
+                bwd_stat(q.z, q0.z, s1.z, mn.z, mx.z, nmin.z, nmax.z);
+                bwd_stat(q.w, q0.w, s1.w, mn.w, mx.w, nmin.w, nmax.w);
+            }
+            const float inv_cnt = rcp_approx((float)cnt);
             const float4 mean = make_float4(fmaf(s1.x, inv_cnt, q0.x), fmaf(s1.y, inv_cnt, q0.y),
                                             fmaf(s1.z, inv_cnt, q0.z), fmaf(s1.w, inv_cnt, q0.w));
-            float4 cm = zero, cmin = zero, cmax = zero, cs = zero;
-            if (live) {
-                st4(dP + node * ldp + c, make_float4(g_mean.x + g_min.x + g_max.x, g_mean.y + g_min.y + g_max.y,
-                                                     g_mean.z + g_min.z + g_max.z, g_mean.w + g_min.w + g_max.w));
+            if (!SRC_ONLY && live)
+                st4(dP + (size_t)node * ldp + c, make_float4(g_mean.x + g_min.x + g_max.x, g_mean.y + g_min.y + g_max.y,
+                                                             g_mean.z + g_min.z + g_max.z, g_mean.w + g_min.w + g_max.w));
+            float4 cm, cmin, cmax, cs;
 #define COEF(X)                                              \
     cm.X = g_mean.X * inv_cnt;                               \
-    cmin.X = g_min.X * __frcp_rn(nmin.X);                    \
-    cmax.X = g_max.X * __frcp_rn(nmax.X);                    \
-    cs.X = sd.X > 0.f ? g_std.X * inv_cnt * __frcp_rn(sd.X) : 0.f;
-                COEF(x) COEF(y) COEF(z) COEF(w)
+    cmin.X = g_min.X * rcp_approx(nmin.X);                   \
+    cmax.X = g_max.X * rcp_approx(nmax.X);                   \
+    cs.X = sd.X > 0.f ? g_std.X * inv_cnt * rcp_approx(sd.X) : 0.f;
+            COEF(x) COEF(y) COEF(z) COEF(w)
 #undef COEF
-            }
             // ---- pass 2: per-slot gradient (rows are L1/L2 hits from pass 1)
+            float* dq_row = dq != nullptr ? dq + (size_t)beg * C + c : nullptr;
+            so = __shfl_sync(GNN_FULL_MASK, my_src, 0);
+            co = __shfl_sync(GNN_FULL_MASK, my_code, 0);
+            pn = ldg4(pbase + so);
+            tn = ldg4(tbase + co);
             for (int k = 0; k < cnt; ++k) {
-                int so, co;
-                if (k < 32) {
-                    so = __shfl_sync(GNN_FULL_MASK, my_src, k);
-                    co = __shfl_sync(GNN_FULL_MASK, my_code, k);
-                } else {
-                    so = __ldg(col_src + beg + k) * ldp + C;
-                    co = (int)__ldg(col_code + beg + k) * C;
+                const float4 q = add4(pn, tn);
+                const int so_k = so, co_k = co;
+                if (k + 1 < cnt) {
+                    if (k + 1 < 32) {
+                        so = __shfl_sync(GNN_FULL_MASK, my_src, k + 1);
+                        co = __shfl_sync(GNN_FULL_MASK, my_code, k + 1);
+                    } else {
+                        so = __ldg(col_src + beg + k + 1) * ldp + soff;
+                        co = (int)__ldg(col_code + beg + k + 1) * C;
+                    }
+                    pn = ldg4(pbase + so);
+                    tn = ldg4(tbase + co);
                 }
-                if (live) {
-                    const float4 q = add4(ldg4(pbase + so), ldg4(tbase + co));
-                    float4 g;
+                float4 g;
 #define GRAD(X) \
     g.X = cm.X + (q.X == mn.X ? cmin.X : 0.f) + (q.X == mx.X ? cmax.X : 0.f) + cs.X * (q.X - mean.X);
-                    GRAD(x) GRAD(y) GRAD(z) GRAD(w)
+                GRAD(x) GRAD(y) GRAD(z) GRAD(w)
 #undef GRAD
-                    if (dq != nullptr) st4(dq + (int64_t)(beg + k) * C + c, g);
-                    else atomicAdd(reinterpret_cast<float4*>(dP + so + c), g);  // dPsrc[src] += g  (so = src*2C + C)
-                    atomicAdd(reinterpret_cast<float4*>(dtab + co + c), g);     // RED.E.ADD.F32x4
+                if (live) {
+                    if (dq != nullptr) st4(dq_row + k * C, g);
+                    else atomicAdd(reinterpret_cast<float4*>(dP + so_k + c), g);  // dPsrc[src] += g  (so = src*ldp + soff)
+                    atomicAdd(reinterpret_cast<float4*>(dtab + co_k + c), g);     // RED.E.ADD.F32x4
                 }
             }
         }
@@ -397,13 +442,15 @@ extern "C" int64_t gnn_pna_aggregate_bwd_workspace_bytes(int towers, int F) {
     return (int64_t)DTAB_PARTS * GNN_NUM_BOND_CODES * towers * F * (int64_t)sizeof(float);
 }
 
-extern "C" int gnn_pna_aggregate_bwd(const float* gA, const float* P, const float* tab, const float* A,
-                                     const int32_t* rowptr, const int32_t* col_src, const uint8_t* col_code,
-                                     int64_t n, int towers, int F, float* dP, float* dq, float* dtab_accum,
-                                     void* zeroed_workspace, int64_t workspace_bytes, void* stream) {
+template <bool SRC_ONLY>
+static int aggregate_bwd_launch(const float* gA, const float* P, const float* tab, const float* A,
+                                const int32_t* rowptr, const int32_t* col_src, const uint8_t* col_code,
+                                int64_t n, int towers, int F, float* dP, float* dq, float* dtab_accum,
+                                void* zeroed_workspace, int64_t workspace_bytes, void* stream) {
     if (n < 0 || towers < 1 || F < 4 || (F & 3)) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
     if (workspace_bytes < gnn_pna_aggregate_bwd_workspace_bytes(towers, F)) return GNN_ERR_WORKSPACE;
+    if (SRC_ONLY && dq == nullptr && dP == nullptr) return GNN_ERR_BAD_ARG;
     const int C = towers * F;
     if ((int64_t)n * 2 * C >= (1ll << 31)) return GNN_ERR_TOO_LARGE;    // 32-bit row offsets
     cudaStream_t st = gnn_stream(stream);
@@ -411,21 +458,38 @@ extern "C" int gnn_pna_aggregate_bwd(const float* gA, const float* P, const floa
     int64_t cap = (int64_t)gnn_sm_count() * 32;
     if (blocks > cap) blocks = cap;
     float* parts = reinterpret_cast<float*>(zeroed_workspace);
-    if (dq == nullptr) {       // source gradients accumulate atomically into dP[:, C:2C]
-        cudaError_t e = cudaMemset2DAsync(dP + C, 2 * (size_t)C * sizeof(float), 0, (size_t)C * sizeof(float), (size_t)n, st);
+    if (dq == nullptr) {       // source gradients accumulate atomically into the source columns of dP
+        cudaError_t e = SRC_ONLY ? cudaMemsetAsync(dP, 0, (size_t)n * C * sizeof(float), st)
+                                 : cudaMemset2DAsync(dP + C, 2 * (size_t)C * sizeof(float), 0, (size_t)C * sizeof(float),
+                                                     (size_t)n, st);
         if (e != cudaSuccess) return (int)e;
     }
-    pna_aggregate_bwd_kernel<<<(unsigned)blocks, AGG_THREADS, 0, st>>>(gA, P, tab, A, rowptr, col_src, col_code, n, C, F,
-                                                                       dP, dq, parts);
+    pna_aggregate_bwd_kernel<SRC_ONLY><<<(unsigned)blocks, AGG_THREADS, 0, st>>>(gA, P, tab, A, rowptr, col_src, col_code,
+                                                                                 (int)n, C, F, dP, dq, parts);
     const int total = GNN_NUM_BOND_CODES * C;
     dtab_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(parts, total, dtab_accum);
     return gnn_launch_status();
 }
 
+extern "C" int gnn_pna_aggregate_bwd(const float* gA, const float* P, const float* tab, const float* A,
+                                     const int32_t* rowptr, const int32_t* col_src, const uint8_t* col_code,
+                                     int64_t n, int towers, int F, float* dP, float* dq, float* dtab_accum,
+                                     void* zeroed_workspace, int64_t workspace_bytes, void* stream) {
+    return aggregate_bwd_launch<false>(gA, P, tab, A, rowptr, col_src, col_code, n, towers, F, dP, dq, dtab_accum,
+                                       zeroed_workspace, workspace_bytes, stream);
+}
+extern "C" int gnn_pna_aggregate_src_bwd(const float* gA, const float* Psrc, const float* tab, const float* A,
+                                         const int32_t* rowptr, const int32_t* col_src, const uint8_t* col_code,
+                                         int64_t n, int towers, int F, float* dPsrc, float* dq, float* dtab_accum,
+                                         void* zeroed_workspace, int64_t workspace_bytes, void* stream) {
+    return aggregate_bwd_launch<true>(gA, Psrc, tab, A, rowptr, col_src, col_code, n, towers, F, dPsrc, dq,
+                                      dtab_accum, zeroed_workspace, workspace_bytes, stream);
+}
+
 // ------------------------------------------------------------------ gather dq by source node
 __global__ void __launch_bounds__(AGG_THREADS)
 scatter_src_bwd_kernel(const float* __restrict__ dq, const int* __restrict__ srcptr,
-                       const int* __restrict__ src_slot, int64_t n, int C, float* __restrict__ dP) {
+                       const int* __restrict__ src_slot, int64_t n, int C, float* __restrict__ out, int64_t ldo) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (int64_t)blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
     const int64_t nwarps = (int64_t)gridDim.x * AGG_WARPS;
@@ -437,7 +501,7 @@ scatter_src_bwd_kernel(const float* __restrict__ dq, const int* __restrict__ src
                 const int slot = __ldg(src_slot + k);
                 acc = add4(acc, ldg4(dq + (int64_t)slot * C + c));
             }
-            st4(dP + node * (2 * (int64_t)C) + C + c, acc);
+            st4(out + node * ldo + c, acc);
         }
     }
 }
@@ -446,7 +510,16 @@ extern "C" int gnn_scatter_src_bwd(const float* dq, const int32_t* srcptr, const
                                    int C, float* dP, void* stream) {
     if (n < 0 || C < 4 || (C & 3)) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
-    scatter_src_bwd_kernel<<<agg_grid(n), AGG_THREADS, 0, gnn_stream(stream)>>>(dq, srcptr, src_slot, n, C, dP);
+    scatter_src_bwd_kernel<<<agg_grid(n), AGG_THREADS, 0, gnn_stream(stream)>>>(dq, srcptr, src_slot, n, C, dP + C,
+                                                                                 2 * (int64_t)C);
+    return gnn_launch_status();
+}
+// out[j, 0:C] (row stride ldo) = sum over out-edges of j of dq[slot]
+extern "C" int gnn_slot_sum_by_source(const float* dq, const int32_t* srcptr, const int32_t* src_slot, int64_t n,
+                                      int C, float* out, int64_t ldo, void* stream) {
+    if (n < 0 || C < 4 || (C & 3) || (ldo & 3) || ldo < C) return GNN_ERR_BAD_ARG;
+    if (n == 0) return 0;
+    scatter_src_bwd_kernel<<<agg_grid(n), AGG_THREADS, 0, gnn_stream(stream)>>>(dq, srcptr, src_slot, n, C, out, ldo);
     return gnn_launch_status();
 }
 

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libgnnepcsaft_b200.so")
-SOURCES = ["graph_build.cu", "aggregate.cu", "gemm_simt.cu", "gemm_tc.cu", "norm_pool.cu", "embed.cu"]
+SOURCES = ["graph_build.cu", "aggregate.cu", "gemm_simt.cu", "gemm_tc.cu", "norm_pool.cu", "embed.cu", "fold.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-v"]
 

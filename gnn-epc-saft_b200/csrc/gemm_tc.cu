@@ -204,12 +204,18 @@ struct VTransposed {        // element (r, k) = p[k*ld + r]
 // post forward weights.  Output features are tiled FoP at a time (FoP multiple of 16); tile j holds
 // rows [j*3*FoP, (j+1)*3*FoP) = three scaler groups of FoP rows: row r -> (tile, s, oo), o = tile*FoP + oo.
 //   k <  F : s == 0 ? Wpost_t[o, k] : 0          k >= F : Wpost_t[o, F + s*4F + (k-F)]
+// vx != nullptr (folded destination projection, fold.cu): the x columns of ALL three scaler groups come from
+//   Vx[t][s][o][k]  instead ( = [s == 0] Wpost_t[o, k] + (Wmean + Wmin + Wmax)_{t,s} . Wdst_t ).
 struct VPostWeight {
     static constexpr bool kTransposed = false;   // lanes of a producer warp run along K
     const float* w;
     int64_t tower_stride;
     int F, F_out, FoP;
-    __device__ __forceinline__ void set_group(int g) { w += (int64_t)g * tower_stride; }
+    const float* vx;
+    __device__ __forceinline__ void set_group(int g) {
+        w += (int64_t)g * tower_stride;
+        if (vx) vx += (int64_t)g * 3 * F_out * F;
+    }
     __device__ __forceinline__ float4 get4(int64_t r, int64_t k) const {
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         int tile = (int)r / (3 * FoP), rem = (int)r - tile * 3 * FoP;
@@ -217,6 +223,7 @@ struct VPostWeight {
         if (o >= F_out || k >= 5 * (int64_t)F) return z;
         const float* row = w + (int64_t)o * 13 * F;
         if (k < F) {
+            if (vx) return ldg4(vx + ((int64_t)s * F_out + o) * F + k);
             if (s != 0) return z;
             return make_float4(__ldg(row + k), __ldg(row + k + 1), __ldg(row + k + 2), __ldg(row + k + 3));
         }
@@ -245,16 +252,17 @@ struct VPostWeightT {
 
 // projection weights of PNAConv.pre_nns[t][0] (first two thirds): row n = part*C + t*F + f (part 0 = destination,
 // 1 = source), k in [0,F)  ->  Wpre_t[f, part*F + k]
+// (first_part, nparts) = (0, 2): both halves; (1, 1): the source half only (folded destination projection)
 struct VProjWeight {
     static constexpr bool kTransposed = false;
     const float* w;
     int64_t tower_stride;
-    int F, towers;
+    int F, towers, first_part, nparts;
     __device__ __forceinline__ void set_group(int) {}
     __device__ __forceinline__ float4 get4(int64_t r, int64_t k) const {
         const int C = towers * F;
-        if (r >= 2 * C || k >= F) return make_float4(0.f, 0.f, 0.f, 0.f);
-        const int part = (int)r / C, rem = (int)r - part * C, t = rem / F, f = rem - t * F;
+        if (r >= nparts * C || k >= F) return make_float4(0.f, 0.f, 0.f, 0.f);
+        const int p0 = (int)r / C, part = first_part + p0, rem = (int)r - p0 * C, t = rem / F, f = rem - t * F;
         return ldg4(w + (int64_t)t * tower_stride + (int64_t)f * 3 * F + part * F + k);
     }
 };
@@ -284,6 +292,33 @@ struct VDxWeight {
     }
 };
 
+// B operand of the fused dx GEMM with a folded destination projection: row kk in [0,F), k over
+// [dPsrc (C) | dO (T*F_out) | amp dO | att dO]:
+//   k < C : (t,f) -> Wpre_t[f, F + kk]        k >= C : (s,t,o) -> Vx[t][s][o][kk]
+struct VDxWeightFold {
+    static constexpr bool kTransposed = true;
+    const float* wpre;
+    const float* vx;
+    int64_t wpre_tower_stride;
+    int F, F_out, towers;
+    __device__ __forceinline__ void set_group(int) {}
+    __device__ __forceinline__ float elem(int64_t kk, int64_t k) const {
+        const int C = towers * F;
+        if (k < C) {
+            const int t = (int)k / F, f = (int)k - t * F;
+            return __ldg(wpre + (int64_t)t * wpre_tower_stride + (int64_t)f * 3 * F + F + kk);
+        }
+        const int j = (int)k - C, TF = towers * F_out;
+        if (j >= 3 * TF) return 0.f;
+        const int sgrp = j / TF, r = j - sgrp * TF, t = r / F_out, o = r - t * F_out;
+        return __ldg(vx + ((int64_t)(t * 3 + sgrp) * F_out + o) * F + kk);
+    }
+    __device__ __forceinline__ float4 get4(int64_t kk, int64_t k) const {
+        if (kk >= F) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return make_float4(elem(kk, k), elem(kk, k + 1), elem(kk, k + 2), elem(kk, k + 3));
+    }
+};
+
 // ------------------------------------------------------------------ activation operands: segmented rows
 // Every activation operand of the model is a row-major [node][column] matrix whose columns are a
 // concatenation of up to three slices of real tensors, optionally multiplied by a per-node degree scaler:
@@ -297,8 +332,9 @@ struct Seg {
     int start, width;        // columns [start, start + width) of the operand
     int scale;               // -1: none, 0: amplification, 1: attenuation  (scal[2*row + scale])
 };
+constexpr int MAX_SEGS = 4;
 struct SegOperand {
-    Seg seg[3];
+    Seg seg[MAX_SEGS];
     int nseg;
     int64_t rows;            // valid rows (nodes)
     const float* scal;       // [rows, 2]
@@ -311,7 +347,7 @@ struct SegRef {
 __device__ __forceinline__ SegRef seg_resolve(const SegOperand& op, int64_t col, int grp) {
     SegRef r{nullptr, 0, -1};
 #pragma unroll
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < MAX_SEGS; ++s) {
         if (s < op.nseg && col >= op.seg[s].start && col < op.seg[s].start + op.seg[s].width) {
             r.ptr = op.seg[s].base + (int64_t)grp * op.seg[s].group_stride + (col - op.seg[s].start);
             r.ld = op.seg[s].ld;
@@ -469,7 +505,7 @@ struct EProjStore {
     }
     __device__ __forceinline__ void store16(int64_t m, int n, float* v) const {
         const int C = towers * F;
-        if (n < C) {                                       // F % 16 == 0: the 16 columns share one tower
+        if (n < C) {                                       // F % 16 == 0: the 16 columns share one tower  (source-only P: N == C)
             const int t = n / F, f = n - t * F;
             const float* b = bias + (int64_t)t * bias_tower_stride + f;
 #pragma unroll
@@ -478,7 +514,7 @@ struct EProjStore {
                 v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
             }
         }
-        float* dst = P + m * (2 * (int64_t)C) + n;
+        float* dst = P + m * ldp + n;
         st_global_v8(dst, v);
         st_global_v8(dst + 8, v + 8);
     }
@@ -486,6 +522,7 @@ struct EProjStore {
     const float* bias;
     int64_t bias_tower_stride;
     int F, towers;
+    int64_t ldp;
     static constexpr int kCombine3 = 0;
     __device__ __forceinline__ void set_group(int) {}
     __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
@@ -495,7 +532,7 @@ struct EProjStore {
             const float* b = bias + (int64_t)t * bias_tower_stride + f;
             v = make_float4(v.x + __ldg(b), v.y + __ldg(b + 1), v.z + __ldg(b + 2), v.w + __ldg(b + 3));
         }
-        *reinterpret_cast<float4*>(P + m * (2 * (int64_t)C) + n) = v;     // N = 2C, C % 4 == 0
+        *reinterpret_cast<float4*>(P + m * ldp + n) = v;     // N = 2C or C, C % 4 == 0
     }
 };
 // fused projection weight gradient: D[(part,t,f), kk] -> dWpre_t[f, part*F + kk]
@@ -503,13 +540,13 @@ struct EProjWgrad {
     static constexpr int kWide = 0;
     float* dw;
     int64_t tower_stride;
-    int F, towers;
+    int F, towers, first_part, nparts;
     static constexpr int kCombine3 = 0;
     __device__ __forceinline__ void set_group(int) {}
     __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
         const int C = towers * F;
-        if (m >= 2 * C) return;
-        const int part = (int)m / C, rem = (int)m - part * C, t = rem / F, f = rem - t * F;
+        if (m >= nparts * C) return;
+        const int p0 = (int)m / C, part = first_part + p0, rem = (int)m - p0 * C, t = rem / F, f = rem - t * F;
         float* dst = dw + (int64_t)t * tower_stride + (int64_t)f * 3 * F + part * F + n;
         if (n + 3 < N) {
             atomicAdd(reinterpret_cast<float4*>(dst), v);
@@ -1464,10 +1501,10 @@ static SegOperand seg_scaled_grad(const float* dO, const float* scal, int64_t n,
     return op;
 }
 
-extern "C" int gnn_tc_pna_post_fwd(const float* x, const float* A, const float* scal, const float* wpost,
-                                   int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
-                                   int64_t n, int F, int F_out, int towers, int act, float* O, int precision,
-                                   void* pack_ws, int64_t pack_ws_bytes, void* stream) {
+static int post_fwd_impl(const float* x, const float* A, const float* scal, const float* vx, const float* wpost,
+                         int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
+                         int64_t n, int F, int F_out, int towers, int act, float* O, int precision,
+                         void* pack_ws, int64_t pack_ws_bytes, void* stream) {
     if (n < 0 || F < 4 || (F & 3) || F_out < 1 || towers < 1) return GNN_ERR_BAD_ARG;
     REQUIRE_VEC(x, F);
     REQUIRE_VEC(A, 4 * (int64_t)F);
@@ -1475,11 +1512,29 @@ extern "C" int gnn_tc_pna_post_fwd(const float* x, const float* A, const float* 
     if (FoP > 64) FoP = 64;
     const int tiles = (F_out + FoP - 1) / FoP;
     SegOperand aop = seg_cat5(x, A, n, F, towers);
-    VPostWeight bl{wpost, wpost_tower_stride, F, F_out, FoP};
+    VPostWeight bl{wpost, wpost_tower_stride, F, F_out, FoP, vx};
     EPostCombine ep{O, scal, bpost, bpost_tower_stride, F_out, FoP, towers, 0, act,
                     (F_out % 4 == 0) && is_vec(O, 0) && is_vec(bpost, bpost_tower_stride)};
     DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, tiles * 3 * FoP, 3 * FoP, 5 * (int64_t)F,
                                                   5 * (int64_t)F, 1, towers, gnn_stream(stream), pack_ws, pack_ws_bytes)));
+}
+
+extern "C" int gnn_tc_pna_post_fwd(const float* x, const float* A, const float* scal, const float* wpost,
+                                   int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
+                                   int64_t n, int F, int F_out, int towers, int act, float* O, int precision,
+                                   void* pack_ws, int64_t pack_ws_bytes, void* stream) {
+    return post_fwd_impl(x, A, scal, nullptr, wpost, wpost_tower_stride, bpost, bpost_tower_stride, n, F, F_out, towers,
+                         act, O, precision, pack_ws, pack_ws_bytes, stream);
+}
+// folded destination projection: A holds the aggregates of q, Vx [T,3,F_out,F] the folded x columns (gnn_pna_fold_fwd)
+extern "C" int gnn_tc_pna_postf_fwd(const float* x, const float* A, const float* scal, const float* Vx,
+                                    const float* wpost, int64_t wpost_tower_stride, const float* bpost,
+                                    int64_t bpost_tower_stride, int64_t n, int F, int F_out, int towers, int act,
+                                    float* O, int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream) {
+    if (Vx == nullptr) return GNN_ERR_BAD_ARG;
+    REQUIRE_VEC(Vx, F);
+    return post_fwd_impl(x, A, scal, Vx, wpost, wpost_tower_stride, bpost, bpost_tower_stride, n, F, F_out, towers, act,
+                         O, precision, pack_ws, pack_ws_bytes, stream);
 }
 
 extern "C" int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const float* wpost, int64_t wpost_tower_stride,
@@ -1529,11 +1584,29 @@ extern "C" int gnn_tc_pna_proj_fwd(const float* x, const float* wpre, int64_t wp
     REQUIRE_VEC(bpre, bpre_tower_stride);
     const int C = towers * F;
     SegOperand aop = seg_plain(x, F, n, F);
-    VProjWeight bl{wpre, wpre_tower_stride, F, towers};
-    EProjStore ep{P, bpre, bpre_tower_stride, F, towers};
+    VProjWeight bl{wpre, wpre_tower_stride, F, towers, 0, 2};
+    EProjStore ep{P, bpre, bpre_tower_stride, F, towers, 2 * (int64_t)C};
     int BN = pick_bn(2 * C);
     if (BN > 128) BN = 128;
     DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, 2 * C, BN, (int64_t)F, (int64_t)F, 1, 1,
+                                                  gnn_stream(stream), pack_ws, pack_ws_bytes)));
+}
+// source half only, bias included: Psrc[N, C] = x Wsrc_t^T + b_t   (folded destination projection)
+extern "C" int gnn_tc_pna_projsrc_fwd(const float* x, const float* wpre, int64_t wpre_tower_stride, const float* bpre,
+                                      int64_t bpre_tower_stride, int64_t n, int F, int towers, float* Psrc,
+                                      int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream) {
+    if (n < 0 || F < 4 || (F & 3) || towers < 1) return GNN_ERR_BAD_ARG;
+    REQUIRE_VEC(x, F);
+    REQUIRE_VEC(Psrc, (int64_t)towers * F);
+    REQUIRE_VEC(wpre, wpre_tower_stride);
+    REQUIRE_VEC(bpre, bpre_tower_stride);
+    const int C = towers * F;
+    SegOperand aop = seg_plain(x, F, n, F);
+    VProjWeight bl{wpre, wpre_tower_stride, F, towers, 1, 1};
+    EProjStore ep{Psrc, bpre, bpre_tower_stride, F, towers, (int64_t)C};
+    int BN = pick_bn(C);
+    if (BN > 128) BN = 128;
+    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, C, BN, (int64_t)F, (int64_t)F, 1, 1,
                                                   gnn_stream(stream), pack_ws, pack_ws_bytes)));
 }
 
@@ -1560,6 +1633,30 @@ extern "C" int gnn_tc_pna_dx_dgrad(const float* dP, const float* dO, const float
                                                   pack_ws_bytes)));
 }
 
+// folded variant: dx (+)= dPsrc . Wsrc + sum_{s,t} scal_s dO_t . Vx_{t,s}
+extern "C" int gnn_tc_pna_dxf_dgrad(const float* dPsrc, const float* dO, const float* scal, const float* wpre,
+                                    int64_t wpre_tower_stride, const float* Vx, int64_t n, int F, int F_out, int towers,
+                                    int accumulate, float* dx, int precision, void* pack_ws, int64_t pack_ws_bytes,
+                                    void* stream) {
+    if (n < 0 || F < 4 || (F & 3) || F_out < 4 || (F_out & 3) || towers < 1) return GNN_ERR_BAD_ARG;
+    const int C = towers * F, TF = towers * F_out;
+    REQUIRE_VEC(dPsrc, (int64_t)C);
+    REQUIRE_VEC(dO, (int64_t)TF);
+    REQUIRE_VEC(dx, F);
+    SegOperand aop{};
+    aop.seg[0] = Seg{dPsrc, (int64_t)C, 0, 0, C, -1};
+    for (int s = 0; s < 3; ++s) aop.seg[1 + s] = Seg{dO, (int64_t)TF, 0, C + s * TF, TF, s - 1};
+    aop.nseg = 4;
+    aop.rows = n;
+    aop.scal = scal;
+    VDxWeightFold bl{wpre, Vx, wpre_tower_stride, F, F_out, towers};
+    EStore ep{dx, F, 0, nullptr, 0, 0, accumulate, is_vec(dx, F)};
+    const int64_t K = (int64_t)C + 3 * (int64_t)TF;
+    const int BN = pick_bn(F);
+    DISPATCH_MODE(precision, return (launch<MODE, false, true>(aop, bl, ep, n, F, BN, K, K, 1, 1, gnn_stream(stream),
+                                                               pack_ws, pack_ws_bytes)));
+}
+
 // dWpre_t[:, :2F] += dP^T x, dbpre_t += colsum(dPdst_t)   (replaces 4 Linear wgrads + colsum)
 extern "C" int gnn_tc_pna_proj_wgrad(const float* dP, const float* x, int64_t n, int F, int towers, float* dwpre,
                                      int64_t wpre_tower_stride, float* dbpre, int64_t bpre_tower_stride, int precision,
@@ -1572,7 +1669,7 @@ extern "C" int gnn_tc_pna_proj_wgrad(const float* dP, const float* x, int64_t n,
     REQUIRE_VEC(dwpre, wpre_tower_stride);
     SegOperand aop = seg_plain(dP, 2 * (int64_t)C, n, 2 * C);
     SegOperand bop = seg_plain(x, F, n, F);
-    EProjWgrad ep{dwpre, wpre_tower_stride, F, towers};
+    EProjWgrad ep{dwpre, wpre_tower_stride, F, towers, 0, 2};
     int64_t k_chunk;
     int splits;
     DISPATCH_MODE(precision, {
@@ -1583,10 +1680,33 @@ extern "C" int gnn_tc_pna_proj_wgrad(const float* dP, const float* x, int64_t n,
                                    ColSum{dbpre, 0, bpre_tower_stride, dbpre ? C : 0, F}));
     });
 }
+// source half only: dWpre_t[:, F:2F] += dPsrc_t^T x, dbpre_t += colsum(dPsrc_t)
+extern "C" int gnn_tc_pna_projsrc_wgrad(const float* dPsrc, const float* x, int64_t n, int F, int towers, float* dwpre,
+                                        int64_t wpre_tower_stride, float* dbpre, int64_t bpre_tower_stride,
+                                        int precision, void* stream) {
+    if (n < 0 || F < 4 || (F & 3) || towers < 1) return GNN_ERR_BAD_ARG;
+    if (n == 0) return 0;
+    const int C = towers * F;
+    REQUIRE_VEC(dPsrc, (int64_t)C);
+    REQUIRE_VEC(x, F);
+    REQUIRE_VEC(dwpre, wpre_tower_stride);
+    SegOperand aop = seg_plain(dPsrc, (int64_t)C, n, C);
+    SegOperand bop = seg_plain(x, F, n, F);
+    EProjWgrad ep{dwpre, wpre_tower_stride, F, towers, 1, 1};
+    int64_t k_chunk;
+    int splits;
+    DISPATCH_MODE(precision, {
+        const int BN = pick_bn_mn(F, MODE);
+        const int64_t tiles = gnn_ceil_div(C, BM) * gnn_ceil_div(F, BN);
+        splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
+        return (launch<MODE, true>(aop, bop, ep, C, F, BN, n, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
+                                   ColSum{dbpre, 0, bpre_tower_stride, dbpre ? C : 0, F}));
+    });
+}
 
-extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const float* scal, int64_t n,
-                                     int F, int F_out, int towers, float* dwpost, int64_t wpost_tower_stride,
-                                     float* dbpost, int64_t bpost_tower_stride, int precision, void* stream) {
+static int post_wgrad_impl(const float* dO, const float* x, const float* A, const float* scal, int64_t n,
+                           int F, int F_out, int towers, float* dwpost, int64_t wpost_tower_stride,
+                           float* dbpost, int64_t bpost_tower_stride, float* dVx, int precision, void* stream) {
     if (n < 0 || F < 4 || (F & 3) || F_out < 1 || towers < 1) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
     if (F_out % 4 != 0) return GNN_ERR_UNSUPPORTED;
@@ -1613,6 +1733,21 @@ extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const floa
                                      ColSum{dbpost, bpost_tower_stride, 0, dbpost ? F_out : 0, F_out}));
         });
         if (rc) return rc;
+    }
+    // (2') folded destination projection: dVx[t][s][o][:] += sum_i scale_s(i) dO[i,o] x[i,:]  (M = 3 F_out)
+    if (dVx != nullptr) {
+        SegOperand aop = seg_scaled_grad(dO, scal, n, F_out, towers, F_out);
+        SegOperand bop = seg_plain(x, F, n, F);
+        EAtomic ep{dVx, (int64_t)F, 3 * (int64_t)F_out * F, is_vec(dVx, F)};
+        int64_t k_chunk;
+        int splits, rc;
+        DISPATCH_MODE(precision, {
+            const int BN = pick_bn_mn(F, MODE);
+            const int64_t tiles = gnn_ceil_div(F, BN) * gnn_ceil_div(3 * F_out, BM) * towers;
+            splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
+            rc = (launch<MODE, true, true>(aop, bop, ep, 3 * F_out, F, BN, n, k_chunk, splits, towers, st));
+        });
+        return rc;
     }
     // (2) x part: dWpost_t[o, :F] += dO_t^T x   (both towers in one launch: group = tower)
     {
@@ -1641,4 +1776,21 @@ extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const floa
 extern "C" int gnn_tc_set_profile_buffer(void* buf) {
     tc::g_prof = reinterpret_cast<unsigned long long*>(buf);
     return 0;
+}
+
+extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const float* scal, int64_t n,
+                                     int F, int F_out, int towers, float* dwpost, int64_t wpost_tower_stride,
+                                     float* dbpost, int64_t bpost_tower_stride, int precision, void* stream) {
+    return post_wgrad_impl(dO, x, A, scal, n, F, F_out, towers, dwpost, wpost_tower_stride, dbpost, bpost_tower_stride,
+                           nullptr, precision, stream);
+}
+// folded destination projection: the aggregate columns go to dwpost as above, the x columns of the three scaler
+// groups go to dVx [T,3,F_out,F] (+=, caller zeroes) and are mapped back to parameters by gnn_pna_fold_bwd
+extern "C" int gnn_tc_pna_postf_wgrad(const float* dO, const float* x, const float* A, const float* scal, int64_t n,
+                                      int F, int F_out, int towers, float* dwpost, int64_t wpost_tower_stride,
+                                      float* dbpost, int64_t bpost_tower_stride, float* dVx, int precision,
+                                      void* stream) {
+    if (dVx == nullptr) return GNN_ERR_BAD_ARG;
+    return post_wgrad_impl(dO, x, A, scal, n, F, F_out, towers, dwpost, wpost_tower_stride, dbpost, bpost_tower_stride,
+                           dVx, precision, stream);
 }

@@ -27,6 +27,10 @@ TOWERS = 2  # reference models.py:76
 # kernel (no per-slot buffer, 248 us per layer).
 DETERMINISTIC_SCATTER = os.environ.get("GNN_B200_ATOMIC_SCATTER", "0") != "1"
 DEFAULT_MATMUL = "tf32x3"
+# Fold the destination projection of PNAConv into post_nns' weights (csrc/fold.cu): the aggregate kernels gather
+# source projections only.  Needs pre_layers == 1, self-loops (every node has an in-edge) and a tensor-core matmul mode;
+# GNN_B200_FOLD=0 keeps the [Pdst | Psrc] formulation everywhere.
+FOLD_DST = os.environ.get("GNN_B200_FOLD", "1") != "0"
 
 
 @dataclasses.dataclass
@@ -316,6 +320,11 @@ class PNAPCSAFT(nn.Module):
         # reference itself sets at train.py:319), "simt" = plain fp32 FMA kernels
         self.matmul_precision = os.environ.get("GNN_B200_MATMUL", DEFAULT_MATMUL)
 
+    def _fold_dst(self, mm: int) -> bool:
+        pp = self.pna_params
+        return (FOLD_DST and mm >= 0 and pp.pre_layers == 1 and bool(pp.self_loops)
+                and (self.hidden_dim // TOWERS) % 4 == 0)
+
     def _matmul_mode(self) -> int:
         try:
             mm = MATMUL_MODES[self.matmul_precision]
@@ -455,6 +464,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
     f32 = dict(dtype=torch.float32, device=dev)
 
     g = graph if graph is not None else GraphStructure(edge_index, edge_attr, batch, n, num_graphs, pp.self_loops)
+    fold = model._fold_dst(mm)
     row_off = model._consts(dev)
     sv = _Saved() if save else None
 
@@ -478,19 +488,34 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         _c("gnn_bond_table_fwd", bond_tab, conv0.edge_encoder.weight, conv0.edge_encoder.bias,
            conv0.pre_nns[0][0].weight, tower_stride_pre, layer_stride, L, H, T, enc, tab)
 
+    Vx_all = None
+    if fold and L > 0:      # folded x columns of post_nns[t][0] for all layers (one launch)
+        tsp = model._offset_of(conv0.post_nns[1][0].weight) - model._offset_of(conv0.post_nns[0][0].weight)
+        Vx_all = torch.empty(L, T, 3, Fo, F, **f32)
+        _c("gnn_pna_fold_fwd", conv0.post_nns[0][0].weight, tsp, conv0.pre_nns[0][0].weight, tower_stride_pre,
+           layer_stride, L, F, Fo, T, Vx_all)
+
     layers = []
     for l in range(L):
         conv, bn = model.convs[l], model.batch_norms[l].module
         rec = _Saved()
         rec.x_in = x
-        # node projections  P = [Pdst_t0 | Pdst_t1 | Psrc_t0 | Psrc_t1]
-        P = torch.empty(n, 2 * C, **f32)
+        # node projections  P = [Pdst_t0 | Pdst_t1 | Psrc_t0 | Psrc_t1]   (folded: [Psrc_t0 | Psrc_t1] only)
+        P = torch.empty(n, C if fold else 2 * C, **f32)
         mm_proj = 0 if mm == 2 else mm      # bf16 mode: messages stay fp32-accurate (min/max/std are selection-sensitive)
         pre0 = conv.pre_nns[0][0]
         ts_pre = model._offset_of(conv.pre_nns[1][0].weight) - model._offset_of(pre0.weight)
         bs_pre = model._offset_of(conv.pre_nns[1][0].bias) - model._offset_of(pre0.bias)
         rec.pre_strides = (ts_pre, bs_pre)
-        if mm_proj >= 0:
+        tower_stride_post = model._offset_of(conv.post_nns[1][0].weight) - model._offset_of(conv.post_nns[0][0].weight)
+        bias_stride_post = model._offset_of(conv.post_nns[1][0].bias) - model._offset_of(conv.post_nns[0][0].bias)
+        rec.post_strides = (tower_stride_post, bias_stride_post)
+        rec.Vx = None
+        if fold:
+            rec.Vx = Vx_all[l]
+            ws = _pack_ws(dev)
+            _c("gnn_tc_pna_projsrc_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, ws.numel())
+        elif mm_proj >= 0:
             ws = _pack_ws(dev)
             _c("gnn_tc_pna_proj_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, ws.numel())
         else:
@@ -501,7 +526,9 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
                 _lin_fwd(mm_proj, x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
         A = torch.empty(n, T * 4 * F, **f32)
         rec.P = P
-        if pp.pre_layers == 1:
+        if fold:
+            _c("gnn_pna_aggregate_src_fwd", P, tab[l], g.rowptr, g.col_src, g.col_code, n, T, F, A)
+        elif pp.pre_layers == 1:
             _c("gnn_pna_aggregate_fwd", P, tab[l], g.rowptr, g.col_src, g.col_code, n, T, F, A)
         else:
             hs = []
@@ -524,12 +551,15 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         _c("gnn_pna_scalers", g.rowptr, conv.aggr_module.avg_deg_log, n, scal)
         rec.scal = scal
         # post_nns (virtual 13F concat) -> lin
-        tower_stride_post = model._offset_of(conv.post_nns[1][0].weight) - model._offset_of(conv.post_nns[0][0].weight)
-        bias_stride_post = model._offset_of(conv.post_nns[1][0].bias) - model._offset_of(conv.post_nns[0][0].bias)
-        rec.post_strides = (tower_stride_post, bias_stride_post)
         O = torch.empty(n, H, **f32)
-        _post_fwd(mm, x, A, scal, conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias,
-           bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O)
+        if fold:
+            ws = _pack_ws(dev)
+            _c("gnn_tc_pna_postf_fwd", x, A, scal, rec.Vx, conv.post_nns[0][0].weight, tower_stride_post,
+               conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O, mm, ws,
+               ws.numel())
+        else:
+            _post_fwd(mm, x, A, scal, conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias,
+               bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O)
         os_ = [O]
         for k in range(1, pp.post_layers):
             O2 = torch.empty(n, H, **f32)
@@ -582,7 +612,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         sv.g, sv.layers, sv.head, sv.enc, sv.tab = g, layers, head, enc, tab
         sv.x_idx, sv.x_final, sv.n, sv.num_graphs = x_idx, x, n, num_graphs
         sv.layer_stride, sv.tower_stride_pre = layer_stride, tower_stride_pre
-        sv.training, sv.mm = training, mm
+        sv.training, sv.mm, sv.fold = training, mm, fold
     return out, sv
 
 
@@ -631,6 +661,7 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
     _c("gnn_segment_pool_bwd", d, g.node_graph, n, H, 0, dx)
 
     dtab = torch.zeros(L, NUM_BOND_CODES, C, **f32) if L > 0 else None
+    sv.dVx = torch.zeros(L, T, 3, Fo, F, **f32) if (sv.fold and L > 0) else None
     for l in reversed(range(L)):
         conv, bn = model.convs[l], model.batch_norms[l].module
         rec = sv.layers[l]
@@ -656,6 +687,9 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
             dO = dprev
         ts_post, bs_post = rec.post_strides
         w0, b0 = conv.post_nns[0][0].weight, conv.post_nns[0][0].bias
+        if sv.fold:
+            _backward_layer_folded(model, sv, rec, l, dO, dx, dtab, gview)
+            continue
         _post_wgrad(mm, dO, x_in, rec.A, rec.scal, n, F, Fo, T, gview(w0), ts_post, gview(b0), bs_post)
         gA = torch.empty(n, T * 4 * F, **f32)
         fused_dx = mm >= 0        # tensor-core path: every node-feature gradient of the layer in ONE GEMM (below)
@@ -709,12 +743,49 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
     _c("gnn_atom_embed_bwd", sv.x_idx, n, dx, model._consts(dev), sum(ATOM_FEATURE_DIMS), H, gview(atom_tab))
     if L > 0:
         conv0 = model.convs[0]
+        if sv.fold:     # dVx of all layers -> post_nns / pre_nns (destination third) weight gradients, one launch
+            w0, wp0 = conv0.post_nns[0][0].weight, conv0.pre_nns[0][0].weight
+            tsp = model._offset_of(conv0.post_nns[1][0].weight) - model._offset_of(w0)
+            _c("gnn_pna_fold_bwd", sv.dVx, w0, tsp, wp0, sv.tower_stride_pre, sv.layer_stride, L, F, Fo, T, gview(w0),
+               gview(wp0))
         denc = torch.empty(L, NUM_BOND_CODES, F, **f32)
         _c("gnn_bond_table_bwd", dtab, model.edge_embed.bond_embedding_list[0].weight, conv0.edge_encoder.weight,
            conv0.pre_nns[0][0].weight, sv.tower_stride_pre, sv.layer_stride, L, sv.enc, H, T, denc,
            gview(model.edge_embed.bond_embedding_list[0].weight), gview(conv0.edge_encoder.weight),
            gview(conv0.edge_encoder.bias), gview(conv0.pre_nns[0][0].weight))
     del arena
+
+
+def _backward_layer_folded(model, sv, rec, l, dO, dx, dtab, gview):
+    """Message / aggregate / post_nns[.][0] part of one conv layer's backward with the destination projection
+    folded into the post weights (csrc/fold.cu): accumulates into dx and the parameter gradients."""
+    conv = model.convs[l]
+    mm, g, n = sv.mm, sv.g, sv.n
+    dev = dO.device
+    H = model.hidden_dim
+    F, Fo, T = H, H // TOWERS, TOWERS
+    C = T * F
+    f32 = dict(dtype=torch.float32, device=dev)
+    ts_post, bs_post = rec.post_strides
+    ts_pre, bs_pre = rec.pre_strides
+    w0, b0 = conv.post_nns[0][0].weight, conv.post_nns[0][0].bias
+    pre0 = conv.pre_nns[0][0]
+    dVx = sv.dVx[l]
+    _c("gnn_tc_pna_postf_wgrad", dO, rec.x_in, rec.A, rec.scal, n, F, Fo, T, gview(w0), ts_post, gview(b0), bs_post,
+       dVx, mm)
+    gA = torch.empty(n, T * 4 * F, **f32)
+    _post_dgrad(mm, dO, rec.scal, w0, ts_post, n, F, Fo, T, None, gA)
+    dPs = torch.empty(n, C, **f32)
+    dq = torch.empty(max(g.ep, 1), C, **f32) if DETERMINISTIC_SCATTER else None
+    nb = _lib.query("gnn_pna_aggregate_bwd_workspace_bytes", T, F)
+    zws = _WS.get_zeroed("aggbwd", nb, dev)
+    _c("gnn_pna_aggregate_src_bwd", gA, rec.P, sv.tab[l], rec.A, g.rowptr, g.col_src, g.col_code, n, T, F, dPs, dq,
+       dtab[l], zws, zws.numel())
+    if dq is not None:
+        _c("gnn_slot_sum_by_source", dq, g.srcptr, g.src_slot, n, C, dPs, C)
+    _c("gnn_tc_pna_projsrc_wgrad", dPs, rec.x_in, n, F, T, gview(pre0.weight), ts_pre, gview(pre0.bias), bs_pre, mm)
+    ws = _pack_ws(dev)
+    _c("gnn_tc_pna_dxf_dgrad", dPs, dO, rec.scal, pre0.weight, ts_pre, rec.Vx, n, F, Fo, T, 1, dx, mm, ws, ws.numel())
 
 
 class _PNAFunction(torch.autograd.Function):

@@ -141,6 +141,34 @@ int gnn_pna_aggregate_bwd(const float* gA, const float* P, const float* tab, con
 int gnn_scatter_src_bwd(const float* dq, const int32_t* srcptr, const int32_t* src_slot,
                         int64_t num_nodes, int C, float* dP, void* stream);
 
+/* Folded destination projection (pre_layers == 1, every node has an in-edge, i.e. self-loops on):
+ *   mean/min/max(m) = Wdst x + mean/min/max(q), std(m) = std(q), and post_nns[t][0] is linear, so the Wdst x
+ * term moves into the x columns of post_nns:  Vx[t][s] = [s==0] Wpost_t[:, :F] + (Wmean+Wmin+Wmax)_{t,s} . Wdst_t
+ * (s = identity / amplification / attenuation group).  The aggregate kernels then read source projections
+ * only (Psrc [N, C], bias of pre_nns included) and emit the aggregates of q.
+ *   gnn_pna_fold_fwd : Vx [L,T,3,F_out,F] from the parameters of all L conv layers in one launch (wpost/wpre
+ *       point at tower 0 of layer 0; layer l sits l*layer_stride floats further, as in gnn_bond_table_fwd)
+ *   gnn_pna_fold_bwd : dVx -> dwpost (x columns and the mean/min/max columns of every group), dwpre (dst third); +=
+ *   gnn_pna_aggregate_src_fwd/bwd : as gnn_pna_aggregate_fwd/bwd with P = Psrc [N, C] and no destination term;
+ *       bwd writes dq [E',C] per CSR slot, or with dq == NULL accumulates atomically into dPsrc [N, C]
+ *   gnn_slot_sum_by_source : out[j, 0:C] (row stride ldo) = sum over out-edges of j of dq[slot] */
+int gnn_pna_fold_fwd(const float* wpost, int64_t wpost_tower_stride, const float* wpre,
+                     int64_t wpre_tower_stride, int64_t layer_stride, int num_layers, int F, int F_out,
+                     int towers, float* Vx, void* stream);
+int gnn_pna_fold_bwd(const float* dVx, const float* wpost, int64_t wpost_tower_stride, const float* wpre,
+                     int64_t wpre_tower_stride, int64_t layer_stride, int num_layers, int F, int F_out,
+                     int towers, float* dwpost, float* dwpre, void* stream);
+int gnn_pna_aggregate_src_fwd(const float* Psrc, const float* tab, const int32_t* rowptr,
+                              const int32_t* col_src, const uint8_t* col_code, int64_t num_nodes,
+                              int towers, int F, float* A, void* stream);
+int gnn_pna_aggregate_src_bwd(const float* gA, const float* Psrc, const float* tab, const float* A,
+                              const int32_t* rowptr, const int32_t* col_src, const uint8_t* col_code,
+                              int64_t num_nodes, int towers, int F, float* dPsrc, float* dq,
+                              float* dtab_accum, void* zeroed_workspace, int64_t workspace_bytes,
+                              void* stream);
+int gnn_slot_sum_by_source(const float* dq, const int32_t* srcptr, const int32_t* src_slot,
+                           int64_t num_nodes, int C, float* out, int64_t ldo, void* stream);
+
 /* General message path (pre_layers > 1): per-edge hidden h_e = relu(Pdst[dst]+Psrc[src]+tab[code])
  * in CSR slot order, [E', C]. */
 int gnn_edge_hidden_fwd(const float* P, const float* tab, const int32_t* rowptr,
@@ -254,6 +282,32 @@ int gnn_tc_pna_dx_dgrad(const float* dP, const float* dO, const float* wpre, int
 int gnn_tc_pna_proj_wgrad(const float* dP, const float* x, int64_t num_nodes, int F, int towers,
                           float* dwpre, int64_t wpre_tower_stride, float* dbpre, int64_t bpre_tower_stride,
                           int precision, void* stream);
+
+/* Tensor-core stages of the folded destination projection (see gnn_pna_fold_fwd):
+ *   projsrc_fwd  : Psrc[N, C] = x Wsrc_t^T + b_t
+ *   postf_fwd    : O_t = act(sum_s scal_s ([x | A^q_t] . [Vx_{t,s} | Wagg_{t,s}]^T) + bpost_t)
+ *   postf_wgrad  : aggregate columns -> dwpost, dbpost as gnn_tc_pna_post_wgrad; x columns of the three scaler
+ *                  groups -> dVx [T,3,F_out,F] (+=, caller zeroes)
+ *   dxf_dgrad    : dx (+)= dPsrc . Wsrc + sum_{s,t} scal_s dO_t . Vx_{t,s}
+ *   projsrc_wgrad: dWpre_t[:, F:2F] += dPsrc_t^T x ;  dbpre_t += colsum(dPsrc_t) */
+int gnn_tc_pna_projsrc_fwd(const float* x, const float* wpre, int64_t wpre_tower_stride, const float* bpre,
+                           int64_t bpre_tower_stride, int64_t num_nodes, int F, int towers, float* Psrc,
+                           int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream);
+int gnn_tc_pna_postf_fwd(const float* x, const float* A, const float* scal, const float* Vx,
+                         const float* wpost, int64_t wpost_tower_stride, const float* bpost,
+                         int64_t bpost_tower_stride, int64_t num_nodes, int F, int F_out, int towers, int act,
+                         float* O, int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream);
+int gnn_tc_pna_postf_wgrad(const float* dO, const float* x, const float* A, const float* scal,
+                           int64_t num_nodes, int F, int F_out, int towers, float* dwpost,
+                           int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride, float* dVx,
+                           int precision, void* stream);
+int gnn_tc_pna_dxf_dgrad(const float* dPsrc, const float* dO, const float* scal, const float* wpre,
+                         int64_t wpre_tower_stride, const float* Vx, int64_t num_nodes, int F, int F_out,
+                         int towers, int accumulate, float* dx, int precision, void* pack_ws,
+                         int64_t pack_ws_bytes, void* stream);
+int gnn_tc_pna_projsrc_wgrad(const float* dPsrc, const float* x, int64_t num_nodes, int F, int towers,
+                             float* dwpre, int64_t wpre_tower_stride, float* dbpre, int64_t bpre_tower_stride,
+                             int precision, void* stream);
 
 /* ---------------------------------------------------------------- BatchNorm / ReLU / skip
  * Replaces PyG BatchNorm / torch BatchNorm1d + F.relu + skip (models.py:128-131, head BN).

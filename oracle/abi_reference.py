@@ -251,6 +251,73 @@ def gnn_scatter_src_bwd(dq, srcptr, src_slot, n, c, dP, stream=None):
         dP[j, c:2 * c] = dq[src_slot[b:e].long()].sum(0) if e > b else 0
 
 
+# ---- folded destination projection (gnn_pna_fold_fwd and friends)
+def _wsum(wp, f, s):
+    """(Wmean + Wmin + Wmax) of scaler group s: [F_out, F]."""
+    base = f + s * 4 * f
+    return wp[:, base:base + f] + wp[:, base + f:base + 2 * f] + wp[:, base + 2 * f:base + 3 * f]
+
+
+def gnn_pna_fold_fwd(wpost, wpost_ts, wpre, wpre_ts, layer_stride, num_layers, f, f_out, towers, Vx, stream=None):
+    v = Vx.view(num_layers, towers, 3, f_out, f)
+    for l in range(num_layers):
+        for t in range(towers):
+            wp = _mat(wpost, f_out, 13 * f, 13 * f, l * layer_stride + t * wpost_ts)
+            wd = _mat(wpre, f, 3 * f, 3 * f, l * layer_stride + t * wpre_ts)[:, :f]
+            for s in range(3):
+                v[l, t, s] = _wsum(wp, f, s) @ wd + (wp[:, :f] if s == 0 else 0)
+
+
+def gnn_pna_fold_bwd(dVx, wpost, wpost_ts, wpre, wpre_ts, layer_stride, num_layers, f, f_out, towers, dwpost, dwpre,
+                     stream=None):
+    dv = dVx.view(num_layers, towers, 3, f_out, f)
+    for l in range(num_layers):
+        for t in range(towers):
+            wp = _mat(wpost, f_out, 13 * f, 13 * f, l * layer_stride + t * wpost_ts)
+            wd = _mat(wpre, f, 3 * f, 3 * f, l * layer_stride + t * wpre_ts)[:, :f]
+            dwp = _mat(dwpost, f_out, 13 * f, 13 * f, l * layer_stride + t * wpost_ts)
+            dwd = _mat(dwpre, f, 3 * f, 3 * f, l * layer_stride + t * wpre_ts)
+            dwp[:, :f] += dv[l, t, 0]
+            for s in range(3):
+                g = dv[l, t, s] @ wd.t()
+                base = f + s * 4 * f
+                for a in range(3):
+                    dwp[:, base + a * f:base + (a + 1) * f] += g
+                dwd[:, :f] += _wsum(wp, f, s).t() @ dv[l, t, s]
+
+
+def gnn_pna_aggregate_src_fwd(Psrc, tab, rowptr, col_src, col_code, n, towers, f, A, stream=None):
+    for i, (b, e) in enumerate(_segments(rowptr, n)):
+        if e == b:
+            A[i] = 0
+            continue
+        q = Psrc[col_src[b:e].long()] + tab[col_code[b:e].long()]
+        _store_A(A, i, towers, f, *_aggregate(q, torch.zeros_like(q[0])))
+
+
+def gnn_pna_aggregate_src_bwd(gA, Psrc, tab, A, rowptr, col_src, col_code, n, towers, f, dPsrc, dq, dtab_accum,
+                              workspace=None, workspace_bytes=0, stream=None):
+    if dq is None:
+        dPsrc[:n] = 0
+    for i, (b, e) in enumerate(_segments(rowptr, n)):
+        if e == b:
+            continue
+        q = Psrc[col_src[b:e].long()] + tab[col_code[b:e].long()]
+        sd = A[i].view(towers, 4, f)[:, 3].reshape(-1)
+        d, _ = _agg_grad(q, gA[i], sd, towers, f)
+        if dq is None:
+            dPsrc.index_add_(0, col_src[b:e].long(), d)
+        else:
+            dq[b:e] = d
+        dtab_accum.index_add_(0, col_code[b:e].long(), d)
+
+
+def gnn_slot_sum_by_source(dq, srcptr, src_slot, n, c, out, ldo, stream=None):
+    o = _mat(out, n, c, ldo)
+    for j, (b, e) in enumerate(_segments(srcptr, n)):
+        o[j] = dq[src_slot[b:e].long()].sum(0) if e > b else 0
+
+
 def gnn_edge_hidden_fwd(P, tab, rowptr, col_src, col_code, n, c, relu, hidden_out, stream=None):
     for i, (b, e) in enumerate(_segments(rowptr, n)):
         if e > b:
@@ -406,6 +473,64 @@ def gnn_tc_pna_proj_wgrad(dP, x, n, f, towers, dwpre, wts, dbpre, bts, precision
 
 def gnn_tc_pna_post_wgrad(dO, x, A, scal, n, f, f_out, towers, dwpost, wts, dbpost, bts, precision, stream=None):
     gnn_pna_post_wgrad(dO, x, A, scal, n, f, f_out, towers, dwpost, wts, dbpost, bts)
+
+
+def gnn_tc_pna_projsrc_fwd(x, wpre, wts, bpre, bts, n, f, towers, Psrc, precision, pack_ws=None, pack_ws_bytes=0,
+                           stream=None):
+    for t in range(towers):
+        w = _mat(wpre, f, 3 * f, 3 * f, t * wts)
+        Psrc[:n, t * f:(t + 1) * f] = x[:n] @ w[:, f:2 * f].t() + _flat(bpre, f, t * bts)
+
+
+def _postf_cat(x, A, scal, n, f, towers, t):
+    """[x | amp x | att x | A | amp A | att A] and the matching folded weight [F_out, 15F] builder."""
+    a = A[:n].view(n, towers, 4 * f)[:, t]
+    amp, att = scal[:n, 0:1], scal[:n, 1:2]
+    return torch.cat([x[:n, :f], x[:n, :f] * amp, x[:n, :f] * att, a, a * amp, a * att], dim=1)
+
+
+def gnn_tc_pna_postf_fwd(x, A, scal, Vx, wpost, wts, bpost, bts, n, f, f_out, towers, act, O, precision,
+                         pack_ws=None, pack_ws_bytes=0, stream=None):
+    v = Vx.view(towers, 3, f_out, f)
+    for t in range(towers):
+        wp = _mat(wpost, f_out, 13 * f, 13 * f, t * wts)
+        w = torch.cat([v[t, 0], v[t, 1], v[t, 2], wp[:, f:]], dim=1)
+        o = _postf_cat(x, A, scal, n, f, towers, t) @ w.t() + _flat(bpost, f_out, t * bts)
+        O[:n, t * f_out:(t + 1) * f_out] = o.clamp(min=0) if act else o
+
+
+def gnn_tc_pna_postf_wgrad(dO, x, A, scal, n, f, f_out, towers, dwpost, wts, dbpost, bts, dVx, precision,
+                           stream=None):
+    dv = dVx.view(towers, 3, f_out, f)
+    for t in range(towers):
+        d = dO[:n, t * f_out:(t + 1) * f_out]
+        g = d.t() @ _postf_cat(x, A, scal, n, f, towers, t)          # [F_out, 15F]
+        for s in range(3):
+            dv[t, s] += g[:, s * f:(s + 1) * f]
+        _mat(dwpost, f_out, 13 * f, 13 * f, t * wts)[:, f:] += g[:, 3 * f:]
+        _flat(dbpost, f_out, t * bts).add_(d.sum(0))
+
+
+def gnn_tc_pna_dxf_dgrad(dPsrc, dO, scal, wpre, wpre_ts, Vx, n, f, f_out, towers, accumulate, dx, precision,
+                         pack_ws=None, pack_ws_bytes=0, stream=None):
+    v = Vx.view(towers, 3, f_out, f)
+    acc = dx[:n].clone() if accumulate else torch.zeros_like(dx[:n])
+    sc = [torch.ones_like(scal[:n, 0:1]), scal[:n, 0:1], scal[:n, 1:2]]
+    for t in range(towers):
+        w = _mat(wpre, f, 3 * f, 3 * f, t * wpre_ts)
+        acc += dPsrc[:n, t * f:(t + 1) * f] @ w[:, f:2 * f]
+        d = dO[:n, t * f_out:(t + 1) * f_out]
+        for s in range(3):
+            acc += (d * sc[s]) @ v[t, s]
+    dx[:n] = acc
+
+
+def gnn_tc_pna_projsrc_wgrad(dPsrc, x, n, f, towers, dwpre, wts, dbpre, bts, precision, stream=None):
+    for t in range(towers):
+        dw = _mat(dwpre, f, 3 * f, 3 * f, t * wts)
+        dw[:, f:2 * f] += dPsrc[:n, t * f:(t + 1) * f].t() @ x[:n]
+        if dbpre is not None:
+            _flat(dbpre, f, t * bts).add_(dPsrc[:n, t * f:(t + 1) * f].sum(0))
 
 
 # ------------------------------------------------------------------ BatchNorm / pool / loss / optimiser
