@@ -273,7 +273,8 @@ def main():
     tot_ms, cnt = agg.get(agg_fwd, (0.0, 0))
     agg_ms = tot_ms / max(cnt, 1)
     achieved = alg_bytes / (agg_ms * 1e-3) / 1e9 if agg_ms > 0 else 0.0
-    roofline = {"kernel": "pna_aggregate_fwd_kernel<1, %s>" % ("true" if folded else "false"), "abi_call": agg_fwd,
+    roofline = {"kernel": "pna_aggregate_fwd_pipe_kernel<1, %s, 3, 3>" % ("true" if folded else "false"),
+                "abi_call": agg_fwd,
                 "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": agg_ms, "launches_timed": cnt}

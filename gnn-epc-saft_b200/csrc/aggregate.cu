@@ -11,6 +11,7 @@
 #include "common.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 constexpr int AGG_WARPS = 8;
 constexpr int AGG_THREADS = AGG_WARPS * 32;
@@ -219,6 +220,129 @@ pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ 
     }
 }
 
+// ---- persistent, software-pipelined variant of the forward kernel.
+// ncu on the kernel above: DRAM 36 % busy, issue slots 41 % busy, 12.5 of 17.8 resident warps per issue waiting on a
+// long scoreboard - the dependent chain rowptr -> col_src/col_code -> gathered rows -> stores costs four exposed
+// memory latencies per node.  Here a warp owns nodes warp, warp + W, ... of a persistent grid and
+//   * requests the rowptr pair of node i+2 and the column indices of node i+1 before it touches node i,
+//   * issues the gathers of the first PF in-edges of node i together (one exposed latency per node),
+// so that only the gather latency itself is left on the critical path.
+template <int NCHUNK, bool SRC_ONLY, int PF, int MINB>
+__global__ void __launch_bounds__(AGG_THREADS, MINB)
+pna_aggregate_fwd_pipe_kernel(const float* __restrict__ P, const float* __restrict__ tab,
+                              const int* __restrict__ rowptr, const int* __restrict__ col_src,
+                              const uint8_t* __restrict__ col_code, int n, int C, int F, float* __restrict__ A) {
+    const int lane = threadIdx.x & 31;
+    const int warp0 = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
+    const int nwarps = gridDim.x * AGG_WARPS;
+    const int ldp = SRC_ONLY ? C : 2 * C, lda = 4 * C, soff = SRC_ONLY ? 0 : C;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cj[NCHUNK], aoff[NCHUNK];
+    bool live[NCHUNK];
+#pragma unroll
+    for (int j = 0; j < NCHUNK; ++j) {
+        cj[j] = j * 128 + lane * 4;
+        live[j] = cj[j] < C;
+        if (!live[j]) cj[j] = 0;                          // dead lanes read column 0 (valid memory), never store
+        const int t = cj[j] / F;
+        aoff[j] = t * 4 * F + (cj[j] - t * F);            // A[node][t][agg][f]
+    }
+    int node = warp0;
+    if (node >= n) return;
+    // prologue: indices of the first node, rowptr pair of the second
+    int beg, cnt, raw_src = 0, raw_code = 0;
+    {
+        const int rp = __ldg(rowptr + node + (lane & 1));
+        beg = __shfl_sync(GNN_FULL_MASK, rp, 0);
+        cnt = __reduce_max_sync(GNN_FULL_MASK, __shfl_sync(GNN_FULL_MASK, rp, 1) - beg);
+        if (lane < cnt) {
+            raw_src = __ldg(col_src + beg + lane);
+            raw_code = (int)__ldg(col_code + beg + lane);
+        }
+    }
+    int node_n = node + nwarps;
+    int rp_n = node_n < n ? __ldg(rowptr + node_n + (lane & 1)) : 0;
+    while (true) {
+        // ---- (1) next node: column indices now (its rowptr pair was requested one iteration ago), rowptr of the one after
+        int beg_n = 0, cnt_n = 0, raw_src_n = 0, raw_code_n = 0;
+        if (node_n < n) {
+            beg_n = __shfl_sync(GNN_FULL_MASK, rp_n, 0);
+            cnt_n = __reduce_max_sync(GNN_FULL_MASK, __shfl_sync(GNN_FULL_MASK, rp_n, 1) - beg_n);
+            if (lane < cnt_n) {
+                raw_src_n = __ldg(col_src + beg_n + lane);
+                raw_code_n = (int)__ldg(col_code + beg_n + lane);
+            }
+        }
+        const int node_nn = node_n + nwarps;
+        const int rp_nn = node_nn < n ? __ldg(rowptr + node_nn + (lane & 1)) : 0;
+        // ---- (2) this node
+        const int my_src = raw_src * ldp + soff, my_code = raw_code * C;
+        float* const arow = A + (size_t)node * lda;
+        const int m = min(cnt, 32);
+#pragma unroll
+        for (int j = 0; j < NCHUNK; ++j) {
+            float* const out = arow + aoff[j];
+            if (cnt == 0) {
+                if (live[j]) {
+                    st4_stream(out, zero);
+                    st4_stream(out + F, zero);
+                    st4_stream(out + 2 * F, zero);
+                    st4_stream(out + 3 * F, zero);
+                }
+                continue;
+            }
+            const float* const pbase = P + cj[j];
+            const float* const tbase = tab + cj[j];
+            float4 pd = zero;
+            if (!SRC_ONLY) pd = ldg4(P + (size_t)node * ldp + cj[j]);
+            float4 pr[PF];
+            int co[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {                 // all gathers of the first PF edges in flight together
+                const int so = __shfl_sync(GNN_FULL_MASK, my_src, k);
+                co[k] = __shfl_sync(GNN_FULL_MASK, my_code, k);
+                if (k < m) pr[k] = ldg4(pbase + so);
+            }
+            const float4 q0 = add4(pr[0], ldg4(tbase + co[0]));     // bond-table rows are L1 hits: fetched at use
+            float4 s1 = zero, s2 = zero, mn = q0, mx = q0;
+#define ACC(Q)                                                                                                     \
+    {                                                                                                              \
+        const float4 q = (Q);                                                                                      \
+        const float dx = q.x - q0.x, dy = q.y - q0.y, dz = q.z - q0.z, dw = q.w - q0.w;                            \
+        s1 = make_float4(s1.x + dx, s1.y + dy, s1.z + dz, s1.w + dw);                                              \
+        s2 = make_float4(fmaf(dx, dx, s2.x), fmaf(dy, dy, s2.y), fmaf(dz, dz, s2.z), fmaf(dw, dw, s2.w));          \
+        mn = make_float4(fminf(mn.x, q.x), fminf(mn.y, q.y), fminf(mn.z, q.z), fminf(mn.w, q.w));                  \
+        mx = make_float4(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z), fmaxf(mx.w, q.w));                  \
+    }
+#pragma unroll
+            for (int k = 1; k < PF; ++k)
+                if (k < m) ACC(add4(pr[k], ldg4(tbase + co[k])))
+            for (int k = PF; k < m; ++k) {                 // in-degree > PF: serial
+                const int so = __shfl_sync(GNN_FULL_MASK, my_src, k), ck = __shfl_sync(GNN_FULL_MASK, my_code, k);
+                ACC(add4(ldg4(pbase + so), ldg4(tbase + ck)))
+            }
+            for (int s = beg + 32; s < beg + cnt; ++s)     // in-degree > 32 (never for molecules)
+                ACC(add4(ldg4(pbase + __ldg(col_src + s) * ldp + soff), ldg4(tbase + (int)__ldg(col_code + s) * C)))
+#undef ACC
+            if (live[j]) {
+                const float inv = __frcp_rn((float)cnt);
+                const float4 m1 = make_float4(s1.x * inv, s1.y * inv, s1.z * inv, s1.w * inv);
+                st4_stream(out, make_float4(q0.x + m1.x + pd.x, q0.y + m1.y + pd.y, q0.z + m1.z + pd.z, q0.w + m1.w + pd.w));
+                st4_stream(out + F, add4(mn, pd));
+                st4_stream(out + 2 * F, add4(mx, pd));
+                st4_stream(out + 3 * F, make_float4(pna_std_fast(fmaf(-m1.x, m1.x, s2.x * inv)),
+                                                    pna_std_fast(fmaf(-m1.y, m1.y, s2.y * inv)),
+                                                    pna_std_fast(fmaf(-m1.z, m1.z, s2.z * inv)),
+                                                    pna_std_fast(fmaf(-m1.w, m1.w, s2.w * inv))));
+            }
+        }
+        // ---- (3) rotate
+        if (node_n >= n) break;
+        node = node_n; beg = beg_n; cnt = cnt_n; raw_src = raw_src_n; raw_code = raw_code_n;
+        node_n = node_nn; rp_n = rp_nn;
+    }
+}
+
 static int agg_grid(int64_t n) {
     int64_t blocks = gnn_ceil_div(n, AGG_WARPS);
     int64_t cap = (int64_t)gnn_sm_count() * 64;   // grid-stride beyond 64 CTAs/SM worth of work
@@ -239,6 +363,23 @@ static int aggregate_fwd_launch(const float* P, const float* tab, const int32_t*
     int64_t cap = (int64_t)gnn_sm_count() * 48;
     if (blocks > cap) blocks = cap;
     const int chunks = (C + 127) / 128;
+    // default: the persistent software-pipelined kernel (3 resident CTAs per SM, 80 registers); GNN_B200_AGG_FWD=0
+    // selects the one-node-per-warp-iteration kernel above (kept for A/B measurements, tools/agg_probe.py)
+    static const int variant = getenv("GNN_B200_AGG_FWD") ? atoi(getenv("GNN_B200_AGG_FWD")) : 1;
+    if (variant >= 1) {
+        int64_t pb = (int64_t)gnn_sm_count() * 3;
+        if (pb > gnn_ceil_div(n, AGG_WARPS)) pb = gnn_ceil_div(n, AGG_WARPS);
+#define LAUNCH_PIPE(CH) pna_aggregate_fwd_pipe_kernel<CH, SRC_ONLY, 3, 3><<<(unsigned)pb, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, (int)n, C, F, A)
+        switch (chunks) {
+            case 1: LAUNCH_PIPE(1); break;
+            case 2: LAUNCH_PIPE(2); break;
+            case 3: case 4: LAUNCH_PIPE(4); break;
+            case 5: case 6: case 7: case 8: LAUNCH_PIPE(8); break;
+            default: return GNN_ERR_UNSUPPORTED;
+        }
+#undef LAUNCH_PIPE
+        return gnn_launch_status();
+    }
 #define LAUNCH_FWD(CH) pna_aggregate_fwd_kernel<CH, SRC_ONLY><<<(unsigned)blocks, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, (int)n, C, F, A)
     switch (chunks) {
         case 1: LAUNCH_FWD(1); break;
@@ -288,6 +429,10 @@ __device__ __forceinline__ void bwd_stat(float q, float q0, float& s1, float& mn
     mx = fmaxf(mx, q);
 }
 
+// Measured (ncu, 4096-graph batch): 720 warp instructions per node, issue slots 56 % busy, DRAM 50 %; a persistent
+// software-pipelined variant like pna_aggregate_fwd_pipe_kernel (indices prefetched across nodes, message rows kept
+// in registers for pass 2) ran at the same 140-145 us with or without the stores and reductions, so it was dropped:
+// this kernel is bound by its instruction stream (per-slot addressing, tie counting), not by memory latency.
 template <bool SRC_ONLY>
 __global__ void __launch_bounds__(AGG_THREADS, 3)
 pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__ P,

@@ -1,0 +1,184 @@
+// Microbenchmark (debug aid, run on the GPU box): issue rate of tcgen05.mma for the shapes the GEMM kernels use.
+// One CTA per SM, one thread issues REPS x (ksteps MMAs) back to back from shared-memory tiles, then commits and
+// waits; prints cycles per MMA for kind::tf32 / kind::f16, N in {64, 96, 128, 192, 256}, K-major SWIZZLE_128B.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_rate tools/mma_rate.cu && tools/mma_rate
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ inline uint32_t instr_desc(int bf16, int n) {
+    uint32_t fmt = bf16 ? 1u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <int BF16>
+__global__ void __launch_bounds__(128, 1) rate_kernel(int N, int reps, int distinct, int use_other_acc, long long* out) {
+    extern __shared__ uint8_t raw[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    // A planes: 2 x [128 x 128 B]; B planes: 2 x [256 x 128 B]  -> 96 KB, zero-filled
+    for (int i = tid; i < (2 * 16384 + 2 * 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + 16384, b_hi = a_hi + 32768, b_lo = b_hi + 32768;
+        const uint32_t idesc = instr_desc(BF16, N);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                   // 4 k-steps of 32 bytes = one 128-byte k-block
+                const uint32_t koff = j * 32;
+                for (int v = 0; v < distinct; ++v) {        // distinct = 3: (lo,hi), (hi,lo), (hi,hi) as TF32x3 does
+                    const uint64_t da = desc_sw128((v == 0 ? a_lo : a_hi) + koff);
+                    const uint64_t db = desc_sw128((v == 1 ? b_lo : b_hi) + koff);
+                    const uint32_t d = tmem + (use_other_acc ? (uint32_t)(v & 1) * 256u : 0u);
+                    if (BF16)
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(da), "l"(db), "r"(idesc), "r"(1u) : "memory");
+                }
+            }
+        }
+        const long long t1 = clock64();
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        const long long t2 = clock64();
+        if (blockIdx.x == 0) {
+            out[0] = t1 - t0;
+            out[1] = t2 - t0;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+// TF32x3 issue pattern of gemm_tc.cu with everything hoisted: 16 descriptors precomputed, 12 MMAs per k-block fully
+// unrolled, optionally one tcgen05.commit per k-block (as the ring release does)
+template <int BF16>
+__global__ void __launch_bounds__(128, 1) rate3_kernel(int N, int reps, int commit_each, long long* out) {
+    extern __shared__ uint8_t raw[];
+    __shared__ __align__(8) uint64_t bar, bar2;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < (2 * 16384 + 2 * 32768) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar2)), "r"(1 << 20));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t a_hi = smem_u32(smem), a_lo = a_hi + 16384, b_hi = a_hi + 32768, b_lo = b_hi + 32768;
+        const uint32_t idesc = instr_desc(BF16, N);
+        uint64_t dah[4], dal[4], dbh[4], dbl[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dah[j] = desc_sw128(a_hi + j * 32); dal[j] = desc_sw128(a_lo + j * 32);
+            dbh[j] = desc_sw128(b_hi + j * 32); dbl[j] = desc_sw128(b_lo + j * 32);
+        }
+#define MMA(DA, DB)                                                                                                      \
+    if (BF16) asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(tmem), "l"(DA), "l"(DB), "r"(idesc) : "memory"); \
+    else asm volatile("tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, 1;" ::"r"(tmem), "l"(DA), "l"(DB), "r"(idesc) : "memory");
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                MMA(dal[j], dbh[j]) MMA(dah[j], dbl[j]) MMA(dah[j], dbh[j])
+            }
+            if (commit_each)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+        }
+        const long long t1 = clock64();
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        const long long t2 = clock64();
+        if (blockIdx.x == 0) {
+            out[0] = t1 - t0;
+            out[1] = t2 - t0;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+int main() {
+    {
+        long long* out;
+        cudaMallocManaged(&out, 2 * sizeof(long long));
+        const int smem = 98304 + 1024;
+        cudaFuncSetAttribute(rate3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(rate3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        for (int bf16 = 0; bf16 < 2; ++bf16)
+            for (int commit = 0; commit < 2; ++commit)
+                for (int n : {32, 64, 96, 128, 192, 256}) {
+                    for (int it = 0; it < 2; ++it) {
+                        if (bf16) rate3_kernel<1><<<148, 128, smem>>>(n, 256, commit, out);
+                        else rate3_kernel<0><<<148, 128, smem>>>(n, 256, commit, out);
+                        cudaError_t e = cudaDeviceSynchronize();
+                        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                    }
+                    printf("hoisted %s N=%3d commit_per_kblock=%d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %.0f)\n",
+                           bf16 ? "bf16" : "tf32", n, commit, out[0] / (256.0 * 12), out[1] / (256.0 * 12), 128.0 * n / 256.0);
+                }
+    }
+    return 0;
+}
+int main_old() {
+    long long* out;
+    cudaMallocManaged(&out, 2 * sizeof(long long));
+    const int smem = 98304 + 1024;
+    cudaFuncSetAttribute(rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int reps = 256;
+    const int ns[] = {64, 96, 128, 192, 256};
+    for (int grid : {1, 148}) {
+        for (int bf16 = 0; bf16 < 2; ++bf16)
+            for (int distinct : {1, 3})
+                for (int other = 0; other < 2; ++other)
+                    for (int n : ns) {
+                        if (other && n > 256) continue;
+                        for (int it = 0; it < 2; ++it) {
+                            if (bf16) rate_kernel<1><<<grid, 128, smem>>>(n, reps, distinct, other, out);
+                            else rate_kernel<0><<<grid, 128, smem>>>(n, reps, distinct, other, out);
+                            cudaError_t e = cudaDeviceSynchronize();
+                            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+                        }
+                        const double mmas = (double)reps * 4 * distinct;
+                        printf("grid %3d %s N=%3d operands=%d alt_acc=%d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %.0f)\n",
+                               grid, bf16 ? "bf16" : "tf32", n, distinct, other, out[0] / mmas, out[1] / mmas, 128.0 * n / 256.0);
+                    }
+    }
+    return 0;
+}
