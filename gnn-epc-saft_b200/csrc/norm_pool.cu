@@ -8,11 +8,13 @@
 #include <math.h>
 
 constexpr int RED_TX = 32, RED_TY = 8;          // column-reduction block: 32 columns x 8 row phases
-constexpr int RED_ROWS_PER_CTA = 256;
+constexpr int RED_ROWS_PER_CTA = 128;
 
 static int red_ctas(int64_t rows) {
     int64_t c = gnn_ceil_div(rows, RED_ROWS_PER_CTA);
-    int64_t cap = (int64_t)gnn_sm_count() * 8;
+    // two CTAs per SM: the finalize kernels read every partial, so few, fat parts (the finalize pass with 400-800
+    // parts cost as much as the reduction itself: 14 us of a 28 us BatchNorm statistics call)
+    int64_t cap = (int64_t)gnn_sm_count() * 2;
     if (c > cap) c = cap;
     if (c < 1) c = 1;
     return (int)c;
@@ -78,13 +80,14 @@ bn_partial_kernel(const float* __restrict__ Y, const float* __restrict__ dOut, c
 }
 
 // vectorised variant for C in {4, 8, ..., 1024} with 256 % (C/4) == 0: 16-byte loads, TX = C/4 threads per row
+constexpr int BN4_THREADS = 512;
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(BN4_THREADS)
 bn_partial4_kernel(const float* __restrict__ Y, const float* __restrict__ dOut, const float* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int C, int relu,
                    double* __restrict__ partial) {
-    extern __shared__ double sred[];                 // [256][8]
-    const int TX = C >> 2, TY = 256 / TX;
+    extern __shared__ double sred[];                 // [BN4_THREADS][8]
+    const int TX = C >> 2, TY = BN4_THREADS / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c = tx * 4;
     const int64_t chunk = ceil_div_dev(rows, gridDim.x);
@@ -97,33 +100,50 @@ bn_partial4_kernel(const float* __restrict__ Y, const float* __restrict__ dOut, 
         ga = ldg4(gamma + c);
         be = ldg4(beta + c);
     }
-    for (int64_t r = r0 + ty; r < r1; r += TY) {
-        const float4 y = ldg4(Y + r * C + c);
-        if (MODE == 0) {
-            a[0] += y.x; a[1] += y.y; a[2] += y.z; a[3] += y.w;
-            a[4] += (double)y.x * y.x; a[5] += (double)y.y * y.y; a[6] += (double)y.z * y.z; a[7] += (double)y.w * y.w;
-        } else {
-            float4 dz = ldg4(dOut + r * C + c);
-            const float4 yh = make_float4((y.x - mu.x) * rs.x, (y.y - mu.y) * rs.y, (y.z - mu.z) * rs.z, (y.w - mu.w) * rs.w);
-            if (relu) {
-                if (!(fmaf(ga.x, yh.x, be.x) > 0.f)) dz.x = 0.f;
-                if (!(fmaf(ga.y, yh.y, be.y) > 0.f)) dz.y = 0.f;
-                if (!(fmaf(ga.z, yh.z, be.z) > 0.f)) dz.z = 0.f;
-                if (!(fmaf(ga.w, yh.w, be.w) > 0.f)) dz.w = 0.f;
-            }
-            a[0] += dz.x; a[1] += dz.y; a[2] += dz.z; a[3] += dz.w;
-            a[4] += (double)dz.x * yh.x; a[5] += (double)dz.y * yh.y; a[6] += (double)dz.z * yh.z; a[7] += (double)dz.w * yh.w;
+    // four rows per trip: the (up to eight) 16-byte loads are independent and issued together, their contributions are
+    // summed in fp32 (4 terms) and only then promoted to the fp64 accumulators
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0 + ty; r < r1; r += 4 * TY) {
+        float4 y[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t ru = r + (int64_t)u * TY;
+            const bool ok = ru < r1;
+            y[u] = ok ? ldg4(Y + ru * C + c) : (MODE == 0 ? z4 : mu);        // padding rows contribute zero
+            if (MODE == 1) d[u] = ok ? ldg4(dOut + ru * C + c) : z4;
         }
+        float4 p = z4, q = z4;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (MODE == 0) {
+                p = make_float4(p.x + y[u].x, p.y + y[u].y, p.z + y[u].z, p.w + y[u].w);
+                q = make_float4(fmaf(y[u].x, y[u].x, q.x), fmaf(y[u].y, y[u].y, q.y), fmaf(y[u].z, y[u].z, q.z),
+                                fmaf(y[u].w, y[u].w, q.w));
+            } else {
+                float4 dz = d[u];
+                const float4 yh = make_float4((y[u].x - mu.x) * rs.x, (y[u].y - mu.y) * rs.y, (y[u].z - mu.z) * rs.z,
+                                              (y[u].w - mu.w) * rs.w);
+                if (relu) {
+                    if (!(fmaf(ga.x, yh.x, be.x) > 0.f)) dz.x = 0.f;
+                    if (!(fmaf(ga.y, yh.y, be.y) > 0.f)) dz.y = 0.f;
+                    if (!(fmaf(ga.z, yh.z, be.z) > 0.f)) dz.z = 0.f;
+                    if (!(fmaf(ga.w, yh.w, be.w) > 0.f)) dz.w = 0.f;
+                }
+                p = make_float4(p.x + dz.x, p.y + dz.y, p.z + dz.z, p.w + dz.w);
+                q = make_float4(fmaf(dz.x, yh.x, q.x), fmaf(dz.y, yh.y, q.y), fmaf(dz.z, yh.z, q.z), fmaf(dz.w, yh.w, q.w));
+            }
+        }
+        a[0] += p.x; a[1] += p.y; a[2] += p.z; a[3] += p.w;
+        a[4] += q.x; a[5] += q.y; a[6] += q.z; a[7] += q.w;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) sred[threadIdx.x * 8 + k] = a[k];
     __syncthreads();
-    if (ty == 0) {
-        for (int k = 0; k < 8; ++k) {
-            double t = 0.0;
-            for (int j = 0; j < TY; ++j) t += sred[(j * TX + tx) * 8 + k];
-            partial[((int64_t)blockIdx.x * 2 + (k >> 2)) * C + c + (k & 3)] = t;
-        }
+    for (int idx = threadIdx.x; idx < TX * 8; idx += BN4_THREADS) {     // one thread per (column quad, sum) pair
+        const int tx2 = idx >> 3, k = idx & 7;
+        double t = 0.0;
+        for (int j = 0; j < TY; ++j) t += sred[(j * TX + tx2) * 8 + k];
+        partial[((int64_t)blockIdx.x * 2 + (k >> 2)) * C + tx2 * 4 + (k & 3)] = t;
     }
 }
 
@@ -137,7 +157,7 @@ __device__ __forceinline__ void reduce_parts(const double* __restrict__ partial,
     __shared__ double r0[FIN_TY][33], r1[FIN_TY][33];
     double a = 0.0, b = 0.0;
     if (c < C)
-#pragma unroll 4
+#pragma unroll 10
         for (int p = threadIdx.y; p < nparts; p += FIN_TY) {
             a += partial[((int64_t)p * 2 + 0) * C + c];
             b += partial[((int64_t)p * 2 + 1) * C + c];
@@ -192,7 +212,7 @@ extern "C" int gnn_bn_stats(const float* Y, int64_t rows, int C, int training, f
     int parts = red_ctas(rows);
     if (training) {
         if (bn_vec_ok(C))
-            bn_partial4_kernel<0><<<parts, 256, 256 * 8 * sizeof(double), st>>>(Y, nullptr, nullptr, nullptr, nullptr,
+            bn_partial4_kernel<0><<<parts, BN4_THREADS, BN4_THREADS * 8 * sizeof(double), st>>>(Y, nullptr, nullptr, nullptr, nullptr,
                                                                                 rows, C, 0, partial);
         else
             bn_partial_kernel<0><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, nullptr, nullptr, nullptr, nullptr, rows, C,
@@ -332,7 +352,7 @@ extern "C" int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* st
     double* partial = reinterpret_cast<double*>(workspace);
     float* sums = reinterpret_cast<float*>(partial + (int64_t)parts * 2 * C);
     if (bn_vec_ok(C))
-        bn_partial4_kernel<1><<<parts, 256, 256 * 8 * sizeof(double), st>>>(Y, dOut, stats, gamma, beta, rows, C, relu,
+        bn_partial4_kernel<1><<<parts, BN4_THREADS, BN4_THREADS * 8 * sizeof(double), st>>>(Y, dOut, stats, gamma, beta, rows, C, relu,
                                                                             partial);
     else
         bn_partial_kernel<1><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, dOut, stats, gamma, beta, rows, C, relu, partial);
