@@ -307,21 +307,58 @@ def main():
             sys.stderr.write(f"{n:32s} {t / 2:9.3f} ms/step {c // 2:4d} calls/step {100 * t / total:5.1f}%\n")
 
     # ---------------- end to end from pinned host buffers (`e2e`)
-    def e2e_step(i):
-        hb = pinned[i % NUM_BATCHES]
-        db = hb._apply(lambda t: t.to(dev, non_blocking=True))
-        return float(engine.step(db).item())     # D2H read of the step loss
+    # The public feed: DevicePrefetcher copies each step's batch from pinned host memory on a side stream while the
+    # previous step computes; every step's loss is read back to the host (one step late, so the read does not drain
+    # the queue).  All copies and reads of the K timed steps happen inside the timed region.
+    from gnnepcsaft_b200.data.loader import DevicePrefetcher
 
-    for i in range(3):
-        e2e_step(i)
+    def host_feed(count):
+        for i in range(count):
+            yield pinned[i % NUM_BATCHES]
+
+    def e2e_run(count):
+        losses, pending = [], None
+        for db in DevicePrefetcher(host_feed(count), dev, depth=2):
+            loss_dev = engine.step(db)
+            host_loss = torch.empty(1, dtype=torch.float32, pin_memory=True)
+            host_loss.copy_(loss_dev, non_blocking=True)                # D2H of this step's loss
+            ev = torch.cuda.Event()
+            ev.record()
+            if pending is not None:
+                pending[1].synchronize()
+                losses.append(float(pending[0]))
+            pending = (host_loss, ev)
+        pending[1].synchronize()
+        losses.append(float(pending[0]))
+        return losses
+
+    e2e_run(3)
     sync_all()
     e0.record()
-    for i in range(args.steps):
-        e2e_step(i)
+    e2e_losses = e2e_run(args.steps)
     e1.record()
     sync_all()
+    assert len(e2e_losses) == args.steps
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * GRAPHS_PER_GPU * args.steps / (ms_e2e * 1e-3)
+
+    # ---------------- batched inference (forward only, eval-mode BatchNorm): reported beside the training metric
+    def infer_pass(count):
+        out = None
+        for i in range(count):
+            out = engine.predict(dev_batches[i % NUM_BATCHES])
+        return out
+
+    infer_pass(3)
+    sync_all()
+    e0.record()
+    infer_pass(args.steps)
+    e1.record()
+    sync_all()
+    ms_inf = max_over_ranks(e0.elapsed_time(e1))
+    inference = {"value": world * GRAPHS_PER_GPU * args.steps / (ms_inf * 1e-3), "unit": "graphs/s",
+                 "ms_per_batch": ms_inf / args.steps,
+                 "what": "eval forward (CSR build + 6 PNAConv + pool + head) on the same device-resident 4096-graph batches"}
 
     # ---------------- CPU baseline (rank 0, N=1 only): bounded sample of the same workload
     cpu_baseline = None
@@ -345,6 +382,7 @@ def main():
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches_per_step * args.steps), "abi_calls_per_step": calls_per_step,
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "kernel_shares": shares,
+                "inference": inference,
                 "final_loss": final_loss}
         _emit(line)
     if world > 1:
