@@ -280,7 +280,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": agg_ms, "launches_timed": cnt}
     # DRAM bytes per launch of the same kernel on the same workload from the committed ncu --set full capture
     try:
-        tname = "r1_agg_src_fwd_traffic.json" if folded else "r1_agg_fwd_traffic.json"
+        tname = "r1_agg_src_fwd_traffic.json" if folded else os.path.join("history", "r1_agg_fwd_traffic.json")
         with open(os.path.join(ROOT, "profiles", tname)) as fh:
             tr = json.load(fh)
         if tr.get("workload_nodes") == int(n_nodes):
@@ -316,11 +316,13 @@ def main():
         for i in range(count):
             yield pinned[i % NUM_BATCHES]
 
+    loss_slots = torch.empty(max(args.steps, 3), dtype=torch.float32, pin_memory=True)   # pinned once, outside the loop
+
     def e2e_run(count):
         losses, pending = [], None
-        for db in DevicePrefetcher(host_feed(count), dev, depth=2):
+        for k, db in enumerate(DevicePrefetcher(host_feed(count), dev, depth=2)):
             loss_dev = engine.step(db)
-            host_loss = torch.empty(1, dtype=torch.float32, pin_memory=True)
+            host_loss = loss_slots[k:k + 1]
             host_loss.copy_(loss_dev, non_blocking=True)                # D2H of this step's loss
             ev = torch.cuda.Event()
             ev.record()

@@ -560,26 +560,31 @@ pna_aggregate_bwd_kernel(const float* __restrict__ gA, const float* __restrict__
 }
 
 // dtab_accum[k] += sum over the partial tables; the partial tables are cleared for the next call.
-// block (32 outputs, 8 part phases): every thread sums DTAB_PARTS / 8 partials with independent loads
+// block (64 float4 columns, 4 part phases): every thread sums DTAB_PARTS / 4 partials with independent 16-byte loads
+// (all in flight together), the phases meet in shared memory.  total % 4 == 0 (C % 4 == 0).
 __global__ void __launch_bounds__(256)
 dtab_reduce_kernel(float* __restrict__ parts, int total, float* __restrict__ dtab_accum) {
-    __shared__ float red[8][33];
-    const int i = blockIdx.x * 32 + threadIdx.x;
-    float acc = 0.f;
-    if (i < total) {
+    __shared__ float4 red[4][64];
+    const int i4 = blockIdx.x * 64 + threadIdx.x;          // float4 column
+    const int total4 = total >> 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i4 < total4) {
+        float4 v[DTAB_PARTS / 4];
 #pragma unroll
-        for (int p = threadIdx.y; p < DTAB_PARTS; p += 8) {
-            acc += parts[(size_t)p * total + i];
-            parts[(size_t)p * total + i] = 0.f;
+        for (int k = 0; k < DTAB_PARTS / 4; ++k)
+            v[k] = *reinterpret_cast<const float4*>(parts + (size_t)(threadIdx.y + 4 * k) * total + 4 * i4);
+#pragma unroll
+        for (int k = 0; k < DTAB_PARTS / 4; ++k) {
+            acc = add4(acc, v[k]);
+            *reinterpret_cast<float4*>(parts + (size_t)(threadIdx.y + 4 * k) * total + 4 * i4) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     red[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.y == 0 && i < total) {
-        float t = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-        dtab_accum[i] += t;
+    if (threadIdx.y == 0 && i4 < total4) {
+        const float4 t = add4(add4(red[0][threadIdx.x], red[1][threadIdx.x]), add4(red[2][threadIdx.x], red[3][threadIdx.x]));
+        float4* dst = reinterpret_cast<float4*>(dtab_accum + 4 * i4);
+        *dst = add4(*dst, t);
     }
 }
 
@@ -612,7 +617,7 @@ static int aggregate_bwd_launch(const float* gA, const float* P, const float* ta
     pna_aggregate_bwd_kernel<SRC_ONLY><<<(unsigned)blocks, AGG_THREADS, 0, st>>>(gA, P, tab, A, rowptr, col_src, col_code,
                                                                                  (int)n, C, F, dP, dq, parts);
     const int total = GNN_NUM_BOND_CODES * C;
-    dtab_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(parts, total, dtab_accum);
+    dtab_reduce_kernel<<<(total / 4 + 63) / 64, dim3(64, 4), 0, st>>>(parts, total, dtab_accum);
     return gnn_launch_status();
 }
 
