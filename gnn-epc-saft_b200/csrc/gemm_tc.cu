@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace tc {
 
@@ -114,6 +115,45 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
             : "memory");
 }
+// D += A . B (accumulate flag as an immediate: no predicate set-up on the single issuing thread)
+template <int MODE>
+__device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (tf32_like(MODE))
+        asm volatile("tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, 1;" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+                     : "memory");
+    else
+        asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
+                     : "memory");
+}
+__device__ __forceinline__ void umma_ts_tf32_acc(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
+    asm volatile("tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, 1;" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc)
+                 : "memory");
+}
+// A operand in tensor memory (lane = row, one 32-bit column per tf32 element), B from a shared-memory descriptor
+__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// registers -> TMEM: 16 consecutive 32-bit columns of this thread's lane (warp w owns lanes 32 (w % 4) ..)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -690,9 +730,18 @@ __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_
 // 16-byte chunk c = p & 7 of rows r0 + 16 i: every load is a 128-bit coalesced access (8 lanes = 128 contiguous
 // bytes of one row), all eight are issued before the first conversion, addresses advance by a constant stride and
 // smem offsets are compile-time strides.  Full tiles take a branch-free path.
+// The tile is produced in two phases so that the global loads of a k-block are already in flight while the producer
+// group still waits for its ring stage to be released by the MMAs (the loads never touch shared memory):
+//   load_a_seg : resolve segments, issue the eight 16-byte loads (and the degree scalers) - no use of the values
+//   store_a_seg: scale, convert and write the swizzled image
 template <int MODE, bool SCALED>
-__device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uint8_t* tile, uint32_t plane_bytes,
-                                              int64_t m0, int64_t kbase, int64_t k_end, int p) {
+struct ATile {
+    float4 v[8], w[MODE == MODE_BF16 ? 8 : 1];
+    float f0[SCALED ? 8 : 1], f1[(SCALED && MODE == MODE_BF16) ? 8 : 1];
+};
+template <int MODE, bool SCALED>
+__device__ __forceinline__ void load_a_seg(const SegOperand& op, int grp, int64_t m0, int64_t kbase, int64_t k_end, int p,
+                                           ATile<MODE, SCALED>& t) {
     constexpr int EPC = tf32_like(MODE) ? 4 : 8;
     const int c = p & 7, r0 = p >> 3;
     const int64_t k = kbase + c * EPC;
@@ -700,54 +749,102 @@ __device__ __forceinline__ void produce_a_seg(const SegOperand& op, int grp, uin
     const SegRef s0 = k < k_end ? seg_resolve(op, k, grp) : SegRef{nullptr, 0, -1};
     const SegRef s1 = (MODE == MODE_BF16 && k + 4 < k_end) ? seg_resolve(op, k + 4, grp) : SegRef{nullptr, 0, -1};
     const int64_t row0 = m0 + r0;
-    const uint32_t off0 = (uint32_t)r0 * ROW_BYTES + (uint32_t)((c ^ (r0 & 7)) << 4);   // (r0 + 16 i) & 7 == r0 & 7
-    const uint32_t coff0 = sw128_coff(r0, c, 0), coff1 = sw128_coff(r0, c, 1);
     const float* q0 = s0.ptr != nullptr ? s0.ptr + row0 * s0.ld : nullptr;
     const float* q1 = s1.ptr != nullptr ? s1.ptr + row0 * s1.ld : nullptr;
     const int64_t st0 = 16 * s0.ld, st1 = 16 * s1.ld;
     const bool full = m0 + BM <= op.rows;
-    float4 v[8], w[MODE == MODE_BF16 ? 8 : 1];
     if (full) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            v[i] = q0 != nullptr ? ldg4(q0 + i * st0) : zero;
-            if (MODE == MODE_BF16) w[i] = q1 != nullptr ? ldg4(q1 + i * st1) : zero;
+            t.v[i] = q0 != nullptr ? ldg4(q0 + i * st0) : zero;
+            if (MODE == MODE_BF16) t.w[i] = q1 != nullptr ? ldg4(q1 + i * st1) : zero;
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const bool ok = row0 + 16 * i < op.rows;
-            v[i] = (ok && q0 != nullptr) ? ldg4(q0 + i * st0) : zero;
-            if (MODE == MODE_BF16) w[i] = (ok && q1 != nullptr) ? ldg4(q1 + i * st1) : zero;
+            t.v[i] = (ok && q0 != nullptr) ? ldg4(q0 + i * st0) : zero;
+            if (MODE == MODE_BF16) t.w[i] = (ok && q1 != nullptr) ? ldg4(q1 + i * st1) : zero;
         }
     }
     if (SCALED) {
-        if (s0.scale >= 0 || (MODE == MODE_BF16 && s1.scale >= 0)) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t row = row0 + 16 * i;
-                if (row < op.rows) {
-                    if (s0.scale >= 0) {
-                        const float f = __ldg(op.scal + 2 * row + s0.scale);
-                        v[i] = make_float4(v[i].x * f, v[i].y * f, v[i].z * f, v[i].w * f);
-                    }
-                    if (MODE == MODE_BF16 && s1.scale >= 0) {
-                        const float f = __ldg(op.scal + 2 * row + s1.scale);
-                        w[i] = make_float4(w[i].x * f, w[i].y * f, w[i].z * f, w[i].w * f);
-                    }
-                }
-            }
+        for (int i = 0; i < 8; ++i) {
+            const int64_t row = row0 + 16 * i;
+            const bool ok = row < op.rows;
+            t.f0[i] = (ok && s0.scale >= 0) ? __ldg(op.scal + 2 * row + s0.scale) : 1.f;
+            if (MODE == MODE_BF16) t.f1[i] = (ok && s1.scale >= 0) ? __ldg(op.scal + 2 * row + s1.scale) : 1.f;
         }
     }
+}
+template <int MODE, bool SCALED>
+__device__ __forceinline__ void store_a_seg(uint8_t* tile, uint32_t plane_bytes, int p, ATile<MODE, SCALED>& t) {
+    const int c = p & 7, r0 = p >> 3;
+    const uint32_t off0 = (uint32_t)r0 * ROW_BYTES + (uint32_t)((c ^ (r0 & 7)) << 4);   // (r0 + 16 i) & 7 == r0 & 7
+    const uint32_t coff0 = sw128_coff(r0, c, 0), coff1 = sw128_coff(r0, c, 1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
+        float4 v = t.v[i], w = t.w[MODE == MODE_BF16 ? i : 0];
+        if (SCALED) {
+            const float f = t.f0[i];
+            v = make_float4(v.x * f, v.y * f, v.z * f, v.w * f);
+            if (MODE == MODE_BF16) {
+                const float g1 = t.f1[MODE == MODE_BF16 ? i : 0];
+                w = make_float4(w.x * g1, w.y * g1, w.z * g1, w.w * g1);
+            }
+        }
         const uint32_t off = off0 + (uint32_t)i * (16 * ROW_BYTES);
-        if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, off, v[i]);
+        if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, off, v);
         else if (MODE == MODE_TF32C)
             put_chunk_tf32c<false>(tile, plane_bytes, off, coff0 + (uint32_t)i * (16 * ROW_BYTES),
-                                   coff1 + (uint32_t)i * (16 * ROW_BYTES), v[i]);
-        else put_chunk_bf16(tile, off, v[i], w[MODE == MODE_BF16 ? i : 0]);
+                                   coff1 + (uint32_t)i * (16 * ROW_BYTES), v);
+        else put_chunk_bf16(tile, off, v, w);
     }
+}
+
+// A operand straight into tensor memory (TF32X3, K-major): thread = one row of the 128-row tile (TMEM lane), which
+// loads its 32 k-block columns as eight 16-byte chunks (one full 128-byte line per thread), splits them into tf32
+// hi / lo and writes 2 x 32 TMEM columns with tcgen05.st.  The MMAs then read only the B operand from shared memory:
+// below N = 128 an SS-mode MMA is bound by its shared-memory operand reads ((128 + N) x 32 B at 128 B/clk, measured
+// with tools/mma_rate.cu), and the producers' own tile stores compete for the same bandwidth.
+// Requires k-block aligned segments (starts and widths multiples of 32 columns, checked by the host): one segment
+// lookup and one row pointer per k-block, all eight loads in flight together.
+struct ATmemRow {
+    float4 v[8];
+    float f;
+};
+template <bool SCALED>
+__device__ __forceinline__ void load_a_tmem(const SegOperand& op, int grp, int64_t row, int64_t kbase, int64_t k_end,
+                                            ATmemRow& t) {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const SegRef sr = kbase < k_end ? seg_resolve(op, kbase, grp) : SegRef{nullptr, 0, -1};
+    const bool ok = row < op.rows && sr.ptr != nullptr;
+    const float* q = ok ? sr.ptr + row * sr.ld : nullptr;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) t.v[c] = ok ? ldg4(q + 4 * c) : zero;
+    t.f = 1.f;
+    if (SCALED) {
+        if (ok && sr.scale >= 0) t.f = __ldg(op.scal + 2 * row + sr.scale);
+    }
+}
+template <bool SCALED>
+__device__ __forceinline__ void store_a_tmem(uint32_t taddr_hi, ATmemRow& t) {
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        float4 a = t.v[2 * qd], b = t.v[2 * qd + 1];
+        if (SCALED) {
+            a = make_float4(a.x * t.f, a.y * t.f, a.z * t.f, a.w * t.f);
+            b = make_float4(b.x * t.f, b.y * t.f, b.z * t.f, b.w * t.f);
+        }
+        float4 h0, l0, h1, l1;
+        split_tf32(a, h0, l0);
+        split_tf32(b, h1, l1);
+        const float hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        tmem_st8(taddr_hi + qd * 8, hi);
+        tmem_st8(taddr_hi + 32 + qd * 8, lo);
+    }
+    tmem_wait_st();
 }
 
 // MN-major tile from a segmented operand (weight gradients: the reduction index is the node).
@@ -957,7 +1054,10 @@ pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t*
     produce_tile<MODE>(bl, tile, b_plane, rows, (int64_t)nt * BN + r_begin, (int64_t)kb * KB_ELEMS, K, threadIdx.x);
 }
 
-template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP>
+// A_TMEM (TF32X3, K-major, packed weights): the activation operand lives in tensor memory (4 ring stages x 64 columns
+// behind the two accumulators) instead of shared memory; the smem ring then holds only the TMA-fetched weight tiles.
+constexpr uint32_t A_TMEM_STAGE_COLS = 64;
+template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP, bool A_TMEM = false>
 __global__ void __launch_bounds__(cta_threads(MN_MAJOR), 1)
 gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b) {
     extern __shared__ uint8_t smem_raw[];
@@ -968,15 +1068,20 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
     constexpr int PARTS = tf32_like(MODE) ? 2 : 1;
     constexpr int EPI_WARPS = epi_warps(MN_MAJOR), MMA_WARP = MN_MAJOR ? 0 : EPI_WARPS;
     constexpr int PROD_WARP0 = MN_MAJOR ? EPI_WARPS : EPI_WARPS + 1;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // The warp index goes through a shuffle so that the compiler treats it (and every role branch on it) as
+    // warp-uniform: inside a branch it believes divergent it cannot use the uniform datapath, and each tcgen05.mma -
+    // whose descriptors live in uniform registers - was wrapped in an ELECT / 4 x R2UR.BROADCAST "waterfall" loop
+    // that paced the single issuing thread at ~140 cycles per MMA (tools/mma_noise.cu reproduces the number).
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int BN = g.BN, NS = g.stages;
     const long long kernel_t0 = g.prof ? clock64() : 0;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int KBR = MN_MAJOR ? g.kb_rows : KB_ELEMS;                 // K rows per ring stage
     const uint32_t kdiv = MN_MAJOR ? (uint32_t)(KB_ELEMS / g.kb_rows) : 1u;
-    const uint32_t a_plane = BM * ROW_BYTES / kdiv, b_plane = (uint32_t)BN * ROW_BYTES / kdiv;
+    const uint32_t a_plane = A_TMEM ? 0u : BM * ROW_BYTES / kdiv, b_plane = (uint32_t)BN * ROW_BYTES / kdiv;
     const uint32_t stage_bytes = PARTS * (a_plane + b_plane);        // multiple of 1024
+    const uint32_t a_tmem_col0 = g.tmem_cols - 4 * A_TMEM_STAGE_COLS;   // A ring: the last 256 columns (A_TMEM only)
 
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, g.tmem_cols);
     if (tid == 0) {
@@ -1077,6 +1182,9 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
     // =============================== MMA issue (one work item, one warp) ===============================
     const uint32_t idesc = instr_desc(MODE, BN, MN_MAJOR ? 1 : 0);
     const uint32_t idesc16 = instr_desc(MODE_BF16, BN, MN_MAJOR ? 1 : 0);      // correction MMAs of MODE_TF32C
+    // The warp shares its scheduler with six busy producer / epilogue warps, so every instruction of the issue loop
+    // counts: running stage counters instead of a division per k-block, descriptors built once per k-block.
+    uint32_t ms = 0, muse = 0;                  // ring stage / use count of the next k-block
     auto mma_item = [&](int64_t item, uint32_t t, uint32_t& it) {
         {
             int64_t m0, k_begin, k_end;
@@ -1088,10 +1196,14 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + b * (uint32_t)BN;
             for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                const uint32_t s = it % NS, use = it / NS;          // warp-uniform, one warp: cheap enough
+                const uint32_t s = ms, use = muse;
+                if (++ms == (uint32_t)NS) {
+                    ms = 0;
+                    ++muse;
+                }
                 const long long mt0 = g.prof ? clock64() : 0;
                 mbar_wait(&full_bar[s], use & 1);
-                tc_fence_after();
+                if (A_TMEM) tc_fence_after();       // TMEM operand written by other threads (tcgen05.st)
                 if (g.prof && lane == 0) {
                     atomicAdd(g.prof + 4, (unsigned long long)(clock64() - mt0));   // MMA warp waiting for operands
                     atomicAdd(g.prof + 5, 1ull);
@@ -1101,33 +1213,48 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     const uint32_t b_hi = a_hi + PARTS * a_plane, b_lo = b_hi + b_plane;
                     const int ksteps = (CHUNKS / 2) / (int)kdiv;
                     uint64_t corr_a[CHUNKS / 2], corr_b[CHUNKS / 2];
+                    // Descriptors of k-step 0 once per k-block; a k-step only advances the 14-bit start-address field
+                    // (16-byte units), so the other k-steps are one 64-bit add each.  This thread's instruction stream
+                    // is what paces the tensor pipe: with the descriptors rebuilt per k-step and a predicate set up per
+                    // MMA it issued one MMA per ~140 cycles against a hardware rate of 48-64 (tools/mma_rate.cu).
+                    uint64_t dah0, dal0, dbh0, dbl0;
+                    uint32_t astep, bstep;
+                    if (MN_MAJOR) {
+                        // one MMA spans two K groups (tf32: 2 x 4 rows, bf16: 2 x 8 rows) linked by the stride offset
+                        constexpr uint32_t ATOM = tf32_like(MODE) ? 512 : 1024;
+                        constexpr uint32_t LT = tf32_like(MODE) ? 1 : 2;
+                        const uint32_t a_kgs = (BM * (tf32_like(MODE) ? 4 : 2) / 128) * ATOM;
+                        const uint32_t b_kgs = ((uint32_t)BN * (tf32_like(MODE) ? 4 : 2) / 128) * ATOM;
+                        dah0 = smem_desc_sw128_mn(a_hi, ATOM, a_kgs, LT);
+                        dal0 = smem_desc_sw128_mn(a_lo, ATOM, a_kgs, LT);
+                        dbh0 = smem_desc_sw128_mn(b_hi, ATOM, b_kgs, LT);
+                        dbl0 = smem_desc_sw128_mn(b_lo, ATOM, b_kgs, LT);
+                        astep = (2 * a_kgs) >> 4;
+                        bstep = (2 * b_kgs) >> 4;
+                    } else {
+                        dah0 = smem_desc_sw128(a_hi);
+                        dal0 = smem_desc_sw128(a_lo);
+                        dbh0 = smem_desc_sw128(b_hi);
+                        dbl0 = smem_desc_sw128(b_lo);
+                        astep = bstep = 32 >> 4;
+                    }
 #pragma unroll
                     for (int j = 0; j < CHUNKS / 2; ++j) {       // one MMA consumes 32 bytes of K (8 tf32 / 16 bf16)
                         if (j >= ksteps) break;
                         const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
-                        uint64_t dah, dal, dbh, dbl;
-                        if (MN_MAJOR) {
-                            // one MMA spans two K groups (tf32: 2 x 4 rows, bf16: 2 x 8 rows) linked by the stride offset
-                            constexpr uint32_t ATOM = tf32_like(MODE) ? 512 : 1024;
-                            constexpr uint32_t LT = tf32_like(MODE) ? 1 : 2;
-                            const uint32_t a_kgs = (BM * (tf32_like(MODE) ? 4 : 2) / 128) * ATOM;
-                            const uint32_t b_kgs = ((uint32_t)BN * (tf32_like(MODE) ? 4 : 2) / 128) * ATOM;
-                            const uint32_t ao = j * 2 * a_kgs, bo = j * 2 * b_kgs;
-                            dah = smem_desc_sw128_mn(a_hi + ao, ATOM, a_kgs, LT);
-                            dal = smem_desc_sw128_mn(a_lo + ao, ATOM, a_kgs, LT);
-                            dbh = smem_desc_sw128_mn(b_hi + bo, ATOM, b_kgs, LT);
-                            dbl = smem_desc_sw128_mn(b_lo + bo, ATOM, b_kgs, LT);
-                        } else {
-                            const uint32_t koff = j * 32;
-                            dah = smem_desc_sw128(a_hi + koff);
-                            dal = smem_desc_sw128(a_lo + koff);
-                            dbh = smem_desc_sw128(b_hi + koff);
-                            dbl = smem_desc_sw128(b_lo + koff);
-                        }
-                        if (MODE == MODE_TF32X3) {
-                            umma<MODE>(tmem_d, dal, dbh, idesc, first);
-                            umma<MODE>(tmem_d, dah, dbl, idesc, 1u);
-                            umma<MODE>(tmem_d, dah, dbh, idesc, 1u);
+                        const uint64_t dah = dah0 + (uint64_t)(j * astep), dal = dal0 + (uint64_t)(j * astep);
+                        const uint64_t dbh = dbh0 + (uint64_t)(j * bstep), dbl = dbl0 + (uint64_t)(j * bstep);
+                        if (A_TMEM) {
+                            const uint32_t ta_hi = tmem_base + a_tmem_col0 + s * A_TMEM_STAGE_COLS + (uint32_t)j * 8u;
+                            if (j == 0) umma_ts_tf32(tmem_d, ta_hi + 32u, dbh, idesc, first);
+                            else umma_ts_tf32_acc(tmem_d, ta_hi + 32u, dbh, idesc);
+                            umma_ts_tf32_acc(tmem_d, ta_hi, dbl, idesc);
+                            umma_ts_tf32_acc(tmem_d, ta_hi, dbh, idesc);
+                        } else if (MODE == MODE_TF32X3) {
+                            if (j == 0) umma<MODE>(tmem_d, dal, dbh, idesc, first);
+                            else umma_acc<MODE>(tmem_d, dal, dbh, idesc);
+                            umma_acc<MODE>(tmem_d, dah, dbl, idesc);
+                            umma_acc<MODE>(tmem_d, dah, dbh, idesc);
                         } else if (MODE == MODE_TF32C) {
                             // hi*hi on the tf32 path, then one bf16 MMA over the K-doubled correction planes
                             uint64_t dac, dbc;
@@ -1143,7 +1270,8 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                             corr_a[j] = dac;
                             corr_b[j] = dbc;
                         } else {
-                            umma<MODE>(tmem_d, dah, dbh, idesc, first);
+                            if (j == 0) umma<MODE>(tmem_d, dah, dbh, idesc, first);
+                            else umma_acc<MODE>(tmem_d, dah, dbh, idesc);
                         }
                     }
                     if (MODE == MODE_TF32C) {      // the bf16 MMAs of the k-block go out together: one kind switch per k-block
@@ -1210,10 +1338,17 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 const uint32_t s = (uint32_t)pg, use = my_use;
                 const long long pt0 = g.prof ? clock64() : 0;
                 if (g.prof && p == 0 && pg == 0 && my_use == 0) atomicAdd(g.prof + 12, (unsigned long long)(pt0 - kernel_t0));   // set-up until the first k-block
+                const int64_t kbase = k_begin + (int64_t)kb * KBR;
+                // K-major activation tiles: the global loads go out before the wait for the ring stage
+                ATile<MODE, SCALED> at;
+                ATmemRow ar;
+                if constexpr (!MN_MAJOR) {
+                    if constexpr (A_TMEM) load_a_tmem<SCALED>(aop, grp, m0 + (warp & 3) * 32 + lane, kbase, k_end, ar);
+                    else load_a_seg<MODE, SCALED>(aop, grp, m0, kbase, k_end, p, at);
+                }
                 if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
                 const long long pt1 = g.prof ? clock64() : 0;
                 uint8_t* stage = smem + (size_t)s * stage_bytes;
-                const int64_t kbase = k_begin + (int64_t)kb * KBR;
                 if constexpr (PACKED) {
                     // the weight operand was pre-packed as the smem image: one TMA bulk copy per k-block
                     if (p == 0) {
@@ -1222,7 +1357,14 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         mbar_expect_tx(&full_bar[s], bytes);
                         bulk_g2s(stage + PARTS * a_plane, packed_b + tile_idx * bytes, bytes, &full_bar[s]);
                     }
-                    produce_a_seg<MODE, SCALED>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
+                    if constexpr (A_TMEM) {
+                        tc_fence_after();          // the MMAs that read this TMEM stage have retired (empty barrier)
+                        const uint32_t q = (uint32_t)(warp & 3);      // TMEM lane quarter this warp may access
+                        store_a_tmem<SCALED>(tmem_base + a_tmem_col0 + s * A_TMEM_STAGE_COLS + ((q * 32u) << 16), ar);
+                        tc_fence_before();
+                    } else {
+                        store_a_seg<MODE, SCALED>(stage, a_plane, p, at);
+                    }
                 } else if constexpr (MN_MAJOR && tf32_like(MODE)) {
                     // loads per thread: A (128 columns) KBR / 4 rows; B (BN columns) KBR * BN / 512 rows
                     const int64_t lim = k_end < aop.rows ? k_end : aop.rows;
@@ -1238,7 +1380,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     produce_mn_seg<MODE, false>(bl, grp, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p,
                                                 nullptr, KBR);
                 } else {
-                    produce_a_seg<MODE, SCALED>(aop, grp, stage, a_plane, m0, kbase, k_end, p);
+                    store_a_seg<MODE, SCALED>(stage, a_plane, p, at);
                     produce_tile<MODE>(bl, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
                 }
                 const long long pt2 = g.prof ? clock64() : 0;
@@ -1343,6 +1485,27 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             dim3 pgrid((unsigned)(num_kb * ((BN + PACK_ROWS - 1) / PACK_ROWS)), (unsigned)g.n_tiles, (unsigned)groups);
             pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
                                                                           reinterpret_cast<uint8_t*>(pack_ws));
+            if constexpr (MODE == MODE_TF32X3) {
+                // activation operand in tensor memory: 2 accumulators (<= 256 columns) + 4 ring stages x 64 columns
+                // opt-in (GNN_B200_TMEM_A=1): correct (same tests) but not faster on the shapes of this model - the TS-mode
+                // MMAs and the tcgen05.st traffic cost what the saved shared-memory reads gain (5.89 vs 5.83 ms/step)
+                static const bool tmem_a_on = getenv("GNN_B200_TMEM_A") && atoi(getenv("GNN_B200_TMEM_A")) == 1;
+                bool aligned = true;       // k-block aligned segments (one segment per 32-column k-block)
+                for (int sg = 0; sg < aop.nseg; ++sg)
+                    aligned = aligned && (aop.seg[sg].start % kb_elems == 0) && (aop.seg[sg].width % kb_elems == 0);
+                if (tmem_a_on && BN <= 128 && aligned) {
+                    Geom ga = g;
+                    ga.stages = PROD_GROUPS;
+                    ga.tmem_cols = 512;
+                    const size_t smem_a = (size_t)PROD_GROUPS * parts * BN * ROW_BYTES + fixed;
+                    auto kern_a = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, true>;
+                    cudaError_t ea = cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+                    if (ea != cudaSuccess) return (int)ea;
+                    kern_a<<<(unsigned)grid, cta_threads(false), smem_a, st>>>(aop, bl, ep, ga,
+                                                                              reinterpret_cast<const uint8_t*>(pack_ws));
+                    return gnn_launch_status();
+                }
+            }
             auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
