@@ -267,3 +267,25 @@ def test_folded_destination_projection_matches_unfolded(train, monkeypatch):
     print(f"folded vs unfolded (train={train}): forward {e:.2e}, gradient rel-L2 {ge:.2e}")
     assert e <= (2e-4 if train else 1e-5), e        # train mode: std-threshold flips (documented floor 1.4e-4)
     assert ge <= 2e-3, ge
+
+
+def test_device_prefetcher_feeds_identical_batches():
+    """data/loader.py: the side-stream H2D feed must deliver exactly the host batches, in order, and the training
+    engine must produce the same losses as with synchronous `.to(device)` copies."""
+    from gnnepcsaft_b200.data.loader import DevicePrefetcher
+    from gnnepcsaft_b200.train.engine import TrainEngine
+    c = cfg(propagation_depth=2)
+    packed = make_packed_graphs(96, seed=5)
+    host = [batch_from_packed(packed, torch.arange(i * 32, (i + 1) * 32)) for i in range(3)]
+    got = list(DevicePrefetcher(iter(host), DEV, depth=2))
+    assert len(got) == 3
+    for h, d in zip(host, got):
+        for k in ("x", "edge_index", "edge_attr", "batch", "para"):
+            assert torch.equal(getattr(d, k).cpu(), getattr(h, k)), k
+    losses = []
+    for feed in ("sync", "prefetch"):
+        _, _, m = make_pair(c, packed.in_degree_histogram(), dtype64=False)
+        eng = TrainEngine.from_config(m.to(DEV), c)
+        it = (b.to(DEV) for b in host) if feed == "sync" else DevicePrefetcher(iter(host), DEV)
+        losses.append([float(eng.step(b)) for b in it])
+    assert losses[0] == losses[1], losses
