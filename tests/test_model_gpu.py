@@ -288,4 +288,7 @@ def test_device_prefetcher_feeds_identical_batches():
         eng = TrainEngine.from_config(m.to(DEV), c)
         it = (b.to(DEV) for b in host) if feed == "sync" else DevicePrefetcher(iter(host), DEV)
         losses.append([float(eng.step(b)) for b in it])
-    assert losses[0] == losses[1], losses
+    # the first loss is bit-identical (deterministic forward); later ones see parameters updated from gradients
+    # whose split-K / bond-table sums use floating-point atomics (order not fixed)
+    assert losses[0][0] == losses[1][0], losses
+    torch.testing.assert_close(torch.tensor(losses[1]), torch.tensor(losses[0]), rtol=1e-4, atol=1e-6)
