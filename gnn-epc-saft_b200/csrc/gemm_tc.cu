@@ -967,10 +967,12 @@ __device__ __forceinline__ MnPlan mn_plan(const SegOperand& op, int grp, int R, 
     pl.kgs16 = (uint32_t)(R >> 6) * 1024u;
     return pl;
 }
-template <int MODE, bool SCALED, int NA, int NB>
+// wait_stage() is called once all loads are in flight and before the first shared-memory store (the ring stage may
+// still be read by the MMAs of the previous use until then).
+template <int MODE, bool SCALED, int NA, int NB, class WaitFn>
 __device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnPlan& pb, uint8_t* a_tile, uint32_t a_plane,
                                                      uint8_t* b_tile, uint32_t b_plane, int64_t kbase, int64_t lim,
-                                                     float4* colacc) {
+                                                     float4* colacc, WaitFn&& wait_stage) {
     constexpr int KBR = NA * 4;                              // K rows (nodes) of this k-block: A has step 4
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 va[NA], vb[NB];
@@ -1000,6 +1002,7 @@ __device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnP
             vb[i] = (ok && qb != nullptr) ? ldg4(qb + i * pb.step_ld) : zero;
         }
     }
+    wait_stage();
 #pragma unroll
     for (int i = 0; i < NA; ++i) {
         if (SCALED) va[i] = make_float4(va[i].x * f[i], va[i].y * f[i], va[i].z * f[i], va[i].w * f[i]);
@@ -1346,8 +1349,13 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     if constexpr (A_TMEM) load_a_tmem<SCALED>(aop, grp, m0 + (warp & 3) * 32 + lane, kbase, k_end, ar);
                     else load_a_seg<MODE, SCALED>(aop, grp, m0, kbase, k_end, p, at);
                 }
-                if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-                const long long pt1 = g.prof ? clock64() : 0;
+                long long pt1 = 0;
+                auto wait_stage = [&]() {
+                    if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
+                    pt1 = g.prof ? clock64() : 0;
+                };
+                // the fp32 MN-major producers call wait_stage themselves, between their load and store phases
+                if constexpr (!(MN_MAJOR && tf32_like(MODE) && !PACKED)) wait_stage();
                 uint8_t* stage = smem + (size_t)s * stage_bytes;
                 if constexpr (PACKED) {
                     // the weight operand was pre-packed as the smem image: one TMA bulk copy per k-block
@@ -1370,10 +1378,10 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     const int64_t lim = k_end < aop.rows ? k_end : aop.rows;
                     uint8_t* bt = stage + PARTS * a_plane;
                     float4* ca = do_colsum ? colacc : nullptr;
-                    if (BN == 256) produce_mn_pair_tf32<MODE, SCALED, 4, 8>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
-                    else if (BN == 128) produce_mn_pair_tf32<MODE, SCALED, 4, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
-                    else if (BN == 64) produce_mn_pair_tf32<MODE, SCALED, 8, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
-                    else produce_mn_pair_tf32<MODE, SCALED, 8, 2>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca);
+                    if (BN == 256) produce_mn_pair_tf32<MODE, SCALED, 4, 8>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
+                    else if (BN == 128) produce_mn_pair_tf32<MODE, SCALED, 4, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
+                    else if (BN == 64) produce_mn_pair_tf32<MODE, SCALED, 8, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
+                    else produce_mn_pair_tf32<MODE, SCALED, 8, 2>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
                 } else if constexpr (MN_MAJOR) {
                     produce_mn_seg<MODE, SCALED>(aop, grp, stage, a_plane, BM, m0, kbase, k_end, p,
                                                  do_colsum ? colacc : nullptr, KBR);
