@@ -461,6 +461,28 @@ struct EStore {     // Y[m, n] = act(v + bias[n]) (+ Y)
         }
     }
 };
+// Y[m, n] = act(v + bias[n]) + skip[m, n]   (eval forward: Linear with BatchNorm folded in, ReLU, skip connection)
+struct EStoreSkip {
+    static constexpr int kWide = 0;
+    static constexpr int kCombine3 = 0;
+    float* y;
+    int64_t ldy;
+    const float* bias;
+    const float* skip;
+    int64_t ldskip;
+    int act;
+    __device__ __forceinline__ void set_group(int) {}
+    __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {   // N % 4 == 0, 16-byte aligned rows
+        const float4 b = ldg4(bias + n);
+        v = make_float4(v.x + b.x, v.y + b.y, v.z + b.z, v.w + b.w);
+        if (act) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+        if (skip != nullptr) {
+            const float4 sk = ldg4(skip + m * ldskip + n);
+            v = make_float4(v.x + sk.x, v.y + sk.y, v.z + sk.z, v.w + sk.w);
+        }
+        *reinterpret_cast<float4*>(y + m * ldy + n) = v;
+    }
+};
 struct EAtomic {
     static constexpr int kWide = 0;    // dW[m, n] += v
     float* y;
@@ -1585,6 +1607,25 @@ extern "C" int gnn_tc_linear_fwd(const float* X, int64_t ldx, const float* W, in
     SegOperand aop = seg_plain(X, ldx, M, K);
     VRowMajor bl{W, ldw, N, K, 0, is_vec(W, ldw)};
     EStore ep{Y, ldy, 0, bias, 0, act, 0, is_vec(Y, ldy) && (bias == nullptr || is_vec(bias, 0))};
+    const int BN = pick_bn(N);
+    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, M, N, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
+                                                  pack_ws_bytes)));
+}
+
+// Y = act(X W^T + bias) + skip   (skip may be NULL; N % 4 == 0).  With W / bias from gnn_bn_fold_linear this is
+// Linear -> BatchNorm(eval) -> ReLU -> skip add of reference models.py:128-131 in one GEMM.
+extern "C" int gnn_tc_linear_skip_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
+                                      int64_t M, int N, int K, int act, const float* skip, int64_t ldskip, float* Y,
+                                      int64_t ldy, int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream) {
+    if (M < 0 || N < 1 || K < 1 || bias == nullptr) return GNN_ERR_BAD_ARG;
+    REQUIRE_VEC(X, ldx);
+    REQUIRE_VEC(Y, ldy);
+    REQUIRE_VEC(bias, 0);
+    if (skip != nullptr) REQUIRE_VEC(skip, ldskip);
+    if (K % 4 != 0 || N % 4 != 0) return GNN_ERR_UNSUPPORTED;
+    SegOperand aop = seg_plain(X, ldx, M, K);
+    VRowMajor bl{W, ldw, N, K, 0, is_vec(W, ldw)};
+    EStoreSkip ep{Y, ldy, bias, skip, ldskip, act};
     const int BN = pick_bn(N);
     DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, M, N, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
                                                   pack_ws_bytes)));

@@ -366,6 +366,26 @@ extern "C" int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* st
     return gnn_launch_status();
 }
 
+// Eval-mode BatchNorm folded into the preceding Linear:  BN(x W^T + b) = x Wf^T + bf  with
+//   Wf[n, :] = W[n, :] * gamma[n] * rstd[n],   bf[n] = (b[n] - mean[n]) * gamma[n] * rstd[n] + beta[n]
+__global__ void bn_fold_linear_kernel(const float* __restrict__ W, int64_t ldw, const float* __restrict__ b,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ mean, const float* __restrict__ var, float eps, int N,
+                                      int K, float* __restrict__ Wf, float* __restrict__ bf) {
+    const int n = blockIdx.x;
+    const float sc = gamma[n] * (float)(1.0 / sqrt((double)var[n] + (double)eps));
+    for (int k = threadIdx.x; k < K; k += blockDim.x) Wf[(int64_t)n * K + k] = W[(int64_t)n * ldw + k] * sc;
+    if (threadIdx.x == 0) bf[n] = fmaf((b ? b[n] : 0.f) - mean[n], sc, beta[n]);
+}
+extern "C" int gnn_bn_fold_linear(const float* W, int64_t ldw, const float* bias, const float* gamma, const float* beta,
+                                  const float* running_mean, const float* running_var, float eps, int N, int K,
+                                  float* Wf, float* bf, void* stream) {
+    if (N < 1 || K < 1 || !W || !gamma || !beta || !running_mean || !running_var) return GNN_ERR_BAD_ARG;
+    bn_fold_linear_kernel<<<N, 64, 0, gnn_stream(stream)>>>(W, ldw, bias, gamma, beta, running_mean, running_var, eps, N,
+                                                           K, Wf, bf);
+    return gnn_launch_status();
+}
+
 // ------------------------------------------------------------------ segment pooling
 __global__ void segment_pool_fwd_kernel(const float* __restrict__ x, const int* __restrict__ graph_ptr, int64_t b,
                                         int C, float* __restrict__ out) {

@@ -442,6 +442,25 @@ def _bn_forward(y, bn: nn.BatchNorm1d, training: bool, skip, relu: bool):
     return out, stats, use_batch
 
 
+def _lin_bn_eval(mm, X, lin: nn.Linear, bn: nn.BatchNorm1d, skip, relu: bool):
+    """Inference fast path: Linear -> BatchNorm(eval) -> ReLU (-> + skip) as ONE tensor-core GEMM with the running
+    statistics folded into the weights (gnn_bn_fold_linear + gnn_tc_linear_skip_fwd).  Returns None when the shape
+    needs the general path."""
+    rows, k, nout = X.shape[0], lin.in_features, lin.out_features
+    if mm < 0 or bn.running_mean is None or (k & 3) or (nout & 3) or not _al(X, k) or rows == 0:
+        return None
+    dev = X.device
+    wf = torch.empty(nout, k, dtype=torch.float32, device=dev)
+    bf = torch.empty(nout, dtype=torch.float32, device=dev)
+    _c("gnn_bn_fold_linear", lin.weight, k, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+       float(bn.eps), nout, k, wf, bf)
+    out = torch.empty(rows, nout, dtype=torch.float32, device=dev)
+    ws = _pack_ws(dev)
+    _c("gnn_tc_linear_skip_fwd", X, k, wf, k, bf, rows, nout, k, 1 if relu else 0, skip, nout, out, nout, mm, ws,
+       ws.numel())
+    return out
+
+
 def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_graphs, save: bool, graph=None):
     _check_inputs(x_idx, edge_index, edge_attr, batch)
     pp, mp = model.pna_params, model.mlp_params
@@ -571,10 +590,16 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
             os_.append(O2)
             O = O2
         rec.os = os_
-        y = torch.empty(n, H, **f32)
-        _lin_fwd(mm, O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H)
-        rec.y = y
-        x, rec.stats, rec.bn_batch = _bn_forward(y, bn, training, rec.x_in if pp.skip_connections else None, True)
+        fused = None
+        if not training and not save:       # inference: lin + BatchNorm(running stats) + ReLU + skip in one GEMM
+            fused = _lin_bn_eval(mm, O, conv.lin, bn, rec.x_in if pp.skip_connections else None, True)
+        if fused is not None:
+            x = fused
+        else:
+            y = torch.empty(n, H, **f32)
+            _lin_fwd(mm, O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H)
+            rec.y = y
+            x, rec.stats, rec.bn_batch = _bn_forward(y, bn, training, rec.x_in if pp.skip_connections else None, True)
         if save:
             layers.append(rec)
 
@@ -588,6 +613,11 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
 
     def head_block(lin: nn.Linear, bn: Optional[nn.BatchNorm1d]):
         nonlocal hcur
+        if bn is not None and not training and not save:
+            fused = _lin_bn_eval(mm, hcur, lin, bn, None, True)
+            if fused is not None:
+                hcur = fused
+                return
         rec = _Saved()
         rec.inp, rec.lin, rec.bn = hcur, lin, bn
         z = torch.empty(hcur.shape[0], lin.out_features, **f32)

@@ -327,6 +327,19 @@ int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* stats, const 
                    float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
                    void* stream);
 
+/* Inference fast path: eval-mode BatchNorm folded into the preceding Linear, then Linear + ReLU + skip add in
+ * one tensor-core GEMM (replaces lin -> BatchNorm -> relu -> x + x_prev of models.py:128-131 and the head's
+ * Linear -> BatchNorm1d -> ReLU blocks when the model is in eval()).
+ *   gnn_bn_fold_linear   : Wf[n,:] = W[n,:] gamma[n] rstd[n];  bf[n] = (bias[n] - mean[n]) gamma[n] rstd[n] + beta[n]
+ *                          (Wf dense [N,K], rstd = 1/sqrt(running_var + eps); bias may be NULL)
+ *   gnn_tc_linear_skip_fwd: Y = act(X W^T + bias) + skip   (skip may be NULL; N, K multiples of 4) */
+int gnn_bn_fold_linear(const float* W, int64_t ldw, const float* bias, const float* gamma, const float* beta,
+                       const float* running_mean, const float* running_var, float eps, int N, int K,
+                       float* Wf, float* bf, void* stream);
+int gnn_tc_linear_skip_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
+                           int64_t M, int N, int K, int act, const float* skip, int64_t ldskip, float* Y,
+                           int64_t ldy, int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- pooling, loss, optimiser
  * global_add_pool (models.py:133): out[g,:] = sum_{i in graph g} x[i,:]; graph_ptr int32 [B+1] */
 int gnn_segment_pool_fwd(const float* x, const int32_t* graph_ptr, int64_t num_graphs, int C,

@@ -582,6 +582,23 @@ def gnn_bn_act_bwd(dOut, Y, stats, gamma, beta, rows, c, relu, training, dY, dga
     dY[:rows] = ga * stats[c:2 * c] * v
 
 
+def gnn_bn_fold_linear(W, ldw, bias, gamma, beta, running_mean, running_var, eps, N, K, Wf, bf, stream=None):
+    sc = _flat(gamma, N) * (1.0 / torch.sqrt(running_var.double() + eps)).to(W.dtype)
+    Wf.reshape(-1)[: N * K].view(N, K).copy_(_mat(W, N, K, ldw) * sc[:, None])
+    b = _flat(bias, N) if bias is not None else torch.zeros(N, dtype=W.dtype)
+    bf.reshape(-1)[:N] = (b - running_mean) * sc + _flat(beta, N)
+
+
+def gnn_tc_linear_skip_fwd(X, ldx, W, ldw, bias, M, N, K, act, skip, ldskip, Y, ldy, precision, pack_ws=None,
+                           pack_ws_bytes=0, stream=None):
+    y = _mat(X, M, K, ldx) @ _mat(W, N, K, ldw).t() + _flat(bias, N)
+    if act:
+        y = y.clamp(min=0)
+    if skip is not None:
+        y = y + _mat(skip, M, N, ldskip)
+    _mat(Y, M, N, ldy).copy_(y)
+
+
 def gnn_segment_pool_fwd(x, graph_ptr, b, c, out, stream=None):
     gp = graph_ptr[: b + 1].tolist()
     for g in range(b):

@@ -694,3 +694,34 @@ def test_tc_folded_stage(precision, n, F):
         return [dPs.to(dev), x.to(dev), n, F, T, gb, pre_ts, gb[F * 3 * F:], pre_ts, precision]
     res = both("gnn_tc_pna_projsrc_wgrad", mkw, 5)
     close(res[1], res[0], 2 * tol, "projsrc wgrad")
+
+
+@pytest.mark.parametrize("precision", [0, 2])
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 64), (4096, 32, 64), (130, 16, 32), (1, 8, 16)])
+def test_bn_fold_linear_and_skip_gemm(precision, M, N, K):
+    """Inference fast path: BatchNorm(eval) folded into the Linear, ReLU and skip add in the GEMM epilogue."""
+    tol = TC_TOL[precision]
+    g = torch.Generator().manual_seed(M + N)
+    X, W, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.2, torch.randn(N, generator=g)
+    gamma, beta = torch.rand(N, generator=g) + 0.5, torch.randn(N, generator=g)
+    mean, var = torch.randn(N, generator=g), torch.rand(N, generator=g) + 0.1
+    skip = torch.randn(M, N, generator=g)
+    cpu, gpu = run_both("gnn_bn_fold_linear", W, K, b, gamma, beta, mean, var, 1e-5, N, K, torch.zeros(N, K), torch.zeros(N))
+    close(gpu[-2], cpu[-2], 1e-6, "folded weight")
+    close(gpu[-1], cpu[-1], 1e-6, "folded bias")
+    Wf, bf = cpu[-2], cpu[-1]
+    # the folded GEMM reproduces Linear -> BatchNorm1d(eval) -> ReLU -> + skip
+    bn = torch.nn.BatchNorm1d(N).eval()
+    with torch.no_grad():
+        bn.weight.copy_(gamma), bn.bias.copy_(beta), bn.running_mean.copy_(mean), bn.running_var.copy_(var)
+        want = torch.relu(bn(X @ W.t() + b)) + skip
+    for sk in (skip, None):
+        res = []
+        for dev in ("cpu", DEV):
+            args = [X.to(dev), K, Wf.to(dev), K, bf.to(dev), M, N, K, 1, None if sk is None else sk.to(dev), N,
+                    torch.zeros(M, N, device=dev), N, precision, torch.zeros(4 << 20, dtype=torch.uint8, device=dev), 4 << 20]
+            R.gnn_tc_linear_skip_fwd(*args) if dev == "cpu" else _lib.call("gnn_tc_linear_skip_fwd", *args, _lib.stream_ptr())
+            res.append(args[11])
+        close(res[1], res[0], tol, "skip gemm")
+        if sk is not None:
+            close(res[1], want, max(tol, 2e-5), "vs torch BatchNorm1d(eval)")
