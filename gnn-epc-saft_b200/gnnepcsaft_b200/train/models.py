@@ -229,7 +229,7 @@ class _Workspace:
 
 
 _WS = _Workspace()
-PACK_WS_BYTES = 4 << 20
+PACK_WS_BYTES = 32 << 20      # covers the wide model (H = 256: 7.9 MB for the post GEMM image)
 
 
 def _pack_ws(device):
