@@ -407,6 +407,10 @@ struct EStore {     // Y[m, n] = act(v + bias[n]) (+ Y)
     int64_t bias_group_stride;
     int act, accumulate, vec;
     static constexpr int kCombine3 = 0;
+    static constexpr int kStaged = 1;       // plain stores may go through the shared-memory transposing epilogue
+    bool staged_ok(int N) const {           // host: no bias / activation / accumulate, 16-byte aligned rows
+        return bias == nullptr && act == 0 && accumulate == 0 && vec && (N & 3) == 0 && ((ldy | y_group_stride) & 3) == 0;
+    }
     static constexpr int kWide = 1;
     __device__ __forceinline__ void set_group(int g) {
         y += (int64_t)g * y_group_stride;
@@ -465,6 +469,7 @@ struct EStore {     // Y[m, n] = act(v + bias[n]) (+ Y)
 struct EStoreSkip {
     static constexpr int kWide = 0;
     static constexpr int kCombine3 = 0;
+    static constexpr int kStaged = 0;
     float* y;
     int64_t ldy;
     const float* bias;
@@ -489,6 +494,7 @@ struct EAtomic {
     int64_t ldy, y_group_stride;
     int vec;
     static constexpr int kCombine3 = 0;
+    static constexpr int kStaged = 0;
     __device__ __forceinline__ void set_group(int g) { y += (int64_t)g * y_group_stride; }
     __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
         float* dst = y + m * ldy + n;
@@ -512,6 +518,7 @@ struct EPostCombine {
     int64_t bias_tower_stride;
     int F_out, FoP, towers, tower, act, vec;
     static constexpr int kCombine3 = 1;
+    static constexpr int kStaged = 0;
     __device__ __forceinline__ void set_group(int g) { tower = g; bias += (int64_t)g * bias_tower_stride; }
     __device__ __forceinline__ void scalers(int64_t i, float& amp, float& att) const {
         amp = __ldg(scal + 2 * i);
@@ -543,6 +550,7 @@ struct EPostWgrad {
     int64_t tower_stride;
     int F, F_out, FoP, vec;
     static constexpr int kCombine3 = 0;
+    static constexpr int kStaged = 0;
     __device__ __forceinline__ void set_group(int g) { dw += (int64_t)g * tower_stride; }
     __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
         int s = (int)m / FoP, o = (int)m - s * FoP;
@@ -586,6 +594,7 @@ struct EProjStore {
     int F, towers;
     int64_t ldp;
     static constexpr int kCombine3 = 0;
+    static constexpr int kStaged = 0;
     __device__ __forceinline__ void set_group(int) {}
     __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
         const int C = towers * F;
@@ -604,6 +613,7 @@ struct EProjWgrad {
     int64_t tower_stride;
     int F, towers, first_part, nparts;
     static constexpr int kCombine3 = 0;
+    static constexpr int kStaged = 0;
     __device__ __forceinline__ void set_group(int) {}
     __device__ __forceinline__ void emit4(int64_t m, int n, int N, float4 v) const {
         const int C = towers * F;
@@ -636,6 +646,7 @@ struct Geom {
     uint32_t tmem_cols;
     ColSum colsum;
     unsigned long long* prof;    // optional cycle counters (debug): see gnn_tc_set_profile_buffer
+    uint32_t epi_stage_off;      // != 0: byte offset (from the aligned smem base) of 8 x 4 KB epilogue staging tiles
 };
 
 // ------------------------------------------------------------------ operand producers
@@ -1163,7 +1174,38 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 if (row_ok) ep.scalers(m, amp, att);
             }
             long long ld_cyc = 0;
-            for (int col = half * 16; col < out_cols; col += 4 * EPI_WARPS) {
+            bool staged = false;
+            if constexpr (EP::kStaged && !MN_MAJOR) {
+                if (g.epi_stage_off != 0) {
+                    // Transposing epilogue for wide plain outputs: with one accumulator row per lane every store
+                    // instruction touched 32 different 128-byte lines (32-byte pieces) and the 128 KB of a
+                    // 128 x 256 item took ~7000 cycles to leave the SM (the kernel ran 72.8 -> 39.4 us with the
+                    // stores removed).  Each warp now stages 32 rows x 32 columns in a swizzled 4 KB tile and writes
+                    // them back as full lines: 8 lanes cover the 128 contiguous bytes of a row.
+                    staged = true;
+                    uint8_t* tile = smem + g.epi_stage_off + (uint32_t)warp * 4096u;
+                    for (int col = half * 32; col < out_cols; col += 8 * EPI_WARPS) {
+                        float v[32];
+                        tmem_ld16(taddr + col, v);
+                        tmem_ld16(taddr + col + 16, v + 16);
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4)
+                            *reinterpret_cast<float4*>(tile + lane * 128 + ((c4 ^ (lane & 7)) << 4)) =
+                                make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = (lane >> 3) + 4 * i, c4 = lane & 7;
+                            const float4 val = *reinterpret_cast<const float4*>(tile + r * 128 + ((c4 ^ (r & 7)) << 4));
+                            const int64_t mr = m0 + q * 32 + r;
+                            const int n = n0 + col + c4 * 4;
+                            if (mr < g.M && n < g.N) *reinterpret_cast<float4*>(ep.y + mr * ep.ldy + n) = val;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            for (int col = half * 16; col < out_cols && !staged; col += 4 * EPI_WARPS) {
                 float v[16];
                 const long long lt0 = g.prof ? clock64() : 0;
                 tmem_ld16(taddr + col, v);
@@ -1496,7 +1538,15 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
     g.tmem_cols = cols;
     g.colsum = colsum;
     g.prof = g_prof;
-    const size_t smem = (size_t)stages * stage_bytes + fixed;
+    g.epi_stage_off = 0;
+    size_t smem = (size_t)stages * stage_bytes + fixed;
+    if constexpr (EP::kStaged && !MN_MAJOR) {
+        // wide plain outputs (BN = 256): 8 epilogue warps x 4 KB transposing tiles behind the operand ring
+        if (BN == 256 && ep.staged_ok(N) && smem + 8 * 4096 <= kSmemLimit) {
+            g.epi_stage_off = (uint32_t)((size_t)stages * stage_bytes);
+            smem += 8 * 4096;
+        }
+    }
     int64_t grid = g.num_items < gnn_sm_count() ? g.num_items : gnn_sm_count();
 
     if constexpr (MN_MAJOR) {
