@@ -69,7 +69,7 @@ class ClockSampler:
                     self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def start(self):
         self.thread.start()
@@ -257,7 +257,6 @@ def main():
         loss = engine.step(dev_batches[i % NUM_BATCHES])
     e1.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1))
     M.set_profiler(None)
     calls_per_step = (M.ABI_CALLS - calls0) / args.steps
@@ -343,6 +342,7 @@ def main():
     assert len(e2e_losses) == args.steps
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * GRAPHS_PER_GPU * args.steps / (ms_e2e * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None       # sampled from the warm-up through both timed regions
 
     # ---------------- batched inference (forward only, eval-mode BatchNorm): reported beside the training metric
     def infer_pass(count):
