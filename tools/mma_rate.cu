@@ -1,4 +1,6 @@
 // Microbenchmark (debug aid, run on the GPU box): issue rate of tcgen05.mma for the shapes the GEMM kernels use.
+// main() runs rate3_kernel (hoisted descriptors, optional concurrent tcgen05.ld); rate_kernel is the first version with
+// descriptors rebuilt in the loop (kept for reference, see tools/mma_noise.cu for the scheduler-contention experiment).
 // One CTA per SM, one thread issues REPS x (ksteps MMAs) back to back from shared-memory tiles, then commits and
 // waits; prints cycles per MMA for kind::tf32 / kind::f16, N in {64, 96, 128, 192, 256}, K-major SWIZZLE_128B.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/mma_rate tools/mma_rate.cu && tools/mma_rate
@@ -185,33 +187,6 @@ int main() {
                     printf("hoisted %s N=%3d flags(16 concurrent tcgen05.ld, 32 duty-cycled)=%2d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %.0f)\n",
                            bf16 ? "bf16" : "tf32", n, commit, out[0] / (4096.0 * 12), out[1] / (4096.0 * 12), 128.0 * n / 256.0);
                 }
-    }
-    return 0;
-}
-int main_old() {
-    long long* out;
-    cudaMallocManaged(&out, 2 * sizeof(long long));
-    const int smem = 98304 + 1024;
-    cudaFuncSetAttribute(rate_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    cudaFuncSetAttribute(rate_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    const int reps = 256;
-    const int ns[] = {64, 96, 128, 192, 256};
-    for (int grid : {1, 148}) {
-        for (int bf16 = 0; bf16 < 2; ++bf16)
-            for (int distinct : {1, 3})
-                for (int other = 0; other < 2; ++other)
-                    for (int n : ns) {
-                        if (other && n > 256) continue;
-                        for (int it = 0; it < 2; ++it) {
-                            if (bf16) rate_kernel<1><<<grid, 128, smem>>>(n, reps, distinct, other, out);
-                            else rate_kernel<0><<<grid, 128, smem>>>(n, reps, distinct, other, out);
-                            cudaError_t e = cudaDeviceSynchronize();
-                            if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-                        }
-                        const double mmas = (double)reps * 4 * distinct;
-                        printf("grid %3d %s N=%3d operands=%d alt_acc=%d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %.0f)\n",
-                               grid, bf16 ? "bf16" : "tf32", n, distinct, other, out[0] / mmas, out[1] / mmas, 128.0 * n / 256.0);
-                    }
     }
     return 0;
 }
