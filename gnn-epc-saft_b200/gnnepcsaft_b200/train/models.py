@@ -22,10 +22,11 @@ from .. import _lib
 from ..data.graph import ATOM_FEATURE_DIMS, BOND_FEATURE_DIMS, NUM_BOND_CODES
 
 TOWERS = 2  # reference models.py:76
-# Source-node gradient scatter: two passes with a fixed summation order (default; also the faster one on B200:
-# 191 + 48 us per layer) or, with GNN_B200_ATOMIC_SCATTER=1, 128-bit atomic adds inside the aggregate backward
-# kernel (no per-slot buffer, 248 us per layer).
-DETERMINISTIC_SCATTER = os.environ.get("GNN_B200_ATOMIC_SCATTER", "0") != "1"
+# Source-node gradient scatter: by default 128-bit atomic adds inside the aggregate backward kernel (no per-slot dq
+# buffer, no second pass: 139 us per layer on B200); GNN_B200_ATOMIC_SCATTER=0 selects the two-pass variant with a
+# fixed summation order (per-slot gradients dq + gnn_slot_sum_by_source: 134 + 49 us per layer).  The weight-gradient
+# split-K and bond-table sums use floating-point atomics in both variants.
+DETERMINISTIC_SCATTER = os.environ.get("GNN_B200_ATOMIC_SCATTER", "1") == "0"
 DEFAULT_MATMUL = "tf32x3"
 # Fold the destination projection of PNAConv into post_nns' weights (csrc/fold.cu): the aggregate kernels gather
 # source projections only.  Needs pre_layers == 1, self-loops (every node has an in-edge) and a tensor-core matmul mode;
