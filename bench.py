@@ -51,25 +51,58 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled during the timed regions.  In-process NVML queries (nvidia_ml_py) every
+    10 ms; spawning nvidia-smi instead takes ~100 ms per sample and its driver calls perturb the run it measures
+    (the end-to-end leg read 5-10 % slow with it), so that is only the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.samples, self.stop_flag, self.index = [], threading.Event(), index
         self.thread = threading.Thread(target=self.run, daemon=True)
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # the NVML index follows CUDA_VISIBLE_DEVICES only through the UUID / PCI bus id of the torch device
+            bus = torch.cuda.get_device_properties(index).pci_bus_id if hasattr(torch.cuda.get_device_properties(index), "pci_bus_id") else None
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self.handle = h
+                        break
+            self.nvml = pynvml
+            self.max_sm = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def sample_nvml(self):
+        n = self.nvml
+        sm = int(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append([str(sm), str(self.max_sm)] + ["Active" if mask & self.BITS[k] else "Not Active" for k in self.NAMES])
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([f.strip() for f in out.split(",")])
+                if self.nvml is not None:
+                    self.sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                          str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.05)
+            self.stop_flag.wait(0.01 if self.nvml is not None else 0.2)
 
     def start(self):
         self.thread.start()
@@ -79,10 +112,9 @@ class ClockSampler:
         self.thread.join(timeout=6)
         sm = [int(s[0]) for s in self.samples if s[0].isdigit()]
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i] == "Active"})
+        reasons = sorted({self.NAMES[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i] == "Active"})
         return {"sm_mhz": int(statistics.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.samples)}
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def build_problem(seed, device=None):
@@ -257,6 +289,7 @@ def main():
         loss = engine.step(dev_batches[i % NUM_BATCHES])
     e1.record()
     sync_all()
+    clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(e0.elapsed_time(e1))
     M.set_profiler(None)
     calls_per_step = (M.ABI_CALLS - calls0) / args.steps
@@ -342,7 +375,6 @@ def main():
     assert len(e2e_losses) == args.steps
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * GRAPHS_PER_GPU * args.steps / (ms_e2e * 1e-3)
-    clocks = sampler.stop() if rank == 0 else None       # sampled from the warm-up through both timed regions
 
     # ---------------- device-resident dataset feed: the packed store lives in HBM, a step's batch is
     # made by the device collate kernels from shuffled graph ids (no per-step H2D of graph data)
