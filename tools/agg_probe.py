@@ -66,4 +66,5 @@ timed("aggregate_fwd [Pdst|Psrc] cold", lambda: _lib.call("gnn_pna_aggregate_fwd
 timed("aggregate_src_fwd cold", lambda: _lib.call("gnn_pna_aggregate_src_fwd", Ps, tab, g.rowptr, g.col_src, g.col_code, n, T, F, A, st()), cold)
 timed("aggregate_src_fwd step-like", lambda: _lib.call("gnn_pna_aggregate_src_fwd", Ps, tab, g.rowptr, g.col_src, g.col_code, n, T, F, A, st()), steplike)
 timed("aggregate_src_bwd cold", lambda: _lib.call("gnn_pna_aggregate_src_bwd", gA, Ps, tab, A, g.rowptr, g.col_src, g.col_code, n, T, F, dPs, dq, dtab, zws, nb, st()), cold)
+timed("aggregate_src_bwd atomic scatter (default) cold", lambda: _lib.call("gnn_pna_aggregate_src_bwd", gA, Ps, tab, A, g.rowptr, g.col_src, g.col_code, n, T, F, dPs, None, dtab, zws, nb, st()), cold)
 timed("slot_sum_by_source cold", lambda: _lib.call("gnn_slot_sum_by_source", dq, g.srcptr, g.src_slot, n, C, dPs, C, st()), cold)
