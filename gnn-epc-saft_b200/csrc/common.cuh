@@ -14,7 +14,7 @@ static inline int gnn_launch_status() {
 
 static inline cudaStream_t gnn_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// number of SMs of the current device (cached per process; 148 on B200)
+// number of SMs of the current device (cached per device ordinal; 148 on B200)
 int gnn_sm_count();
 
 static inline int64_t gnn_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -7,7 +7,7 @@
 // ------------------------------------------------------------------ AtomEncoder forward
 __global__ void atom_embed_fwd_kernel(const int64_t* __restrict__ x, int64_t n, const float* __restrict__ tables,
                                       const int* __restrict__ row_off, int total_rows, int H,
-                                      float* __restrict__ out) {
+                                      float* __restrict__ out, int* err_flag) {
     const int H4 = H >> 2;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * H4) return;
@@ -19,6 +19,7 @@ __global__ void atom_embed_fwd_kernel(const int64_t* __restrict__ x, int64_t n, 
         int lo = __ldg(row_off + k);
         int hi = (k + 1 < GNN_NUM_ATOM_FEATS) ? __ldg(row_off + k + 1) : total_rows;
         int64_t v = __ldg(x + i * GNN_NUM_ATOM_FEATS + k);
+        if ((v < 0 || v >= hi - lo) && err_flag != nullptr && c == 0) atomicOr(err_flag, GNN_INPUT_ERR_ATOM_FEATURE);   // torch would raise IndexError
         int row = lo + (int)(v < 0 ? 0 : (v >= hi - lo ? hi - lo - 1 : v));
         float4 e = ldg4(tables + (int64_t)row * H + c);
         acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
@@ -27,12 +28,12 @@ __global__ void atom_embed_fwd_kernel(const int64_t* __restrict__ x, int64_t n, 
 }
 
 extern "C" int gnn_atom_embed_fwd(const int64_t* x, int64_t n, const float* tables, const int32_t* row_off,
-                                  int32_t total_rows, int hidden, float* out, void* stream) {
+                                  int32_t total_rows, int hidden, float* out, int32_t* err_flag, void* stream) {
     if (n < 0 || hidden < 4 || (hidden & 3)) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
     int64_t work = n * (hidden >> 2);
     atom_embed_fwd_kernel<<<(unsigned)gnn_ceil_div(work, 256), 256, 0, gnn_stream(stream)>>>(x, n, tables, row_off,
-                                                                                             total_rows, hidden, out);
+                                                                                             total_rows, hidden, out, err_flag);
     return gnn_launch_status();
 }
 

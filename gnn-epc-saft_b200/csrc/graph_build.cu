@@ -4,17 +4,16 @@
 // (reference gnnepcsaft/train/models.py:118-121,133; train/train.py:74-79).
 #include "common.cuh"
 
-static int g_sm_count = 0;
+// SM count of the CURRENT device, cached per device ordinal (a process may drive several GPUs)
 int gnn_sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_sm_count = n;
-        else
-            g_sm_count = 148;
+    static int cache[64] = {0};
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cache[dev] = n;
+        else cache[dev] = 148;
     }
-    return g_sm_count;
+    return cache[dev];
 }
 
 extern "C" const char* gnn_error_string(int code) {
@@ -148,7 +147,7 @@ __global__ void csr_count_kernel(const int64_t* __restrict__ edge_index, int64_t
     if (i >= e) return;
     int64_t s = edge_index[i], d = edge_index[e + i];
     if (s < 0 || s >= n || d < 0 || d >= n) {
-        if (err) atomicExch(err, 1);
+        if (err) atomicOr(err, GNN_INPUT_ERR_EDGE_INDEX);
         return;
     }
     atomicAdd(&rowptr[d], 1);
@@ -203,7 +202,7 @@ __global__ void csr_finalize_kernel(const int64_t* __restrict__ edge_index,
         int64_t a0 = edge_attr[3 * (int64_t)eid], a1 = edge_attr[3 * (int64_t)eid + 1],
                 a2 = edge_attr[3 * (int64_t)eid + 2];
         if (a0 < 0 || a0 >= 5 || a1 < 0 || a1 >= 6 || a2 < 0 || a2 >= 2) {
-            if (err) atomicExch(err, 2);
+            if (err) atomicOr(err, GNN_INPUT_ERR_BOND_FEATURE);
             a0 = a1 = a2 = 0;
         }
         code = (int)(a0 * 12 + a1 * 2 + a2);
@@ -261,10 +260,16 @@ extern "C" int gnn_build_csr(const int64_t* edge_index, const int64_t* edge_attr
 
 // ------------------------------------------------------------------ graph_ptr from batch
 __global__ void graph_count_kernel(const int64_t* __restrict__ batch, int64_t n, int64_t b,
-                                   int* node_graph, int* graph_ptr) {
+                                   int* node_graph, int* graph_ptr, int* err_flag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int64_t g = batch[i];
+    // the reference's scatter-based global_add_pool raises on an out-of-range id and accepts any order; this path
+    // needs the sorted vector PyG's Batch produces: both violations are reported through err_flag
+    if (err_flag != nullptr) {
+        if (g < 0 || g >= b) atomicOr(err_flag, GNN_INPUT_ERR_BATCH_RANGE);
+        else if (i > 0 && batch[i - 1] > g) atomicOr(err_flag, GNN_INPUT_ERR_BATCH_UNSORTED);
+    }
     if (g < 0) g = 0;
     if (g >= b) g = b - 1;
     node_graph[i] = (int)g;
@@ -283,16 +288,26 @@ __global__ void graph_ptr_empty_kernel(int* graph_ptr, int64_t b) {
     if (i <= b) graph_ptr[i] = 0;
 }
 
-extern "C" int64_t gnn_graph_ptr_workspace_bytes(int64_t) { return 256; }
 extern "C" int gnn_graph_ptr_from_batch(const int64_t* batch, int64_t n, int64_t b, int32_t* node_graph,
-                                        int32_t* graph_ptr, void*, int64_t, void* stream) {
+                                        int32_t* graph_ptr, int32_t* err_flag, void* stream) {
     if (n < 0 || b < 1 || n >= (1ll << 31)) return GNN_ERR_BAD_ARG;
     cudaStream_t st = gnn_stream(stream);
     if (n == 0) {
         graph_ptr_empty_kernel<<<(unsigned)gnn_ceil_div(b + 1, 256), 256, 0, st>>>(graph_ptr, b);
         return gnn_launch_status();
     }
-    graph_count_kernel<<<(unsigned)gnn_ceil_div(n, 256), 256, 0, st>>>(batch, n, b, node_graph, graph_ptr);
+    graph_count_kernel<<<(unsigned)gnn_ceil_div(n, 256), 256, 0, st>>>(batch, n, b, node_graph, graph_ptr, err_flag);
+    return gnn_launch_status();
+}
+
+// single molecule (data.batch is None): graph_ptr = [0, n]
+__global__ void graph_ptr_single_kernel(int* graph_ptr, int n) {
+    graph_ptr[0] = 0;
+    graph_ptr[1] = n;
+}
+extern "C" int gnn_graph_ptr_single(int64_t n, int32_t* graph_ptr, void* stream) {
+    if (n < 0 || n >= (1ll << 31)) return GNN_ERR_BAD_ARG;
+    graph_ptr_single_kernel<<<1, 1, 0, gnn_stream(stream)>>>(graph_ptr, (int)n);
     return gnn_launch_status();
 }
 

@@ -15,6 +15,18 @@ from typing import Iterable, Iterator
 import torch
 
 
+def _apply_to_tensors(batch, fn):
+    """Map `fn` over the tensors of a batch object: PyG `Data.apply` (public), this package's containers (`_apply`),
+    or a plain dict."""
+    if isinstance(batch, dict):
+        return {k: fn(v) if isinstance(v, torch.Tensor) else v for k, v in batch.items()}
+    if hasattr(batch, "_apply"):
+        return batch._apply(fn)
+    if hasattr(batch, "apply"):
+        return batch.apply(fn)
+    raise TypeError(f"DevicePrefetcher: cannot map over the tensors of {type(batch).__name__}")
+
+
 class DevicePrefetcher:
     """Iterate device batches; the copy of batch i+1.. runs while batch i is being consumed."""
 
@@ -41,7 +53,7 @@ class DevicePrefetcher:
             return t.to(self.device, non_blocking=True)
 
         with torch.cuda.stream(self.copy_stream):
-            dev_batch = host._apply(to_dev)
+            dev_batch = _apply_to_tensors(host, to_dev)
             done = torch.cuda.Event()
             done.record(self.copy_stream)
         self.queue.append((dev_batch, done))
@@ -55,6 +67,6 @@ class DevicePrefetcher:
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(done)
             # the tensors were allocated on the copy stream: tell the caching allocator they are used on `cur`
-            dev_batch._apply(lambda t: (t.record_stream(cur), t)[1])
+            _apply_to_tensors(dev_batch, lambda t: (t.record_stream(cur), t)[1])
             self._enqueue()
             yield dev_batch

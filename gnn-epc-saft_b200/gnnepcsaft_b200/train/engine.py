@@ -15,6 +15,7 @@ No autograd graph is built on this path.
 
 from __future__ import annotations
 
+import math
 from typing import Optional
 
 import torch
@@ -63,9 +64,14 @@ class TrainEngine:
     def step(self, batch) -> torch.Tensor:
         """One optimisation step on `batch` (needs `.para`); returns the (rank-mean) loss as a
         device scalar without synchronising."""
+        with models._device_guard(self.grad.device):
+            return self._step(batch)
+
+    def _step(self, batch) -> torch.Tensor:
         net = self.net
         net.train()
         arena = net.arena()
+        models.check_input_errors(block=False)
         batchvec = getattr(batch, "batch", None)
         num_graphs = batch.num_graphs if batchvec is not None else 1
         out, sv = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs), save=True)
@@ -96,6 +102,7 @@ class TrainEngine:
         was_training = net.training
         net.eval()
         try:
+          with models._device_guard(self.grad.device):
             batchvec = getattr(batch, "batch", None)
             num_graphs = batch.num_graphs if batchvec is not None else 1
             out, _ = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs),
@@ -113,6 +120,60 @@ class TrainEngine:
                         "exp_avg": self.exp_avg[sl].view(p.shape).clone(),
                         "exp_avg_sq": self.exp_avg_sq[sl].view(p.shape).clone(),
                         "max_exp_avg_sq": self.max_exp_avg_sq[sl].view(p.shape).clone()}
-        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.wd, "amsgrad": True,
+        t = int(self.step_count.item())
+        cur_lr = 0.5 * self.lr * (1.0 + math.cos(math.pi * (t % self.t0) / self.t0))     # after t scheduler steps
+        group = {"lr": cur_lr, "initial_lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.wd, "amsgrad": True,
                  "params": list(range(len(state)))}
         return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, state_dict):
+        """Inverse of `optimizer_state_dict`: restores the Adam moments, the amsgrad maxima and the step counter
+        (which also fixes the phase of the cosine-restart schedule), so a resumed run continues where it stopped
+        (reference train/utils.py:220-233, train.py:158-184)."""
+        state = state_dict["state"]
+        params = self.net._param_list()
+        if len(state) != len(params):
+            raise ValueError(f"optimizer state has {len(state)} entries, the model has {len(params)} parameters")
+        step = 0
+        with torch.no_grad():
+            for i, (p, off) in enumerate(zip(params, self.net._arena_offsets)):
+                st = state[i] if i in state else state[str(i)]
+                sl = slice(off, off + p.numel())
+                self.exp_avg[sl].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[sl].copy_(st["exp_avg_sq"].reshape(-1))
+                self.max_exp_avg_sq[sl].copy_(st["max_exp_avg_sq"].reshape(-1))
+                step = int(st["step"])
+            self.step_count.fill_(step)
+        groups = state_dict.get("param_groups") or [{}]
+        self.wd = float(groups[0].get("weight_decay", self.wd))
+        self.lr = float(groups[0].get("initial_lr", self.lr))
+
+    def scheduler_state_dict(self):
+        """`CosineAnnealingWarmRestarts(T_0 = warmup_steps)` state after `step_count` per-step calls."""
+        t = int(self.step_count.item())
+        return {"T_0": self.t0, "T_i": self.t0, "T_mult": 1, "eta_min": 0, "T_cur": t % self.t0, "last_epoch": t,
+                "base_lrs": [self.lr]}
+
+    def save_checkpoint(self, path: str, step=None):
+        """`.pth` (reference train/utils.py:109-119 layout) or Lightning-style `.ckpt`, chosen by the extension."""
+        from . import utils
+        step = int(self.step_count.item()) if step is None else step
+        if str(path).endswith(".ckpt"):
+            utils.save_lightning_checkpoint(self.net, path, engine=self, global_step=step)
+        else:
+            utils.savemodel(self.net, self, None, path, step)
+
+    def load_checkpoint(self, path: str, load_optimizer: bool = True):
+        """Reads either layout back (model weights, and optimizer / schedule state unless `load_optimizer=False`,
+        the reference's `config.change_opt`, train.py:170-175)."""
+        ckpt = torch.load(path, map_location="cpu", weights_only=False)
+        if "model_state_dict" in ckpt:
+            self.net.load_state_dict(ckpt["model_state_dict"])
+            opt = ckpt.get("optimizer_state_dict")
+        else:
+            sd = {k[len("model."):] if k.startswith("model.") else k: v for k, v in ckpt["state_dict"].items()}
+            self.net.load_state_dict(sd)
+            opt = (ckpt.get("optimizer_states") or [None])[0]
+        if load_optimizer and opt is not None:
+            self.load_optimizer_state_dict(opt)
+        return ckpt.get("step", ckpt.get("global_step"))

@@ -10,6 +10,8 @@ under the reference's names; the arithmetic runs in the CUDA library behind the 
 
 from __future__ import annotations
 
+import collections
+import contextlib
 import dataclasses
 import math
 import os
@@ -238,6 +240,38 @@ def _pack_ws(device):
     return _WS.get("pack", PACK_WS_BYTES, device)
 
 
+_INPUT_ERRORS = ((1, IndexError, "edge_index out of range [0, num_nodes)"),
+                 (2, IndexError, "edge_attr (bond feature) out of range"),
+                 (4, IndexError, "batch id out of range [0, num_graphs)"),
+                 (8, ValueError, "data.batch is not sorted (PyG Batch vectors are; sort the nodes by graph)"),
+                 (16, IndexError, "x (atom feature) out of range"))
+# GNN_B200_CHECK=1: read the device-side input error word right after every forward (synchronises).  Default: the
+# word of a forward is read, without blocking, by a later forward / step once its kernels have finished, and by
+# every call that synchronises anyway (`check_input_errors()`, TrainEngine.loss_value, smoke tests).
+CHECK_INPUTS_EAGERLY = os.environ.get("GNN_B200_CHECK", "0") == "1"
+_PENDING_ERR = collections.deque()
+
+
+def _raise_input_error(code: int):
+    for bit, exc, msg in _INPUT_ERRORS:
+        if code & bit:
+            raise exc(f"gnnepcsaft_b200: {msg} (the reference's torch indexing raises on the same input)")
+
+
+def check_input_errors(block: bool = True):
+    """Raise IndexError / ValueError for malformed inputs of earlier forwards (the kernels clamp and flag instead of
+    faulting).  block=False only looks at forwards whose kernels have already completed."""
+    while _PENDING_ERR:
+        err, ev = _PENDING_ERR[0]
+        if not block and not ev.query():
+            return
+        _PENDING_ERR.popleft()
+        code = int(err.item())
+        if code:
+            _PENDING_ERR.clear()
+            _raise_input_error(code)
+
+
 class GraphStructure:
     """Device-side CSR / slot lists of one batch (gnn_build_csr, gnn_graph_ptr_from_batch)."""
 
@@ -261,16 +295,31 @@ class GraphStructure:
         self.graph_ptr = torch.empty(self.b + 1, **i32)
         if batch is None:
             self.node_graph = None
-            self.graph_ptr.copy_(torch.tensor([0, n], dtype=torch.int32), non_blocking=False)
+            _c("gnn_graph_ptr_single", n, self.graph_ptr)
         else:
             self.node_graph = torch.empty(max(n, 1), **i32)
-            _c("gnn_graph_ptr_from_batch", batch, n, self.b, self.node_graph, self.graph_ptr, None, 0)
+            _c("gnn_graph_ptr_from_batch", batch, n, self.b, self.node_graph, self.graph_ptr, self.err)
+
+    def defer_check(self):
+        """Queue this batch's error word (call after the last kernel that writes it was enqueued)."""
+        if self.err.is_cuda and torch.cuda.is_current_stream_capturing():
+            return
+        if CHECK_INPUTS_EAGERLY or not self.err.is_cuda:
+            _raise_input_error(int(self.err.item()))
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        _PENDING_ERR.append((self.err, ev))
 
     def check(self):
         """Synchronising validity check (the reference would raise IndexError inside torch)."""
-        code = int(self.err.item())
-        if code:
-            raise IndexError("edge_index / edge_attr out of range" if code == 1 else "bond feature out of range")
+        _raise_input_error(int(self.err.item()))
+
+
+def _device_guard(dev: torch.device):
+    """Make `dev` the current CUDA device for the enclosed launches (streams, scratch buffers and the SM count all
+    follow the current device); a no-op for the host tensors of the CPU-side host-logic tests."""
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -289,7 +338,8 @@ class PNAPCSAFT(nn.Module):
         if hidden_dim % 4 != 0:
             raise ValueError("hidden_dim must be divisible by 4 (towers=2, head uses H//2 and H//4)")
         if hidden_dim % 8 != 0:
-            raise ValueError("gnnepcsaft_b200 kernels use 128-bit accesses: hidden_dim must be a multiple of 8")
+            raise ValueError("gnnepcsaft_b200 kernels use 128-bit accesses on per-tower rows: hidden_dim must be a "
+                             "multiple of 8 (the reference accepts multiples of 4; its configs use 64 / 128 / 256)")
         self.hidden_dim = hidden_dim
         self.pna_params = pna_params
         self.mlp_params = mlp_params
@@ -393,20 +443,31 @@ class PNAPCSAFT(nn.Module):
         """Forward pass of the model (reference models.py:105-135)."""
         x, edge_index, edge_attr, batch = data.x, data.edge_index, data.edge_attr, getattr(data, "batch", None)
         _require_cuda(x, "data.x")
-        arena = self.arena()
-        _require_cuda(arena, "the model")
-        if batch is None:
-            num_graphs = 1
-        else:
-            num_graphs = getattr(data, "num_graphs", None)
-            if num_graphs is None:
-                ptr = getattr(data, "ptr", None)
-                num_graphs = int(ptr.numel()) - 1 if ptr is not None else int(batch.max()) + 1
-        params = self._param_list()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-            return _PNAFunction.apply(self, x, edge_index, edge_attr, batch, int(num_graphs), *params)
-        out, _ = _forward_impl(self, x, edge_index, edge_attr, batch, int(num_graphs), save=False)
-        return out
+        # every launch of this call goes to the current stream OF THE DATA'S DEVICE, whatever device is current
+        with _device_guard(x.device):
+            arena = self.arena()
+            _require_cuda(arena, "the model")
+            _same_device(x.device, model=arena, edge_index=edge_index, edge_attr=edge_attr, batch=batch)
+            check_input_errors(block=False)
+            if batch is None:
+                num_graphs = 1
+            else:
+                num_graphs = getattr(data, "num_graphs", None)
+                if num_graphs is None:
+                    ptr = getattr(data, "ptr", None)
+                    num_graphs = int(ptr.numel()) - 1 if ptr is not None else int(batch.max()) + 1
+            params = self._param_list()
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                return _PNAFunction.apply(self, x, edge_index, edge_attr, batch, int(num_graphs), *params)
+            out, _ = _forward_impl(self, x, edge_index, edge_attr, batch, int(num_graphs), save=False)
+            return out
+
+
+def _same_device(dev, **tensors):
+    for name, t in tensors.items():
+        if t is not None and t.device != dev:
+            raise RuntimeError(f"gnnepcsaft_b200: {name} is on {t.device} but data.x is on {dev}; the model and every "
+                               "tensor of the batch must live on the same CUDA device")
 
 
 def _check_inputs(x, edge_index, edge_attr, batch):
@@ -435,7 +496,12 @@ def _bn_forward(y, bn: nn.BatchNorm1d, training: bool, skip, relu: bool):
     use_batch = training or bn.running_mean is None
     nbytes = _lib.query("gnn_bn_workspace_bytes", rows, ch)
     ws = _WS.get("bn", nbytes, dev)
-    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if use_batch and rows == 1:
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(y.shape)}")
+    if bn.momentum is None:     # torch: cumulative moving average, factor 1 / num_batches_tracked (after the increment)
+        momentum = 1.0 / (int(bn.num_batches_tracked) + 1) if (use_batch and bn.num_batches_tracked is not None) else 0.0
+    else:
+        momentum = bn.momentum
     _c("gnn_bn_stats", y, rows, ch, 1 if use_batch else 0, float(bn.eps), float(momentum), bn.running_mean,
        bn.running_var, bn.num_batches_tracked if use_batch else None, stats, ws, ws.numel())
     out = torch.empty_like(y)
@@ -492,7 +558,9 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
     atom_tab = model.node_embed.atom_embedding_list[0].weight
     total_rows = sum(ATOM_FEATURE_DIMS)
     x = torch.empty(n, H, **f32)
-    _c("gnn_atom_embed_fwd", x_idx, n, atom_tab, row_off, total_rows, H, x)
+    _c("gnn_atom_embed_fwd", x_idx, n, atom_tab, row_off, total_rows, H, x, g.err)
+    if graph is None:
+        g.defer_check()
 
     # bond-code tables of all layers in one launch
     conv0 = model.convs[0] if L > 0 else None
@@ -832,10 +900,14 @@ class _PNAFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         model, sv = ctx.model, ctx.sv
+        if sv is None:
+            raise RuntimeError("gnnepcsaft_b200: backward was already run for this forward (the saved kernel state "
+                               "is freed after the first backward; retain_graph is not supported)")
         if not model._arena_valid():
             raise RuntimeError("gnnepcsaft_b200: parameters were moved between forward and backward")
-        grad_arena = torch.zeros_like(model._arena)
-        _backward_impl(model, sv, dout, grad_arena)
+        with _device_guard(dout.device):
+            grad_arena = torch.zeros_like(model._arena)
+            _backward_impl(model, sv, dout, grad_arena)
         grads = []
         for p, off in zip(model._param_list(), model._arena_offsets):
             grads.append(grad_arena[off:off + p.numel()].view(p.shape) if p.requires_grad else None)
@@ -848,17 +920,44 @@ def mape(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     return torch.sum((pred - target).abs() / target.abs().clamp(min=1.17e-06)) / target.numel()
 
 
-class PNApcsaftL(nn.Module):
-    """The reference's Lightning wrapper (models.py:138-202) without the Lightning dependency:
-    holds `self.model` (so checkpoint keys carry the `model.` prefix), builds the same
-    optimizer / scheduler, and computes the same training loss."""
+try:  # the reference's wrapper is a LightningModule (models.py:138); subclass it whenever Lightning is importable
+    import lightning as _L  # type: ignore
+    _LightningBase = _L.LightningModule
+except ImportError:  # pragma: no cover - depends on the environment
+    try:
+        import pytorch_lightning as _L  # type: ignore
+        _LightningBase = _L.LightningModule
+    except ImportError:
+        _L = None
+
+        class _LightningBase(nn.Module):
+            """Lightning is not installed: same attribute surface (`log`, `log_dict`, hooks the reference's
+            train.py never overrides) on a plain module, so `TrainEngine` / a hand-written loop can drive it."""
+
+            def log(self, *args, **kwargs):
+                return None
+
+            def log_dict(self, *args, **kwargs):
+                return None
+
+
+class PNApcsaftL(_LightningBase):
+    """Graph neural network to predict ePCSAFT parameters with pytorch lightning (reference models.py:138-251).
+
+    Holds `self.model = PNAPCSAFT(...)` (checkpoint keys carry the `model.` prefix), builds the same optimizer /
+    per-step cosine-restart schedule and computes the same training loss, so `L.Trainer.fit(model, loader)` of
+    reference train.py:129-201 drives the CUDA kernels through autograd.  `validation_step` / `test_step` hand the
+    predicted parameters to `property_metrics` - the ePC-SAFT density / vapour-pressure evaluation (feos, reference
+    models.py:204-248) is CPU thermodynamics outside this path; plug the reference's functions in there."""
 
     def __init__(self, pna_params: PnaconvsParams, mlp_params: ReadoutMLPParams, config):
         super().__init__()
         self.config = config
         self.model = PNAPCSAFT(config.hidden_dim, pna_params=pna_params, mlp_params=mlp_params)
+        self.property_metrics = None        # optional callable(pred_para float64 cpu [P], graphs) -> dict of floats
 
     def forward(self, data):
+        """Forward pass of the model"""
         return self.model(data)
 
     def configure_optimizers(self):
@@ -876,4 +975,18 @@ class PNApcsaftL(nn.Module):
     def training_step(self, graphs, batch_idx=0):
         target = graphs.para.view(-1, self.config.num_para)
         pred = self(graphs)
-        return mape(pred, target)
+        loss_mape = mape(pred, target)
+        self.log("train_mape", loss_mape, on_step=True, batch_size=target.shape[0], sync_dist=True)
+        return loss_mape
+
+    def validation_step(self, graphs, batch_idx=0):
+        pred_para = self(graphs).squeeze().to(torch.float64).cpu()
+        metrics = {}
+        if self.property_metrics is not None:
+            metrics = dict(self.property_metrics(pred_para, graphs))
+        if metrics:
+            self.log_dict(metrics, on_step=True, batch_size=1, sync_dist=True)
+        return metrics
+
+    def test_step(self, graphs, batch_idx=0):
+        return self.validation_step(graphs, batch_idx)

@@ -29,6 +29,14 @@ extern "C" {
 #define GNN_ERR_UNSUPPORTED (-3)
 #define GNN_ERR_WORKSPACE (-4)
 
+/* bits of the device-side input error word (`err_flag` arguments): malformed inputs on which the reference's
+ * torch indexing would raise IndexError are reported here instead of being silently clamped */
+#define GNN_INPUT_ERR_EDGE_INDEX 1     /* edge_index outside [0, N) */
+#define GNN_INPUT_ERR_BOND_FEATURE 2   /* edge_attr outside the OGB bond feature ranges */
+#define GNN_INPUT_ERR_BATCH_RANGE 4    /* batch id outside [0, B) */
+#define GNN_INPUT_ERR_BATCH_UNSORTED 8 /* batch vector not sorted (PyG Batch always is) */
+#define GNN_INPUT_ERR_ATOM_FEATURE 16  /* x outside the OGB atom feature ranges */
+
 #define GNN_NUM_ATOM_FEATS 9
 #define GNN_NUM_BOND_FEATS 3
 #define GNN_NUM_BOND_CODES 60 /* 5*6*2, code = a0*12 + a1*2 + a2; self-loop = code 0 */
@@ -48,7 +56,7 @@ int gnn_device_info(int32_t* out_host);
  *   srcptr   int32 [N+1]   src_slot int32 [E']      E' = E + (self_loops ? N : 0)
  * col_eid[s] is the index into the PyG-order edge list (loops are E+i).
  * err_flag (int32[1], may be NULL) is set non-zero if an index or bond feature is out of
- * range (the reference would raise an IndexError). */
+ * range (the reference would raise an IndexError): GNN_INPUT_ERR_* bits, cleared on entry. */
 int64_t gnn_build_csr_workspace_bytes(int64_t num_nodes, int64_t num_edges);
 int gnn_build_csr(const int64_t* edge_index, const int64_t* edge_attr, int64_t num_nodes,
                   int64_t num_edges, int self_loops, int32_t* rowptr, int32_t* col_src,
@@ -56,11 +64,14 @@ int gnn_build_csr(const int64_t* edge_index, const int64_t* edge_attr, int64_t n
                   int32_t* err_flag, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* batch vector (int64, sorted, PyG `Batch.batch`) -> int32 node->graph map and graph_ptr
- * [B+1].  Replaces the index handling of global_add_pool (models.py:133). */
-int64_t gnn_graph_ptr_workspace_bytes(int64_t num_graphs);
+ * [B+1].  Replaces the index handling of global_add_pool (models.py:133).  err_flag (may be
+ * NULL) receives GNN_INPUT_ERR_BATCH_RANGE / _UNSORTED bits (OR-ed in, not cleared). */
 int gnn_graph_ptr_from_batch(const int64_t* batch, int64_t num_nodes, int64_t num_graphs,
-                             int32_t* node_graph, int32_t* graph_ptr, void* workspace,
-                             int64_t workspace_bytes, void* stream);
+                             int32_t* node_graph, int32_t* graph_ptr, int32_t* err_flag,
+                             void* stream);
+
+/* single molecule (`data.batch is None`, reference models.py:116 / PyG global_add_pool): graph_ptr = [0, N] */
+int gnn_graph_ptr_single(int64_t num_nodes, int32_t* graph_ptr, void* stream);
 
 /* Device collate. Replaces PyG DataLoader/Collater/Batch.from_data_list (train.py:74-79)
  * over an InMemoryDataset-format packed store (graphdataset.py:48,137): concatenated
@@ -85,7 +96,7 @@ int gnn_collate_gather(const int64_t* ids, int64_t num_ids, const int64_t* node_
  * `tables` is the 9 embedding weights stacked along rows (174 rows), row_off int32[9]. */
 int gnn_atom_embed_fwd(const int64_t* x, int64_t num_nodes, const float* tables,
                        const int32_t* row_off, int32_t total_rows, int hidden, float* out,
-                       void* stream);
+                       int32_t* err_flag, void* stream);
 /* d tables[row] += sum_i dout[i,:] (tables gradient must be zeroed by the caller) */
 int gnn_atom_embed_bwd(const int64_t* x, int64_t num_nodes, const float* dout,
                        const int32_t* row_off, int32_t total_rows, int hidden, float* dtables,

@@ -71,15 +71,23 @@ def gnn_build_csr(edge_index, edge_attr, n, e, self_loops, rowptr, col_src, col_
         err_flag.zero_()
 
 
-def gnn_graph_ptr_workspace_bytes(b):
-    return 256
-
-
-def gnn_graph_ptr_from_batch(batch, n, b, node_graph, graph_ptr, workspace, workspace_bytes, stream=None):
+def gnn_graph_ptr_from_batch(batch, n, b, node_graph, graph_ptr, err_flag=None, stream=None):
+    if err_flag is not None and n > 0:
+        bv = batch[:n]
+        if bool(((bv < 0) | (bv >= b)).any()):
+            err_flag |= 4
+        elif n > 1 and bool((bv[1:] < bv[:-1]).any()):
+            err_flag |= 8
+    batch = batch[:n].clamp(0, b - 1)
     counts = torch.bincount(batch[:n], minlength=b)
     graph_ptr[0] = 0
     graph_ptr[1: b + 1] = counts.cumsum(0).to(torch.int32)
     node_graph[:n] = batch[:n].to(torch.int32)
+
+
+def gnn_graph_ptr_single(n, graph_ptr, stream=None):
+    graph_ptr[0] = 0
+    graph_ptr[1] = n
 
 
 def gnn_collate_workspace_bytes(nb):
@@ -110,11 +118,15 @@ def gnn_collate_gather(ids, nb, node_slices, edge_slices, sx, sei, store_e, sea,
 
 
 # ------------------------------------------------------------------ encoders
-def gnn_atom_embed_fwd(x, n, tables, row_off, total_rows, hidden, out, stream=None):
+def gnn_atom_embed_fwd(x, n, tables, row_off, total_rows, hidden, out, err_flag=None, stream=None):
     tab = _mat(tables, total_rows, hidden, hidden)
     acc = torch.zeros(n, hidden, dtype=tab.dtype)
     for k in range(9):
-        acc = acc + tab[row_off[k].long() + x[:n, k]]
+        hi = (int(row_off[k + 1]) if k + 1 < 9 else total_rows) - int(row_off[k])
+        v = x[:n, k]
+        if err_flag is not None and bool(((v < 0) | (v >= hi)).any()):
+            err_flag |= 16
+        acc = acc + tab[row_off[k].long() + v.clamp(0, hi - 1)]
     out[:n] = acc
 
 

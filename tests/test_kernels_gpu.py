@@ -96,7 +96,7 @@ def test_graph_ptr_with_empty_graphs():
     batch = torch.tensor([0, 0, 2, 2, 2, 5])
     n, b = 6, 8
     ng, gp = torch.zeros(n, dtype=torch.int32), torch.zeros(b + 1, dtype=torch.int32)
-    cpu, gpu = run_both("gnn_graph_ptr_from_batch", batch, n, b, ng, gp, None, 0)
+    cpu, gpu = run_both("gnn_graph_ptr_from_batch", batch, n, b, ng, gp, None)
     assert torch.equal(gpu[3].cpu(), cpu[3]) and torch.equal(gpu[4].cpu(), cpu[4])
     assert cpu[4].tolist() == [0, 2, 2, 5, 5, 5, 6, 6, 6]
 
@@ -123,7 +123,7 @@ def test_atom_embed_fwd_bwd():
     tables = torch.randn(rows, H)
     off = torch.tensor([0, 119, 124, 136, 148, 158, 164, 170, 172], dtype=torch.int32)
     out = torch.zeros(n, H)
-    cpu, gpu = run_both("gnn_atom_embed_fwd", x, n, tables, off, rows, H, out)
+    cpu, gpu = run_both("gnn_atom_embed_fwd", x, n, tables, off, rows, H, out, None)
     close(gpu[-1], cpu[-1], 1e-6, "atom embedding")
     dout = torch.randn(n, H)
     dt = torch.zeros(rows, H)
