@@ -9,23 +9,19 @@
 // no atomics are needed and the summation order is deterministic.  HBM-bound: per node it
 // reads one gathered row per in-edge (L2-resident re-reads) and writes 4*C floats.
 #include "common.cuh"
+#include "pna_agg.cuh"
 
 #include <float.h>
-#include <stdlib.h>
 
 constexpr int AGG_WARPS = 8;
 constexpr int AGG_THREADS = AGG_WARPS * 32;
-
-struct Stat4 {
-    float4 mean, m2, mn, mx;
-};
 
 __device__ __forceinline__ void welford_update(float& mean, float& m2, float q, float inv_k) {
     float d = q - mean;
     mean = fmaf(d, inv_k, mean);
     m2 = fmaf(d, q - mean, m2);
 }
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return pna_add4(a, b); }
 
 // std of DegreeScalerAggregation's StdAggregation: sqrt(clamp(var,1e-5)) masked to 0 at the floor
 __device__ __forceinline__ float pna_std(float var) {
@@ -45,188 +41,18 @@ __device__ __forceinline__ void store_aggregates(float* __restrict__ A, int64_t 
 }
 
 // ------------------------------------------------------------------ forward, factorised message
-// One warp walks the CSR slots of NODES_PER_WARP consecutive destination nodes as ONE edge stream:
-//   * rowptr / col_src / col_code of the whole chunk are fetched with coalesced lane-parallel loads
-//     and distributed by shuffles (no dependent scalar index loads per edge);
-//   * gathers are issued four edges ahead of their use (memory-level parallelism), Pdst of the next
-//     node is prefetched while the current node accumulates;
-//   * statistics are single-pass on data shifted by the segment's first message q0:
-//     s1 = sum(q-q0), s2 = sum((q-q0)^2) -> mean = q0 + s1/n, var = s2/n - (s1/n)^2  (the shift removes
-//     the cancellation of the textbook E[q^2]-E[q]^2 form; no per-edge division as in Welford);
-//   * results leave through streaming 128-bit stores.
-
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // max rel. error 2^-23, one MUFU op
-    return y;
-}
-__device__ __forceinline__ float pna_std_fast(float var) {
-    return var > 1e-5f ? sqrt_approx(var) : 0.0f;             // == sqrt(clamp(var,1e-5)) masked at the floor
-}
-
-struct SegStat {
-    float4 q0, s1, s2, mn, mx;
-};
-
-__device__ __forceinline__ void seg_first(SegStat& st, float4 q) {
-    st.q0 = q;
-    st.mn = q;
-    st.mx = q;
-    st.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    st.s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-__device__ __forceinline__ void seg_add(SegStat& st, float4 q) {
-    float dx = q.x - st.q0.x, dy = q.y - st.q0.y, dz = q.z - st.q0.z, dw = q.w - st.q0.w;
-    st.s1.x += dx; st.s1.y += dy; st.s1.z += dz; st.s1.w += dw;
-    st.s2.x = fmaf(dx, dx, st.s2.x); st.s2.y = fmaf(dy, dy, st.s2.y);
-    st.s2.z = fmaf(dz, dz, st.s2.z); st.s2.w = fmaf(dw, dw, st.s2.w);
-    st.mn = make_float4(fminf(st.mn.x, q.x), fminf(st.mn.y, q.y), fminf(st.mn.z, q.z), fminf(st.mn.w, q.w));
-    st.mx = make_float4(fmaxf(st.mx.x, q.x), fmaxf(st.mx.y, q.y), fmaxf(st.mx.z, q.z), fmaxf(st.mx.w, q.w));
-}
-__device__ __forceinline__ void seg_finish(const SegStat& st, int cnt, float4 pd, float* __restrict__ A, int64_t node,
-                                           int C, int F, int c) {
-    if (cnt == 0) {
-        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        store_aggregates(A, node, C, F, c, z, z, z, z);
-        return;
-    }
-    const float inv = __frcp_rn((float)cnt);
-    float4 m1 = make_float4(st.s1.x * inv, st.s1.y * inv, st.s1.z * inv, st.s1.w * inv);
-    float4 sd = make_float4(pna_std_fast(fmaf(-m1.x, m1.x, st.s2.x * inv)), pna_std_fast(fmaf(-m1.y, m1.y, st.s2.y * inv)),
-                            pna_std_fast(fmaf(-m1.z, m1.z, st.s2.z * inv)), pna_std_fast(fmaf(-m1.w, m1.w, st.s2.w * inv)));
-    float4 mean = make_float4(st.q0.x + m1.x + pd.x, st.q0.y + m1.y + pd.y, st.q0.z + m1.z + pd.z, st.q0.w + m1.w + pd.w);
-    store_aggregates(A, node, C, F, c, mean, add4(st.mn, pd), add4(st.mx, pd), sd);
-}
-
-// one warp per destination node, NCHUNK x 128 channels; the gather of edge k+1 is in flight while edge k is
-// accumulated (software pipelining), indices come from one lane-parallel load + shuffles, and everything that
-// does not depend on the node (channel -> tower/feature split, column pointers) is hoisted out of the node loop.
-// Measured on B200 (tools/agg_probe.py, ncu): the kernel is bound by instruction issue / the per-node dependent
-// chain rather than by DRAM; variants tried and rejected: 8-node edge streams per warp (register pressure),
-// higher occupancy via register caps (spills), cross-node index prefetch, two nodes per warp, and a streamed
-// variant (contiguous node range per warp, source rows through a 16-row cp.async ring in shared memory 12 rows
-// ahead, indices read 32 at a time): bit-identical output and the same 79-80 us, i.e. the kernel is not bound by
-// latency hiding.  Stores alone (209 MB) take 43 us in the same harness, a torch fill of that size 41 us; in the
-// training step the 105 MB of P written by the projection GEMM are still dirty in L2 and are evicted by this
-// kernel's stores, so DRAM sees ~314 MB of writes per launch.
-// SRC_ONLY: P is [n, C] = source projections only and the aggregates are those of the shift-free q (the destination
-// term is folded into the post GEMM's weights, gnn_pna_fold_fwd) - the kernel then reads half as much.
-template <int NCHUNK, bool SRC_ONLY>
-__global__ void __launch_bounds__(AGG_THREADS, 4)
-pna_aggregate_fwd_kernel(const float* __restrict__ P, const float* __restrict__ tab,
-                         const int* __restrict__ rowptr, const int* __restrict__ col_src,
-                         const uint8_t* __restrict__ col_code, int n, int C, int F, float* __restrict__ A) {
-    const int lane = threadIdx.x & 31;
-    const int warp0 = blockIdx.x * AGG_WARPS + (threadIdx.x >> 5);
-    const int nwarps = gridDim.x * AGG_WARPS;
-    const int ldp = SRC_ONLY ? C : 2 * C, lda = 4 * C, soff = SRC_ONLY ? 0 : C;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cj[NCHUNK], aoff[NCHUNK];
-    bool live[NCHUNK];
-#pragma unroll
-    for (int j = 0; j < NCHUNK; ++j) {
-        cj[j] = j * 128 + lane * 4;
-        live[j] = cj[j] < C;
-        const int t = cj[j] / F;
-        aoff[j] = t * 4 * F + (cj[j] - t * F);            // A[node][t][agg][f]
-    }
-    for (int node = warp0; node < n; node += nwarps) {
-        const int rp = __ldg(rowptr + node + (lane & 1));
-        const int beg = __shfl_sync(GNN_FULL_MASK, rp, 0), end = __shfl_sync(GNN_FULL_MASK, rp, 1);
-        // REDUX result lives in a uniform register: the edge loops below are then provably warp-uniform and the
-        // compiler drops the divergence bookkeeping (BSSY / WARPSYNC) around the shuffles
-        const int cnt = __reduce_max_sync(GNN_FULL_MASK, end - beg);
-        int my_src = 0, my_code = 0;                      // pre-scaled element offsets of the first 32 in-edges
-        if (lane < cnt) {
-            my_src = __ldg(col_src + beg + lane) * ldp + soff;
-            my_code = (int)__ldg(col_code + beg + lane) * C;
-        }
-        float* const arow = A + (size_t)node * lda;
-        const float* const prow = P + (size_t)node * ldp;
-        const int m = min(cnt, 32);
-#pragma unroll
-        for (int j = 0; j < NCHUNK; ++j) {
-            float* const out = arow + aoff[j];
-            if (cnt == 0) {
-                if (live[j]) {
-                    st4_stream(out, zero);
-                    st4_stream(out + F, zero);
-                    st4_stream(out + 2 * F, zero);
-                    st4_stream(out + 3 * F, zero);
-                }
-                continue;
-            }
-            const float* const pbase = P + cj[j];
-            const float* const tbase = tab + cj[j];
-            const float4 pd = (!SRC_ONLY && live[j]) ? ldg4(prow + cj[j]) : zero;
-            int so = __shfl_sync(GNN_FULL_MASK, my_src, 0), co = __shfl_sync(GNN_FULL_MASK, my_code, 0);
-            float4 pn = live[j] ? ldg4(pbase + so) : zero, tn = live[j] ? ldg4(tbase + co) : zero;
-            // edge 0 defines the shift q0
-            float4 q0, s1 = zero, s2 = zero, mn, mx;
-            {
-                const float4 pc = pn, tcur = tn;
-                if (1 < m) {
-                    so = __shfl_sync(GNN_FULL_MASK, my_src, 1);
-                    co = __shfl_sync(GNN_FULL_MASK, my_code, 1);
-                    if (live[j]) {
-                        pn = ldg4(pbase + so);
-                        tn = ldg4(tbase + co);
-                    }
-                }
-                q0 = add4(pc, tcur);
-                mn = q0;
-                mx = q0;
-            }
-            for (int k = 1; k < m; ++k) {
-                const float4 pc = pn, tcur = tn;
-                if (k + 1 < m) {                                           // warp-uniform: prefetch the next edge
-                    so = __shfl_sync(GNN_FULL_MASK, my_src, k + 1);
-                    co = __shfl_sync(GNN_FULL_MASK, my_code, k + 1);
-                    if (live[j]) {
-                        pn = ldg4(pbase + so);
-                        tn = ldg4(tbase + co);
-                    }
-                }
-                const float4 q = add4(pc, tcur);
-                const float dx = q.x - q0.x, dy = q.y - q0.y, dz = q.z - q0.z, dw = q.w - q0.w;
-                s1 = make_float4(s1.x + dx, s1.y + dy, s1.z + dz, s1.w + dw);
-                s2 = make_float4(fmaf(dx, dx, s2.x), fmaf(dy, dy, s2.y), fmaf(dz, dz, s2.z), fmaf(dw, dw, s2.w));
-                mn = make_float4(fminf(mn.x, q.x), fminf(mn.y, q.y), fminf(mn.z, q.z), fminf(mn.w, q.w));
-                mx = make_float4(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z), fmaxf(mx.w, q.w));
-            }
-            for (int s = beg + 32; s < end; ++s) {         // in-degree > 32 (never for molecules)
-                const int so2 = __ldg(col_src + s) * ldp + soff, co2 = (int)__ldg(col_code + s) * C;
-                if (live[j]) {
-                    const float4 q = add4(ldg4(pbase + so2), ldg4(tbase + co2));
-                    const float dx = q.x - q0.x, dy = q.y - q0.y, dz = q.z - q0.z, dw = q.w - q0.w;
-                    s1 = make_float4(s1.x + dx, s1.y + dy, s1.z + dz, s1.w + dw);
-                    s2 = make_float4(fmaf(dx, dx, s2.x), fmaf(dy, dy, s2.y), fmaf(dz, dz, s2.z), fmaf(dw, dw, s2.w));
-                    mn = make_float4(fminf(mn.x, q.x), fminf(mn.y, q.y), fminf(mn.z, q.z), fminf(mn.w, q.w));
-                    mx = make_float4(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z), fmaxf(mx.w, q.w));
-                }
-            }
-            if (live[j]) {
-                const float inv = __frcp_rn((float)cnt);
-                const float4 m1 = make_float4(s1.x * inv, s1.y * inv, s1.z * inv, s1.w * inv);
-                st4_stream(out, make_float4(q0.x + m1.x + pd.x, q0.y + m1.y + pd.y, q0.z + m1.z + pd.z, q0.w + m1.w + pd.w));
-                st4_stream(out + F, add4(mn, pd));
-                st4_stream(out + 2 * F, add4(mx, pd));
-                st4_stream(out + 3 * F, make_float4(pna_std_fast(fmaf(-m1.x, m1.x, s2.x * inv)),
-                                                    pna_std_fast(fmaf(-m1.y, m1.y, s2.y * inv)),
-                                                    pna_std_fast(fmaf(-m1.z, m1.z, s2.z * inv)),
-                                                    pna_std_fast(fmaf(-m1.w, m1.w, s2.w * inv))));
-            }
-        }
-    }
-}
-
-// ---- persistent, software-pipelined variant of the forward kernel.
-// ncu on the kernel above: DRAM 36 % busy, issue slots 41 % busy, 12.5 of 17.8 resident warps per issue waiting on a
-// long scoreboard - the dependent chain rowptr -> col_src/col_code -> gathered rows -> stores costs four exposed
-// memory latencies per node.  Here a warp owns nodes warp, warp + W, ... of a persistent grid and
+// Persistent grid, one warp per destination node, lanes over channels (NCHUNK x 128, 128-bit accesses).  The in-edges
+// of a node are a contiguous CSR segment walked in PyG edge order (no atomics, deterministic).  ncu on the first
+// version (one node per warp iteration): DRAM 36 % busy, issue slots 41 %, 12.5 of 17.8 resident warps per issue
+// waiting on a long scoreboard - the dependent chain rowptr -> col_src/col_code -> gathered rows -> stores costs four
+// exposed memory latencies per node.  Here a warp owns nodes warp, warp + W, ... and
 //   * requests the rowptr pair of node i+2 and the column indices of node i+1 before it touches node i,
 //   * issues the gathers of the first PF in-edges of node i together (one exposed latency per node),
-// so that only the gather latency itself is left on the critical path.
+// so that only the gather latency itself is left on the critical path.  Statistics: pna_agg.cuh (single pass, sums
+// shifted by the first message).  Results leave through streaming 128-bit stores.
+// SRC_ONLY: P is [n, C] = source projections only and the aggregates are those of the shift-free q (the destination
+// term is folded into the post GEMM's weights, gnn_pna_fold_fwd) - the kernel then reads half as much.
+
 template <int NCHUNK, bool SRC_ONLY, int PF, int MINB>
 __global__ void __launch_bounds__(AGG_THREADS, MINB)
 pna_aggregate_fwd_pipe_kernel(const float* __restrict__ P, const float* __restrict__ tab,
@@ -254,6 +80,8 @@ pna_aggregate_fwd_pipe_kernel(const float* __restrict__ P, const float* __restri
     {
         const int rp = __ldg(rowptr + node + (lane & 1));
         beg = __shfl_sync(GNN_FULL_MASK, rp, 0);
+        // REDUX writes a uniform register: the edge loops below are then provably warp-uniform and the compiler drops
+        // the divergence bookkeeping (BSSY / WARPSYNC) around the shuffles
         cnt = __reduce_max_sync(GNN_FULL_MASK, __shfl_sync(GNN_FULL_MASK, rp, 1) - beg);
         if (lane < cnt) {
             raw_src = __ldg(col_src + beg + lane);
@@ -303,37 +131,24 @@ pna_aggregate_fwd_pipe_kernel(const float* __restrict__ P, const float* __restri
                 co[k] = __shfl_sync(GNN_FULL_MASK, my_code, k);
                 if (k < m) pr[k] = ldg4(pbase + so);
             }
-            const float4 q0 = add4(pr[0], ldg4(tbase + co[0]));     // bond-table rows are L1 hits: fetched at use
-            float4 s1 = zero, s2 = zero, mn = q0, mx = q0;
-#define ACC(Q)                                                                                                     \
-    {                                                                                                              \
-        const float4 q = (Q);                                                                                      \
-        const float dx = q.x - q0.x, dy = q.y - q0.y, dz = q.z - q0.z, dw = q.w - q0.w;                            \
-        s1 = make_float4(s1.x + dx, s1.y + dy, s1.z + dz, s1.w + dw);                                              \
-        s2 = make_float4(fmaf(dx, dx, s2.x), fmaf(dy, dy, s2.y), fmaf(dz, dz, s2.z), fmaf(dw, dw, s2.w));          \
-        mn = make_float4(fminf(mn.x, q.x), fminf(mn.y, q.y), fminf(mn.z, q.z), fminf(mn.w, q.w));                  \
-        mx = make_float4(fmaxf(mx.x, q.x), fmaxf(mx.y, q.y), fmaxf(mx.z, q.z), fmaxf(mx.w, q.w));                  \
-    }
+            PnaAcc<false> acc;
+            acc.first(add4(pr[0], ldg4(tbase + co[0])));    // bond-table rows are L1 hits: fetched at use
 #pragma unroll
             for (int k = 1; k < PF; ++k)
-                if (k < m) ACC(add4(pr[k], ldg4(tbase + co[k])))
+                if (k < m) acc.next(add4(pr[k], ldg4(tbase + co[k])));
             for (int k = PF; k < m; ++k) {                 // in-degree > PF: serial
                 const int so = __shfl_sync(GNN_FULL_MASK, my_src, k), ck = __shfl_sync(GNN_FULL_MASK, my_code, k);
-                ACC(add4(ldg4(pbase + so), ldg4(tbase + ck)))
+                acc.next(add4(ldg4(pbase + so), ldg4(tbase + ck)));
             }
             for (int s = beg + 32; s < beg + cnt; ++s)     // in-degree > 32 (never for molecules)
-                ACC(add4(ldg4(pbase + __ldg(col_src + s) * ldp + soff), ldg4(tbase + (int)__ldg(col_code + s) * C)))
-#undef ACC
+                acc.next(add4(ldg4(pbase + __ldg(col_src + s) * ldp + soff), ldg4(tbase + (int)__ldg(col_code + s) * C)));
             if (live[j]) {
-                const float inv = __frcp_rn((float)cnt);
-                const float4 m1 = make_float4(s1.x * inv, s1.y * inv, s1.z * inv, s1.w * inv);
-                st4_stream(out, make_float4(q0.x + m1.x + pd.x, q0.y + m1.y + pd.y, q0.z + m1.z + pd.z, q0.w + m1.w + pd.w));
-                st4_stream(out + F, add4(mn, pd));
-                st4_stream(out + 2 * F, add4(mx, pd));
-                st4_stream(out + 3 * F, make_float4(pna_std_fast(fmaf(-m1.x, m1.x, s2.x * inv)),
-                                                    pna_std_fast(fmaf(-m1.y, m1.y, s2.y * inv)),
-                                                    pna_std_fast(fmaf(-m1.z, m1.z, s2.z * inv)),
-                                                    pna_std_fast(fmaf(-m1.w, m1.w, s2.w * inv))));
+                float4 mean, sd;
+                acc.finish(cnt, mean, sd);
+                st4_stream(out, add4(mean, pd));
+                st4_stream(out + F, add4(acc.mn, pd));
+                st4_stream(out + 2 * F, add4(acc.mx, pd));
+                st4_stream(out + 3 * F, sd);
             }
         }
         // ---- (3) rotate
@@ -359,36 +174,19 @@ static int aggregate_fwd_launch(const float* P, const float* tab, const int32_t*
     const int C = towers * F;
     if ((int64_t)n * 2 * C >= (1ll << 31)) return GNN_ERR_TOO_LARGE;    // 32-bit row offsets in the gather
     cudaStream_t st = gnn_stream(stream);
-    int64_t blocks = gnn_ceil_div(n, AGG_WARPS);
-    int64_t cap = (int64_t)gnn_sm_count() * 48;
-    if (blocks > cap) blocks = cap;
     const int chunks = (C + 127) / 128;
-    // default: the persistent software-pipelined kernel (3 resident CTAs per SM, 80 registers); GNN_B200_AGG_FWD=0
-    // selects the one-node-per-warp-iteration kernel above (kept for A/B measurements, tools/agg_probe.py)
-    static const int variant = getenv("GNN_B200_AGG_FWD") ? atoi(getenv("GNN_B200_AGG_FWD")) : 1;
-    if (variant >= 1) {
-        int64_t pb = (int64_t)gnn_sm_count() * 3;
-        if (pb > gnn_ceil_div(n, AGG_WARPS)) pb = gnn_ceil_div(n, AGG_WARPS);
+    // persistent grid: 3 resident CTAs per SM (80 registers per thread)
+    int64_t pb = (int64_t)gnn_sm_count() * 3;
+    if (pb > gnn_ceil_div(n, AGG_WARPS)) pb = gnn_ceil_div(n, AGG_WARPS);
 #define LAUNCH_PIPE(CH) pna_aggregate_fwd_pipe_kernel<CH, SRC_ONLY, 3, 3><<<(unsigned)pb, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, (int)n, C, F, A)
-        switch (chunks) {
-            case 1: LAUNCH_PIPE(1); break;
-            case 2: LAUNCH_PIPE(2); break;
-            case 3: case 4: LAUNCH_PIPE(4); break;
-            case 5: case 6: case 7: case 8: LAUNCH_PIPE(8); break;
-            default: return GNN_ERR_UNSUPPORTED;
-        }
-#undef LAUNCH_PIPE
-        return gnn_launch_status();
-    }
-#define LAUNCH_FWD(CH) pna_aggregate_fwd_kernel<CH, SRC_ONLY><<<(unsigned)blocks, AGG_THREADS, 0, st>>>(P, tab, rowptr, col_src, col_code, (int)n, C, F, A)
     switch (chunks) {
-        case 1: LAUNCH_FWD(1); break;
-        case 2: LAUNCH_FWD(2); break;
-        case 3: case 4: LAUNCH_FWD(4); break;
-        case 5: case 6: case 7: case 8: LAUNCH_FWD(8); break;
+        case 1: LAUNCH_PIPE(1); break;
+        case 2: LAUNCH_PIPE(2); break;
+        case 3: case 4: LAUNCH_PIPE(4); break;
+        case 5: case 6: case 7: case 8: LAUNCH_PIPE(8); break;
         default: return GNN_ERR_UNSUPPORTED;
     }
-#undef LAUNCH_FWD
+#undef LAUNCH_PIPE
     return gnn_launch_status();
 }
 
@@ -412,11 +210,7 @@ extern "C" int gnn_pna_aggregate_src_fwd(const float* Psrc, const float* tab, co
 // partial tables in global memory with native 128-bit reductions (RED.E.ADD.F32x4 at the L2), summed afterwards.
 constexpr int DTAB_PARTS = 64;
 
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));     // one MUFU op, max rel. error 2^-23 (no slow-path call)
-    return y;
-}
+__device__ __forceinline__ float rcp_approx(float x) { return pna_rcp_approx(x); }
 
 // statistics of one more message for pass 1 (shifted sum, min / max with tie counts)
 __device__ __forceinline__ void bwd_stat(float q, float q0, float& s1, float& mn, float& mx, float& nmin, float& nmax) {
@@ -625,13 +419,14 @@ extern "C" int gnn_pna_aggregate_bwd(const float* gA, const float* P, const floa
                                      const int32_t* rowptr, const int32_t* col_src, const uint8_t* col_code,
                                      int64_t n, int towers, int F, float* dP, float* dq, float* dtab_accum,
                                      void* zeroed_workspace, int64_t workspace_bytes, void* stream) {
-    return aggregate_bwd_launch<false>(gA, P, tab, A, rowptr, col_src, col_code, n, towers, F, dP, dq, dtab_accum,
-                                       zeroed_workspace, workspace_bytes, stream);
+    return aggregate_bwd_launch<false>(gA, P, tab, A, rowptr, col_src, col_code, n, towers, F, dP, dq,
+                                       dtab_accum, zeroed_workspace, workspace_bytes, stream);
 }
 extern "C" int gnn_pna_aggregate_src_bwd(const float* gA, const float* Psrc, const float* tab, const float* A,
-                                         const int32_t* rowptr, const int32_t* col_src, const uint8_t* col_code,
-                                         int64_t n, int towers, int F, float* dPsrc, float* dq, float* dtab_accum,
-                                         void* zeroed_workspace, int64_t workspace_bytes, void* stream) {
+                                         const int32_t* rowptr, const int32_t* col_src,
+                                         const uint8_t* col_code, int64_t n, int towers, int F, float* dPsrc, float* dq,
+                                         float* dtab_accum, void* zeroed_workspace, int64_t workspace_bytes,
+                                         void* stream) {
     return aggregate_bwd_launch<true>(gA, Psrc, tab, A, rowptr, col_src, col_code, n, towers, F, dPsrc, dq,
                                       dtab_accum, zeroed_workspace, workspace_bytes, stream);
 }

@@ -32,18 +32,22 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    stamp = LIB + ".stamp"
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB
-    objdir = os.path.join(HERE, "build")
+def build(force: bool = False, verbose: bool = False, profile: bool = False) -> str:
+    """profile=True builds libgnnepcsaft_b200_prof.so with -DGNN_B200_PROFILE (per-role cycle counters of the
+    tensor-core GEMMs and the gnn_tc_set_profile_buffer hook, tools/tc_probe.py); the product library has neither."""
+    lib = LIB.replace(".so", "_prof.so") if profile else LIB
+    flags = NVCC_FLAGS + (["-DGNN_B200_PROFILE"] if profile else [])
+    stamp = lib + ".stamp"
+    digest = _digest() + ("p" if profile else "")
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return lib
+    objdir = os.path.join(HERE, "build_prof" if profile else "build")
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(HERE, src), "-o", obj]
+        cmd = [nvcc, *flags, "-c", os.path.join(HERE, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -53,12 +57,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     open(stamp, "w").write(digest)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, profile="--profile" in sys.argv))

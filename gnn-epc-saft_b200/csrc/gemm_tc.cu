@@ -17,7 +17,18 @@
 #include "common.cuh"
 
 #include <cuda_bf16.h>
-#include <stdlib.h>
+
+#include <type_traits>
+
+#include "pna_agg.cuh"
+
+// Per-role cycle counters (tools/tc_probe.py) exist only in a -DGNN_B200_PROFILE build; the product library has
+// neither the counters nor the process-global hook that enables them.
+#ifdef GNN_B200_PROFILE
+#define GNN_PROF(g) ((g).prof)
+#else
+#define GNN_PROF(g) (static_cast<unsigned long long*>(nullptr))
+#endif
 
 namespace tc {
 
@@ -29,17 +40,18 @@ constexpr int CHUNKS = ROW_BYTES / 16;
 // Weight-gradient (MN-major) launches have one light epilogue per CTA and register-hungry producers: 4 warps
 // there, the first of which also issues the MMAs (20 warps = 5 per SM sub-partition -> 96 registers per
 // thread); 8 epilogue warps + a dedicated MMA warp elsewhere (25 warps -> 72 registers).
-__host__ __device__ constexpr int epi_warps(bool mn_major) { return mn_major ? 4 : 8; }
+// Launches whose producers also compute the PNA aggregates (AggSrc below) need ~96 registers per producer thread as
+// well and use the same 20-warp shape (the register file is split over four sub-partitions: a 21st warp would put six
+// warps on one of them and cap every thread at 80 registers again).
+__host__ __device__ constexpr int epi_warps(bool mn_major, bool agg = false) { return (mn_major || agg) ? 4 : 8; }
                                              // warp EW: one elected lane issues tcgen05.mma
 constexpr int PROD_GROUPS = 4;               // warps 5-20: four producer groups take k-blocks round-robin
 constexpr int PROD_GROUP_THREADS = 128;
-__host__ __device__ constexpr int cta_threads(bool mn_major) {
-    return (epi_warps(mn_major) + (mn_major ? 0 : 1)) * 32 + PROD_GROUPS * PROD_GROUP_THREADS;
+__host__ __device__ constexpr int cta_threads(bool mn_major, bool agg = false) {
+    return (epi_warps(mn_major, agg) + ((mn_major || agg) ? 0 : 1)) * 32 + PROD_GROUPS * PROD_GROUP_THREADS;
 }
-// MODE_TF32X3: three tf32 MMAs per K step.  MODE_TF32C: the hi*hi product on the tf32 path plus ONE bf16 MMA whose
-// doubled K carries both cross terms ([lo | hi] x [hi ; lo], operands rounded to bf16): two instructions instead of
-// three at ~2^-19 relative error per product.  MODE_BF16: one bf16 MMA.
-enum { MODE_TF32X3 = 0, MODE_BF16 = 1, MODE_TF32C = 2 };
+// MODE_TF32X3: three tf32 MMAs per K step (fp32-level accuracy).  MODE_BF16: one bf16 MMA.
+enum { MODE_TF32X3 = 0, MODE_BF16 = 1 };
 __host__ __device__ constexpr bool tf32_like(int mode) { return mode != MODE_BF16; }
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -125,35 +137,6 @@ __device__ __forceinline__ void umma_acc(uint32_t tmem_d, uint64_t adesc, uint64
         asm volatile("tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, 1;" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
                      : "memory");
 }
-__device__ __forceinline__ void umma_ts_tf32_acc(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc) {
-    asm volatile("tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, 1;" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc)
-                 : "memory");
-}
-// A operand in tensor memory (lane = row, one 32-bit column per tf32 element), B from a shared-memory descriptor
-__device__ __forceinline__ void umma_ts_tf32(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// registers -> TMEM: 16 consecutive 32-bit columns of this thread's lane (warp w owns lanes 32 (w % 4) ..)
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
-        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
-                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-                 "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t r[16];
     asm volatile(
@@ -246,12 +229,16 @@ struct VTransposed {        // element (r, k) = p[k*ld + r]
 //   k <  F : s == 0 ? Wpost_t[o, k] : 0          k >= F : Wpost_t[o, F + s*4F + (k-F)]
 // vx != nullptr (folded destination projection, fold.cu): the x columns of ALL three scaler groups come from
 //   Vx[t][s][o][k]  instead ( = [s == 0] Wpost_t[o, k] + (Wmean + Wmin + Wmax)_{t,s} . Wdst_t ).
+// agg_xpad > 0 selects the K order of the fused aggregate producers (AggSrc): k < agg_xpad are the x columns (zero
+// beyond F), then one 32-column k-block per group of 8 features: column cc of k-block j is aggregator (cc >> 3),
+// feature 8 j + 4 ((cc >> 2) & 1) + (cc & 3).
 struct VPostWeight {
     static constexpr bool kTransposed = false;   // lanes of a producer warp run along K
     const float* w;
     int64_t tower_stride;
     int F, F_out, FoP;
     const float* vx;
+    int agg_xpad;
     __device__ __forceinline__ void set_group(int g) {
         w += (int64_t)g * tower_stride;
         if (vx) vx += (int64_t)g * 3 * F_out * F;
@@ -260,6 +247,15 @@ struct VPostWeight {
         float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         int tile = (int)r / (3 * FoP), rem = (int)r - tile * 3 * FoP;
         int s = rem / FoP, o = tile * FoP + (rem - s * FoP);
+        if (agg_xpad > 0) {
+            if (o >= F_out || k >= agg_xpad + 4 * (int64_t)F) return z;
+            if (k >= agg_xpad) {
+                const int kk = (int)k - agg_xpad, j = kk >> 5, cc = kk & 31;
+                k = F + (int64_t)(cc >> 3) * F + 8 * j + 4 * ((cc >> 2) & 1);      // cc & 3 == 0: four consecutive features
+            } else if (k >= F) {
+                return z;
+            }
+        }
         if (o >= F_out || k >= 5 * (int64_t)F) return z;
         const float* row = w + (int64_t)o * 13 * F;
         if (k < F) {
@@ -397,6 +393,26 @@ __device__ __forceinline__ SegRef seg_resolve(const SegOperand& op, int64_t col,
     return r;
 }
 
+// ------------------------------------------------------------------ aggregates produced on the fly
+// Post forward with the aggregates computed by the GEMM's own producers (folded formulation): instead of reading
+// A = [mean | min | max | std] of q = Psrc[src] + tab[code] from HBM (2 KB per node and layer, written by a separate
+// kernel), a producer group gathers the source rows of its 128 nodes for 8 features, reduces them in registers
+// (pna_agg.cuh - the arithmetic of the stand-alone kernel, bit-identical) and writes the four aggregates straight into
+// the SWIZZLE_128B operand stage (tf32 hi / lo planes).  One such pass = one 32-column k-block (4 aggregators x 8
+// features); the weight image is packed in the same K order (VPostWeight::agg_xpad).  A_out != NULL (training) also
+// stores the aggregates for the backward pass: one 209 MB write instead of a write and a read.
+struct NoAgg {};
+struct AggSrc {
+    const float* P;            // Psrc [n, C], C = towers * F
+    const float* tab;          // [60, C]
+    const int* rowptr;
+    const int* col_src;
+    const uint8_t* col_code;
+    float* A_out;              // [n, towers, 4, F] or nullptr
+    int F, C, xpad;            // xpad: K columns of the x part (F rounded up to the 32-column k-block)
+};
+// results of one thread - rows r and r + 64 of the tile, four features, four aggregators - live in the eight float4
+// of the plain producer's ATile (v[4 * half + aggregator]): the two producer paths never hold values at the same time
 // ------------------------------------------------------------------ epilogues
 // emit4(m, n, N, v): four consecutive output columns n..n+3 of row m (n % 4 == 0); lanes of a warp
 // cover consecutive columns, so the vector paths are fully coalesced.
@@ -658,30 +674,6 @@ __device__ __forceinline__ void put_chunk_tf32(uint8_t* tile, uint32_t plane_byt
     *reinterpret_cast<float4*>(tile + off) = hi;
     *reinterpret_cast<float4*>(tile + plane_bytes + off) = lo;
 }
-// four fp32 -> four bf16 by truncation: one PRMT per pair (the cvt.rn.bf16x2 path made the producers the
-// bottleneck); the operands of the correction MMA only need ~8 bits
-__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
-    return make_uint2(__byte_perm(__float_as_uint(v.x), __float_as_uint(v.y), 0x7632),
-                      __byte_perm(__float_as_uint(v.z), __float_as_uint(v.w), 0x7632));
-}
-// MODE_TF32C: hi goes to the tf32 plane at `off`; the second plane is a bf16 tile whose K is doubled: part 0 at
-// `coff0`, part 1 at `coff1` (8-byte half chunks).  A operands store (lo, hi), B operands (hi, lo), so that the bf16
-// MMA over the doubled K sums lo_a*hi_b + hi_a*lo_b.
-template <bool IS_B>
-__device__ __forceinline__ void put_chunk_tf32c(uint8_t* tile, uint32_t plane_bytes, uint32_t off, uint32_t coff0,
-                                                uint32_t coff1, float4 v) {
-    float4 hi, lo;
-    split_tf32(v, hi, lo);
-    *reinterpret_cast<float4*>(tile + off) = hi;
-    *reinterpret_cast<uint2*>(tile + plane_bytes + coff0) = pack_bf16x4(IS_B ? hi : lo);
-    *reinterpret_cast<uint2*>(tile + plane_bytes + coff1) = pack_bf16x4(IS_B ? lo : hi);
-}
-// K-major tiles: correction-plane offset of the 4-element chunk c (0..7) of `row`, part 0 / 1.  The two parts of
-// eight consecutive K values share one 32-byte MMA slice (16-byte chunk 2*(c>>1) + part): any K order works as long
-// as A and B agree, and this one lets a warp's 8-byte stores (4 rows x 64 B) cover all 32 banks.
-__device__ __forceinline__ uint32_t sw128_coff(int row, int c, int part) {
-    return (uint32_t)row * ROW_BYTES + (uint32_t)((((c >> 1) * 2 + part) ^ (row & 7)) << 4) + (uint32_t)(c & 1) * 8u;
-}
 __device__ __forceinline__ void put_chunk_bf16(uint8_t* tile, uint32_t off, float4 a, float4 b) {
     __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
     __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
@@ -725,8 +717,6 @@ __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_
                 const int r = rb + r0 + 16 * i;
                 if (r < rows) {
                     if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, sw128_offset(r, c), v[i]);
-                    else if (MODE == MODE_TF32C)
-                        put_chunk_tf32c<true>(tile, plane_bytes, sw128_offset(r, c), sw128_coff(r, c, 0), sw128_coff(r, c, 1), v[i]);
                     else put_chunk_bf16(tile, sw128_offset(r, c), v[i], w[MODE == MODE_BF16 ? i : 0]);
                 }
             }
@@ -749,9 +739,6 @@ __device__ __forceinline__ void produce_tile(const L& ld, uint8_t* tile, uint32_
 #pragma unroll
                 for (int i = 0; i < NB; ++i) {
                     if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, sw128_offset(r, cb + i), v[i]);
-                    else if (MODE == MODE_TF32C)
-                        put_chunk_tf32c<true>(tile, plane_bytes, sw128_offset(r, cb + i), sw128_coff(r, cb + i, 0),
-                                              sw128_coff(r, cb + i, 1), v[i]);
                     else put_chunk_bf16(tile, sw128_offset(r, cb + i), v[i], w[MODE == MODE_BF16 ? i : 0]);
                 }
             }
@@ -814,7 +801,6 @@ template <int MODE, bool SCALED>
 __device__ __forceinline__ void store_a_seg(uint8_t* tile, uint32_t plane_bytes, int p, ATile<MODE, SCALED>& t) {
     const int c = p & 7, r0 = p >> 3;
     const uint32_t off0 = (uint32_t)r0 * ROW_BYTES + (uint32_t)((c ^ (r0 & 7)) << 4);   // (r0 + 16 i) & 7 == r0 & 7
-    const uint32_t coff0 = sw128_coff(r0, c, 0), coff1 = sw128_coff(r0, c, 1);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float4 v = t.v[i], w = t.w[MODE == MODE_BF16 ? i : 0];
@@ -828,56 +814,8 @@ __device__ __forceinline__ void store_a_seg(uint8_t* tile, uint32_t plane_bytes,
         }
         const uint32_t off = off0 + (uint32_t)i * (16 * ROW_BYTES);
         if (MODE == MODE_TF32X3) put_chunk_tf32<MODE>(tile, plane_bytes, off, v);
-        else if (MODE == MODE_TF32C)
-            put_chunk_tf32c<false>(tile, plane_bytes, off, coff0 + (uint32_t)i * (16 * ROW_BYTES),
-                                   coff1 + (uint32_t)i * (16 * ROW_BYTES), v);
         else put_chunk_bf16(tile, off, v, w);
     }
-}
-
-// A operand straight into tensor memory (TF32X3, K-major): thread = one row of the 128-row tile (TMEM lane), which
-// loads its 32 k-block columns as eight 16-byte chunks (one full 128-byte line per thread), splits them into tf32
-// hi / lo and writes 2 x 32 TMEM columns with tcgen05.st.  The MMAs then read only the B operand from shared memory:
-// below N = 128 an SS-mode MMA is bound by its shared-memory operand reads ((128 + N) x 32 B at 128 B/clk, measured
-// with tools/mma_rate.cu), and the producers' own tile stores compete for the same bandwidth.
-// Requires k-block aligned segments (starts and widths multiples of 32 columns, checked by the host): one segment
-// lookup and one row pointer per k-block, all eight loads in flight together.
-struct ATmemRow {
-    float4 v[8];
-    float f;
-};
-template <bool SCALED>
-__device__ __forceinline__ void load_a_tmem(const SegOperand& op, int grp, int64_t row, int64_t kbase, int64_t k_end,
-                                            ATmemRow& t) {
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    const SegRef sr = kbase < k_end ? seg_resolve(op, kbase, grp) : SegRef{nullptr, 0, -1};
-    const bool ok = row < op.rows && sr.ptr != nullptr;
-    const float* q = ok ? sr.ptr + row * sr.ld : nullptr;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) t.v[c] = ok ? ldg4(q + 4 * c) : zero;
-    t.f = 1.f;
-    if (SCALED) {
-        if (ok && sr.scale >= 0) t.f = __ldg(op.scal + 2 * row + sr.scale);
-    }
-}
-template <bool SCALED>
-__device__ __forceinline__ void store_a_tmem(uint32_t taddr_hi, ATmemRow& t) {
-#pragma unroll
-    for (int qd = 0; qd < 4; ++qd) {
-        float4 a = t.v[2 * qd], b = t.v[2 * qd + 1];
-        if (SCALED) {
-            a = make_float4(a.x * t.f, a.y * t.f, a.z * t.f, a.w * t.f);
-            b = make_float4(b.x * t.f, b.y * t.f, b.z * t.f, b.w * t.f);
-        }
-        float4 h0, l0, h1, l1;
-        split_tf32(a, h0, l0);
-        split_tf32(b, h1, l1);
-        const float hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-        const float lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        tmem_st8(taddr_hi + qd * 8, hi);
-        tmem_st8(taddr_hi + 32 + qd * 8, lo);
-    }
-    tmem_wait_st();
 }
 
 // MN-major tile from a segmented operand (weight gradients: the reduction index is the node).
@@ -969,15 +907,7 @@ struct MnPlan {
     int64_t step_ld;       // step * row_ld
     int kk0, step;
     uint32_t off0, off1, dk2;   // smem offset of row i: off[i & 1] + (i >> 1) * dk2
-    int ch;                     // 4-column chunk index inside the tile (MODE_TF32C correction plane)
-    uint32_t kgs16;             // bytes between 8-row K groups of the bf16 correction plane
 };
-// bf16 MN-major tile (8-row atoms, 16-byte swizzle): byte offset of the 4-column half chunk ch4 in K row kk2
-__device__ __forceinline__ uint32_t mn_coff_bf16(int kk2, int ch4, uint32_t kgs16) {
-    const int kr = kk2 & 7, c16 = ch4 >> 1;
-    return (uint32_t)(kk2 >> 3) * kgs16 + (uint32_t)(c16 >> 3) * 1024u + (uint32_t)kr * 128u +
-           (uint32_t)(((c16 & 7) ^ kr) << 4) + (uint32_t)(ch4 & 1) * 8u;
-}
 __device__ __forceinline__ uint32_t mn_off_tf32(int kk, int c8, uint32_t mg_off, uint32_t kgs) {
     const int kr = kk & 3;
     return (uint32_t)(kk >> 2) * kgs + mg_off + (uint32_t)kr * 128u + (uint32_t)((((c8 >> 1) ^ kr) << 5) | ((c8 & 1) << 4));
@@ -996,8 +926,6 @@ __device__ __forceinline__ MnPlan mn_plan(const SegOperand& op, int grp, int R, 
     pl.off0 = mn_off_tf32(pl.kk0, ch & 7, mg_off, kgs);
     pl.off1 = mn_off_tf32(pl.kk0 + pl.step, ch & 7, mg_off, kgs);
     pl.dk2 = mn_off_tf32(pl.kk0 + 2 * pl.step, ch & 7, mg_off, kgs) - pl.off0;
-    pl.ch = ch;
-    pl.kgs16 = (uint32_t)(R >> 6) * 1024u;
     return pl;
 }
 // wait_stage() is called once all loads are in flight and before the first shared-memory store (the ring stage may
@@ -1006,7 +934,6 @@ template <int MODE, bool SCALED, int NA, int NB, class WaitFn>
 __device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnPlan& pb, uint8_t* a_tile, uint32_t a_plane,
                                                      uint8_t* b_tile, uint32_t b_plane, int64_t kbase, int64_t lim,
                                                      float4* colacc, WaitFn&& wait_stage) {
-    constexpr int KBR = NA * 4;                              // K rows (nodes) of this k-block: A has step 4
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 va[NA], vb[NB];
     float f[NA];
@@ -1042,23 +969,123 @@ __device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnP
         if (colacc != nullptr)
             colacc[0] = make_float4(colacc[0].x + va[i].x, colacc[0].y + va[i].y, colacc[0].z + va[i].z, colacc[0].w + va[i].w);
         const uint32_t off = ((i & 1) ? pa.off1 : pa.off0) + (uint32_t)(i >> 1) * pa.dk2;
-        if (MODE == MODE_TF32C) {
-            const int kk = pa.kk0 + i * pa.step;
-            put_chunk_tf32c<false>(a_tile, a_plane, off, mn_coff_bf16(kk, pa.ch, pa.kgs16),
-                                   mn_coff_bf16(KBR + kk, pa.ch, pa.kgs16), va[i]);
-        } else {
-            put_chunk_tf32<MODE_TF32X3>(a_tile, a_plane, off, va[i]);
-        }
+        put_chunk_tf32<MODE_TF32X3>(a_tile, a_plane, off, va[i]);
     }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
         const uint32_t off = ((i & 1) ? pb.off1 : pb.off0) + (uint32_t)(i >> 1) * pb.dk2;
-        if (MODE == MODE_TF32C) {
-            const int kk = pb.kk0 + i * pb.step;
-            put_chunk_tf32c<true>(b_tile, b_plane, off, mn_coff_bf16(kk, pb.ch, pb.kgs16),
-                                  mn_coff_bf16(KBR + kk, pb.ch, pb.kgs16), vb[i]);
-        } else {
-            put_chunk_tf32<MODE_TF32X3>(b_tile, b_plane, off, vb[i]);
+        put_chunk_tf32<MODE_TF32X3>(b_tile, b_plane, off, vb[i]);
+    }
+}
+
+// thread p of the 128-thread producer group -> (row r in [0, 64), feature half h): a warp covers 16 rows, two lanes
+// share the 32 contiguous bytes a k-block needs of every gathered row.  The row order inside a quarter warp is
+// {0,2,4,6}, {1,3,5,7}, ... so that the eight 16-byte stores of a quarter warp (chunks 2a + h XOR (r & 7)) fall into
+// eight different bank groups.
+// Measured (tools/fused_probe.py, ncu): the producers are bound by the number of distinct 128-byte lines their gathers
+// touch (L1 wavefronts), not by bytes or latency - one lane per row (32 lines per load instead of 16) ran 25 % slower,
+// as did re-reading the first message in place of predicated-off slots.
+__device__ __forceinline__ void agg_thread_map(int p, int& r, int& h) {
+    const int lane = p & 31, q = lane >> 1;
+    h = lane & 1;
+    r = 16 * (p >> 5) + ((q >> 2) & 1) + 2 * (q & 3) + 8 * (q >> 3);
+}
+// predicated 128-bit gather: `v` keeps its value when `pred` is false (no branch, no memory request)
+__device__ __forceinline__ void ldg4_pred(float4& v, const float* p, bool pred) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+        : "l"(p), "r"((int)pred));
+}
+// Branch-free for the first PF in-edges: slots beyond the segment re-read its first message, which leaves every
+// statistic unchanged (q - q0 = 0, min / max idempotent), so the index loads of both rows, then all gathers of both
+// rows, are issued back to back - three exposed latencies per k-block instead of three per row and edge.
+__device__ __forceinline__ void agg_compute(const AggSrc& ag, int grp, int64_t m0, int64_t rows, int j, int p, float4 (&v)[8]) {
+    constexpr int PF = 3;
+    int r, h;
+    agg_thread_map(p, r, h);
+    const int col = grp * ag.F + 8 * j + 4 * h;                     // channel of Psrc / tab
+    const float* const pbase = ag.P + col;
+    const float* const tbase = ag.tab + col;
+    int beg[2], cnt[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int64_t node = m0 + r + 64 * half;
+        const bool ok = node < rows;
+        const int64_t nn = ok ? node : 0;                           // rows > 0: always a valid address
+        beg[half] = __ldg(ag.rowptr + nn);
+        cnt[half] = ok ? __ldg(ag.rowptr + nn + 1) : 0;
+    }
+    int so[2][PF], co[2][PF];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        cnt[half] = max(cnt[half] - beg[half], 0);
+        if (cnt[half] == 0) beg[half] = 0;                          // empty segment: read slot 0 (valid), result discarded
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int slot = beg[half] + (k < cnt[half] ? k : 0);
+            so[half][k] = __ldg(ag.col_src + slot);
+            co[half][k] = (int)__ldg(ag.col_code + slot);
+        }
+    }
+    float4 tab0 = ldg4(tbase);                                      // bond code 0: every self-loop, plain single bonds
+    float4 pr[2][PF], tb[2][PF];
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const bool on = k < cnt[half] || k == 0;
+            pr[half][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            tb[half][k] = tab0;
+            ldg4_pred(pr[half][k], pbase + so[half][k] * ag.C, on);
+            ldg4_pred(tb[half][k], tbase + co[half][k] * ag.C, on && co[half][k] != 0);
+        }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        PnaAcc<false> acc;
+        const float4 q0 = pna_add4(pr[half][0], tb[half][0]);
+        acc.first(q0);
+#pragma unroll
+        for (int k = 1; k < PF; ++k) acc.next(k < cnt[half] ? pna_add4(pr[half][k], tb[half][k]) : q0);
+        for (int k = PF; k < cnt[half]; ++k)                        // in-degree > PF: serial
+            acc.next(pna_add4(ldg4(pbase + __ldg(ag.col_src + beg[half] + k) * ag.C),
+                              ldg4(tbase + (int)__ldg(ag.col_code + beg[half] + k) * ag.C)));
+        float4 mean, sd;
+        acc.finish(max(cnt[half], 1), mean, sd);
+        const bool some = cnt[half] > 0;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * half] = some ? mean : zero;
+        v[4 * half + 1] = some ? acc.mn : zero;
+        v[4 * half + 2] = some ? acc.mx : zero;
+        v[4 * half + 3] = some ? sd : zero;
+    }
+}
+// shared-space 128-bit store (the generic ST.E the compiler emits for pointers derived from the aligned dynamic
+// shared-memory base costs an address-space check per access)
+__device__ __forceinline__ void sts4(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void agg_store(const AggSrc& ag, int grp, int64_t m0, int64_t rows, int j, int p, uint8_t* tile,
+                                          uint32_t plane_bytes, const float4 (&v)[8]) {
+    int r, h;
+    agg_thread_map(p, r, h);
+    const uint32_t base = smem_u32(tile);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int row = r + 64 * half;                               // (row & 7) == (r & 7)
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            float4 hi, lo;
+            split_tf32(v[4 * half + a], hi, lo);
+            const uint32_t off = base + sw128_offset(row, 2 * a + h);
+            sts4(off, hi);
+            sts4(off + plane_bytes, lo);
+        }
+        if (ag.A_out != nullptr && m0 + row < rows) {
+            float* dst = ag.A_out + (m0 + row) * (4 * (int64_t)ag.C) + (int64_t)grp * 4 * ag.F + 8 * j + 4 * h;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) st4_stream(dst + a * ag.F, v[4 * half + a]);
         }
     }
 }
@@ -1090,34 +1117,34 @@ pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t*
     produce_tile<MODE>(bl, tile, b_plane, rows, (int64_t)nt * BN + r_begin, (int64_t)kb * KB_ELEMS, K, threadIdx.x);
 }
 
-// A_TMEM (TF32X3, K-major, packed weights): the activation operand lives in tensor memory (4 ring stages x 64 columns
-// behind the two accumulators) instead of shared memory; the smem ring then holds only the TMA-fetched weight tiles.
-constexpr uint32_t A_TMEM_STAGE_COLS = 64;
-template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP, bool A_TMEM = false>
-__global__ void __launch_bounds__(cta_threads(MN_MAJOR), 1)
-gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b) {
+template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP, class AG = NoAgg>
+__global__ void __launch_bounds__(cta_threads(MN_MAJOR, !std::is_same<AG, NoAgg>::value), 1)
+gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b,
+               const AG ag) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar[2], tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_s;
 
     constexpr int KB_ELEMS = tf32_like(MODE) ? 32 : 64;
     constexpr int PARTS = tf32_like(MODE) ? 2 : 1;
-    constexpr int EPI_WARPS = epi_warps(MN_MAJOR), MMA_WARP = MN_MAJOR ? 0 : EPI_WARPS;
-    constexpr int PROD_WARP0 = MN_MAJOR ? EPI_WARPS : EPI_WARPS + 1;
+    constexpr bool AGG = !std::is_same<AG, NoAgg>::value;      // aggregate k-blocks produced on the fly (K-major, TF32X3)
+    static_assert(!AGG || (MODE == MODE_TF32X3 && !MN_MAJOR), "fused aggregates: K-major TF32X3 launches only");
+    constexpr bool MMA_IN_EPI = MN_MAJOR || AGG;               // epilogue warp 0 also issues the MMAs (20-warp CTA)
+    constexpr int EPI_WARPS = epi_warps(MN_MAJOR, AGG), MMA_WARP = MMA_IN_EPI ? 0 : EPI_WARPS;
+    constexpr int PROD_WARP0 = MMA_IN_EPI ? EPI_WARPS : EPI_WARPS + 1;
     // The warp index goes through a shuffle so that the compiler treats it (and every role branch on it) as
     // warp-uniform: inside a branch it believes divergent it cannot use the uniform datapath, and each tcgen05.mma -
     // whose descriptors live in uniform registers - was wrapped in an ELECT / 4 x R2UR.BROADCAST "waterfall" loop
     // that paced the single issuing thread at ~140 cycles per MMA (tools/mma_noise.cu reproduces the number).
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int BN = g.BN, NS = g.stages;
-    const long long kernel_t0 = g.prof ? clock64() : 0;
+    const long long kernel_t0 = GNN_PROF(g) ? clock64() : 0;
 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int KBR = MN_MAJOR ? g.kb_rows : KB_ELEMS;                 // K rows per ring stage
     const uint32_t kdiv = MN_MAJOR ? (uint32_t)(KB_ELEMS / g.kb_rows) : 1u;
-    const uint32_t a_plane = A_TMEM ? 0u : BM * ROW_BYTES / kdiv, b_plane = (uint32_t)BN * ROW_BYTES / kdiv;
+    const uint32_t a_plane = BM * ROW_BYTES / kdiv, b_plane = (uint32_t)BN * ROW_BYTES / kdiv;
     const uint32_t stage_bytes = PARTS * (a_plane + b_plane);        // multiple of 1024
-    const uint32_t a_tmem_col0 = g.tmem_cols - 4 * A_TMEM_STAGE_COLS;   // A ring: the last 256 columns (A_TMEM only)
 
     if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, g.tmem_cols);
     if (tid == 0) {
@@ -1161,10 +1188,10 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             EP ep = ep0;
             ep.set_group(grp);
             const uint32_t b = t & 1, tuse = t >> 1;
-            const long long et0 = g.prof ? clock64() : 0;
+            const long long et0 = GNN_PROF(g) ? clock64() : 0;
             mbar_wait(&tmem_full_bar[b], tuse & 1);
             tc_fence_after();
-            const long long et1 = g.prof ? clock64() : 0;
+            const long long et1 = GNN_PROF(g) ? clock64() : 0;
             const uint32_t taddr = tmem_base + b * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
             const int64_t m = m0 + q * 32 + lane;
             const bool row_ok = m < g.M;
@@ -1207,9 +1234,9 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             }
             for (int col = half * 16; col < out_cols && !staged; col += 4 * EPI_WARPS) {
                 float v[16];
-                const long long lt0 = g.prof ? clock64() : 0;
+                const long long lt0 = GNN_PROF(g) ? clock64() : 0;
                 tmem_ld16(taddr + col, v);
-                if (g.prof) ld_cyc += clock64() - lt0;
+                if (GNN_PROF(g)) ld_cyc += clock64() - lt0;
                 if constexpr (EP::kCombine3) {
                     float d1[16], d2[16];
                     tmem_ld16(taddr + out_cols + col, d1);
@@ -1237,18 +1264,17 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty_bar[b]);
-            if (g.prof && tid == 0) {
-                atomicAdd(g.prof + 6, (unsigned long long)(et1 - et0));             // epilogue waiting for the accumulator
-                atomicAdd(g.prof + 7, (unsigned long long)(clock64() - et1));       // epilogue work
-                atomicAdd(g.prof + 8, 1ull);
-                atomicAdd(g.prof + 11, (unsigned long long)ld_cyc);                 // ... of which first tcgen05.ld + wait per chunk
-                if (t == 0) atomicAdd(g.prof + 14, (unsigned long long)(et1 - kernel_t0));       // first item: accumulator ready
+            if (GNN_PROF(g) && tid == 0) {
+                atomicAdd(GNN_PROF(g) + 6, (unsigned long long)(et1 - et0));             // epilogue waiting for the accumulator
+                atomicAdd(GNN_PROF(g) + 7, (unsigned long long)(clock64() - et1));       // epilogue work
+                atomicAdd(GNN_PROF(g) + 8, 1ull);
+                atomicAdd(GNN_PROF(g) + 11, (unsigned long long)ld_cyc);                 // ... of which first tcgen05.ld + wait per chunk
+                if (t == 0) atomicAdd(GNN_PROF(g) + 14, (unsigned long long)(et1 - kernel_t0));       // first item: accumulator ready
             }
         }
     };
     // =============================== MMA issue (one work item, one warp) ===============================
     const uint32_t idesc = instr_desc(MODE, BN, MN_MAJOR ? 1 : 0);
-    const uint32_t idesc16 = instr_desc(MODE_BF16, BN, MN_MAJOR ? 1 : 0);      // correction MMAs of MODE_TF32C
     // The warp shares its scheduler with six busy producer / epilogue warps, so every instruction of the issue loop
     // counts: running stage counters instead of a division per k-block, descriptors built once per k-block.
     uint32_t ms = 0, muse = 0;                  // ring stage / use count of the next k-block
@@ -1268,18 +1294,16 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     ms = 0;
                     ++muse;
                 }
-                const long long mt0 = g.prof ? clock64() : 0;
+                const long long mt0 = GNN_PROF(g) ? clock64() : 0;
                 mbar_wait(&full_bar[s], use & 1);
-                if (A_TMEM) tc_fence_after();       // TMEM operand written by other threads (tcgen05.st)
-                if (g.prof && lane == 0) {
-                    atomicAdd(g.prof + 4, (unsigned long long)(clock64() - mt0));   // MMA warp waiting for operands
-                    atomicAdd(g.prof + 5, 1ull);
+                if (GNN_PROF(g) && lane == 0) {
+                    atomicAdd(GNN_PROF(g) + 4, (unsigned long long)(clock64() - mt0));   // MMA warp waiting for operands
+                    atomicAdd(GNN_PROF(g) + 5, 1ull);
                 }
                 if (elect_one()) {
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes), a_lo = a_hi + a_plane;
                     const uint32_t b_hi = a_hi + PARTS * a_plane, b_lo = b_hi + b_plane;
                     const int ksteps = (CHUNKS / 2) / (int)kdiv;
-                    uint64_t corr_a[CHUNKS / 2], corr_b[CHUNKS / 2];
                     // Descriptors of k-step 0 once per k-block; a k-step only advances the 14-bit start-address field
                     // (16-byte units), so the other k-steps are one 64-bit add each.  This thread's instruction stream
                     // is what paces the tensor pipe: with the descriptors rebuilt per k-step and a predicate set up per
@@ -1311,47 +1335,22 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         const uint32_t first = (kb == 0 && j == 0) ? 0u : 1u;
                         const uint64_t dah = dah0 + (uint64_t)(j * astep), dal = dal0 + (uint64_t)(j * astep);
                         const uint64_t dbh = dbh0 + (uint64_t)(j * bstep), dbl = dbl0 + (uint64_t)(j * bstep);
-                        if (A_TMEM) {
-                            const uint32_t ta_hi = tmem_base + a_tmem_col0 + s * A_TMEM_STAGE_COLS + (uint32_t)j * 8u;
-                            if (j == 0) umma_ts_tf32(tmem_d, ta_hi + 32u, dbh, idesc, first);
-                            else umma_ts_tf32_acc(tmem_d, ta_hi + 32u, dbh, idesc);
-                            umma_ts_tf32_acc(tmem_d, ta_hi, dbl, idesc);
-                            umma_ts_tf32_acc(tmem_d, ta_hi, dbh, idesc);
-                        } else if (MODE == MODE_TF32X3) {
+                        if (MODE == MODE_TF32X3) {
                             if (j == 0) umma<MODE>(tmem_d, dal, dbh, idesc, first);
                             else umma_acc<MODE>(tmem_d, dal, dbh, idesc);
                             umma_acc<MODE>(tmem_d, dah, dbl, idesc);
                             umma_acc<MODE>(tmem_d, dah, dbh, idesc);
-                        } else if (MODE == MODE_TF32C) {
-                            // hi*hi on the tf32 path, then one bf16 MMA over the K-doubled correction planes
-                            uint64_t dac, dbc;
-                            if (MN_MAJOR) {
-                                const uint32_t a_kgs16 = (BM * 2 / 128) * 1024u, b_kgs16 = ((uint32_t)BN * 2 / 128) * 1024u;
-                                dac = smem_desc_sw128_mn(a_lo + j * 2 * a_kgs16, 1024u, a_kgs16, 2u);
-                                dbc = smem_desc_sw128_mn(b_lo + j * 2 * b_kgs16, 1024u, b_kgs16, 2u);
-                            } else {
-                                dac = dal;
-                                dbc = dbl;
-                            }
-                            umma<MODE>(tmem_d, dah, dbh, idesc, first);
-                            corr_a[j] = dac;
-                            corr_b[j] = dbc;
                         } else {
                             if (j == 0) umma<MODE>(tmem_d, dah, dbh, idesc, first);
                             else umma_acc<MODE>(tmem_d, dah, dbh, idesc);
                         }
-                    }
-                    if (MODE == MODE_TF32C) {      // the bf16 MMAs of the k-block go out together: one kind switch per k-block
-#pragma unroll
-                        for (int j = 0; j < CHUNKS / 2; ++j)
-                            if (j < ksteps) umma<MODE_BF16>(tmem_d, corr_a[j], corr_b[j], idesc16, 1u);
                     }
                     umma_commit(&empty_bar[s]);                       // smem stage reusable once these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full_bar[b]);
                 }
                 __syncwarp();
             }
-            if (g.prof && lane == 0 && t == 0) atomicAdd(g.prof + 13, (unsigned long long)(clock64() - kernel_t0));   // first item: all MMAs issued
+            if (GNN_PROF(g) && lane == 0 && t == 0) atomicAdd(GNN_PROF(g) + 13, (unsigned long long)(clock64() - kernel_t0));   // first item: all MMAs issued
         }
     };
 
@@ -1361,6 +1360,17 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             uint32_t it = 0, t = 0;
             for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) {
                 if (warp == 0) mma_item(item, t, it);
+                epi_item(item, t);
+            }
+        }
+    } else if constexpr (AGG) {
+        // warp 0 issues the MMAs of item i+1 (the other accumulator) before it joins the epilogue of item i, so the
+        // tensor pipe keeps running while the four warps drain an accumulator
+        if (warp < EPI_WARPS) {
+            uint32_t it = 0, t = 0;
+            if (warp == 0 && (int64_t)blockIdx.x < g.num_items) mma_item(blockIdx.x, 0, it);
+            for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x, ++t) {
+                if (warp == 0 && item + gridDim.x < g.num_items) mma_item(item + gridDim.x, t + 1, it);
                 epi_item(item, t);
             }
         }
@@ -1403,20 +1413,24 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
             it_mod = (it_mod + (uint32_t)num_kb) % (uint32_t)NS;
             for (int kb = kb_first; kb < num_kb; kb += NS, ++my_use) {
                 const uint32_t s = (uint32_t)pg, use = my_use;
-                const long long pt0 = g.prof ? clock64() : 0;
-                if (g.prof && p == 0 && pg == 0 && my_use == 0) atomicAdd(g.prof + 12, (unsigned long long)(pt0 - kernel_t0));   // set-up until the first k-block
+                const long long pt0 = GNN_PROF(g) ? clock64() : 0;
+                if (GNN_PROF(g) && p == 0 && pg == 0 && my_use == 0) atomicAdd(GNN_PROF(g) + 12, (unsigned long long)(pt0 - kernel_t0));   // set-up until the first k-block
                 const int64_t kbase = k_begin + (int64_t)kb * KBR;
                 // K-major activation tiles: the global loads go out before the wait for the ring stage
                 ATile<MODE, SCALED> at;
-                ATmemRow ar;
-                if constexpr (!MN_MAJOR) {
-                    if constexpr (A_TMEM) load_a_tmem<SCALED>(aop, grp, m0 + (warp & 3) * 32 + lane, kbase, k_end, ar);
+                bool agg_kb = false;           // this k-block holds aggregates computed here (warp-uniform)
+                if constexpr (AGG) agg_kb = kbase >= ag.xpad;
+                if constexpr (AGG) {
+                    if (agg_kb) agg_compute(ag, grp, m0, g.M, (int)((kbase - ag.xpad) >> 5), p, at.v);
                     else load_a_seg<MODE, SCALED>(aop, grp, m0, kbase, k_end, p, at);
+                } else if constexpr (!MN_MAJOR) {
+                    load_a_seg<MODE, SCALED>(aop, grp, m0, kbase, k_end, p, at);
                 }
+                if (GNN_PROF(g) && p == 0 && agg_kb) atomicAdd(GNN_PROF(g) + 15, (unsigned long long)(clock64() - pt0));   // gather + reduce
                 long long pt1 = 0;
                 auto wait_stage = [&]() {
                     if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1);
-                    pt1 = g.prof ? clock64() : 0;
+                    pt1 = GNN_PROF(g) ? clock64() : 0;
                 };
                 // the fp32 MN-major producers call wait_stage themselves, between their load and store phases
                 if constexpr (!(MN_MAJOR && tf32_like(MODE) && !PACKED)) wait_stage();
@@ -1429,11 +1443,9 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         mbar_expect_tx(&full_bar[s], bytes);
                         bulk_g2s(stage + PARTS * a_plane, packed_b + tile_idx * bytes, bytes, &full_bar[s]);
                     }
-                    if constexpr (A_TMEM) {
-                        tc_fence_after();          // the MMAs that read this TMEM stage have retired (empty barrier)
-                        const uint32_t q = (uint32_t)(warp & 3);      // TMEM lane quarter this warp may access
-                        store_a_tmem<SCALED>(tmem_base + a_tmem_col0 + s * A_TMEM_STAGE_COLS + ((q * 32u) << 16), ar);
-                        tc_fence_before();
+                    if constexpr (AGG) {
+                        if (agg_kb) agg_store(ag, grp, m0, g.M, (int)((kbase - ag.xpad) >> 5), p, stage, a_plane, at.v);
+                        else store_a_seg<MODE, SCALED>(stage, a_plane, p, at);
                     } else {
                         store_a_seg<MODE, SCALED>(stage, a_plane, p, at);
                     }
@@ -1452,17 +1464,22 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     produce_mn_seg<MODE, false>(bl, grp, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p,
                                                 nullptr, KBR);
                 } else {
-                    store_a_seg<MODE, SCALED>(stage, a_plane, p, at);
+                    if constexpr (AGG) {
+                        if (agg_kb) agg_store(ag, grp, m0, g.M, (int)((kbase - ag.xpad) >> 5), p, stage, a_plane, at.v);
+                        else store_a_seg<MODE, SCALED>(stage, a_plane, p, at);
+                    } else {
+                        store_a_seg<MODE, SCALED>(stage, a_plane, p, at);
+                    }
                     produce_tile<MODE>(bl, stage + PARTS * a_plane, b_plane, BN, (int64_t)n0, kbase, k_end, p);
                 }
-                const long long pt2 = g.prof ? clock64() : 0;
+                const long long pt2 = GNN_PROF(g) ? clock64() : 0;
                 fence_async_smem();                                 // generic-proxy writes -> async (tensor core) proxy
                 mbar_arrive(&full_bar[s]);
-                if (g.prof && p == 0) {
-                    atomicAdd(g.prof + 0, (unsigned long long)(pt1 - pt0));     // wait for a free stage
-                    atomicAdd(g.prof + 1, (unsigned long long)(pt2 - pt1));     // load + convert + store
-                    atomicAdd(g.prof + 2, (unsigned long long)(clock64() - pt2));   // fence + arrive
-                    atomicAdd(g.prof + 3, 1ull);
+                if (GNN_PROF(g) && p == 0) {
+                    atomicAdd(GNN_PROF(g) + 0, (unsigned long long)(pt1 - pt0));     // wait for a free stage
+                    atomicAdd(GNN_PROF(g) + 1, (unsigned long long)(pt2 - pt1));     // load + convert + store
+                    atomicAdd(GNN_PROF(g) + 2, (unsigned long long)(clock64() - pt2));   // fence + arrive
+                    atomicAdd(GNN_PROF(g) + 3, 1ull);
                 }
             }
             if constexpr (MN_MAJOR) {
@@ -1500,21 +1517,24 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
     tc_fence_before();
     __syncthreads();
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, g.tmem_cols);
-    if (g.prof && tid == 0) {
-        atomicAdd(g.prof + 9, (unsigned long long)(clock64() - kernel_t0));
-        atomicAdd(g.prof + 10, 1ull);
+    if (GNN_PROF(g) && tid == 0) {
+        atomicAdd(GNN_PROF(g) + 9, (unsigned long long)(clock64() - kernel_t0));
+        atomicAdd(GNN_PROF(g) + 10, 1ull);
     }
 }
 
 // ------------------------------------------------------------------ host side
 static const size_t kSmemLimit = 232448;     // 227 KB opt-in maximum per CTA
-static unsigned long long* g_prof = nullptr; // debug only: per-role cycle counters of the next launches
+#ifdef GNN_B200_PROFILE
+static unsigned long long* g_prof = nullptr; // debug build only: per-role cycle counters of the next launches
+#endif
 
 // BL: K-major weight functor (packed through pack_ws when possible) or, for MN_MAJOR, a SegOperand
-template <int MODE, bool MN_MAJOR = false, bool SCALED = false, class BL, class EP>
+template <int MODE, bool MN_MAJOR = false, bool SCALED = false, class BL, class EP, class AG = NoAgg>
 static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN, int64_t K, int64_t k_chunk, int splits,
                   int groups, cudaStream_t st, void* pack_ws = nullptr, int64_t pack_ws_bytes = 0,
-                  ColSum colsum = ColSum{nullptr, 0, 0, 0, 1}) {
+                  ColSum colsum = ColSum{nullptr, 0, 0, 0, 1}, AG ag = AG{}) {
+    constexpr bool AGG = !std::is_same<AG, NoAgg>::value;
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     if (BN % 16 != 0 || BN < 16 || BN > 256) return GNN_ERR_UNSUPPORTED;
     constexpr int parts = tf32_like(MODE) ? 2 : 1;
@@ -1537,7 +1557,11 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
     while ((int)cols < 2 * BN) cols <<= 1;
     g.tmem_cols = cols;
     g.colsum = colsum;
+#ifdef GNN_B200_PROFILE
     g.prof = g_prof;
+#else
+    g.prof = nullptr;
+#endif
     g.epi_stage_off = 0;
     size_t smem = (size_t)stages * stage_bytes + fixed;
     if constexpr (EP::kStaged && !MN_MAJOR) {
@@ -1551,10 +1575,11 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
 
     if constexpr (MN_MAJOR) {
         if ((BN & (BN - 1)) != 0 || BN < (MODE == MODE_TF32X3 ? 32 : 64)) return GNN_ERR_UNSUPPORTED;   // whole 128-byte groups
+        if constexpr (AGG) return GNN_ERR_UNSUPPORTED;
         auto kern = gemm_tc_kernel<MODE, false, true, SCALED, BL, EP>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr);
+        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr, NoAgg{});
     } else {
         // weights (B) are packed once per call when a workspace is given and the M loop re-uses them
         const int num_kb = (int)gnn_ceil_div(K, kb_elems);
@@ -1565,36 +1590,16 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             dim3 pgrid((unsigned)(num_kb * ((BN + PACK_ROWS - 1) / PACK_ROWS)), (unsigned)g.n_tiles, (unsigned)groups);
             pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
                                                                           reinterpret_cast<uint8_t*>(pack_ws));
-            if constexpr (MODE == MODE_TF32X3) {
-                // activation operand in tensor memory: 2 accumulators (<= 256 columns) + 4 ring stages x 64 columns
-                // opt-in (GNN_B200_TMEM_A=1): correct (same tests) but not faster on the shapes of this model - the TS-mode
-                // MMAs and the tcgen05.st traffic cost what the saved shared-memory reads gain (5.89 vs 5.83 ms/step)
-                static const bool tmem_a_on = getenv("GNN_B200_TMEM_A") && atoi(getenv("GNN_B200_TMEM_A")) == 1;
-                bool aligned = true;       // k-block aligned segments (one segment per 32-column k-block)
-                for (int sg = 0; sg < aop.nseg; ++sg)
-                    aligned = aligned && (aop.seg[sg].start % kb_elems == 0) && (aop.seg[sg].width % kb_elems == 0);
-                if (tmem_a_on && BN <= 128 && aligned) {
-                    Geom ga = g;
-                    ga.stages = PROD_GROUPS;
-                    ga.tmem_cols = 512;
-                    const size_t smem_a = (size_t)PROD_GROUPS * parts * BN * ROW_BYTES + fixed;
-                    auto kern_a = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, true>;
-                    cudaError_t ea = cudaFuncSetAttribute(kern_a, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
-                    if (ea != cudaSuccess) return (int)ea;
-                    kern_a<<<(unsigned)grid, cta_threads(false), smem_a, st>>>(aop, bl, ep, ga,
-                                                                              reinterpret_cast<const uint8_t*>(pack_ws));
-                    return gnn_launch_status();
-                }
-            }
-            auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP>;
+            auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            kern<<<(unsigned)grid, cta_threads(false), smem, st>>>(aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws));
+            kern<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g,
+                                                                        reinterpret_cast<const uint8_t*>(pack_ws), ag);
         } else {
-            auto kern = gemm_tc_kernel<MODE, false, false, SCALED, BL, EP>;
+            auto kern = gemm_tc_kernel<MODE, false, false, SCALED, BL, EP, AG>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            kern<<<(unsigned)grid, cta_threads(false), smem, st>>>(aop, bl, ep, g, nullptr);
+            kern<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g, nullptr, ag);
         }
     }
     return gnn_launch_status();
@@ -1640,7 +1645,6 @@ using namespace tc;
 #define DISPATCH_MODE(precision, CALL)                         \
     do {                                                       \
         if ((precision) == 0) { constexpr int MODE = MODE_TF32X3; CALL; } \
-        else if ((precision) == 1) { constexpr int MODE = MODE_TF32C; CALL; } \
         else if ((precision) == 2) { constexpr int MODE = MODE_BF16; CALL; } \
         else return GNN_ERR_BAD_ARG;                           \
     } while (0)
@@ -1715,34 +1719,6 @@ extern "C" int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X
     });
 }
 
-// column sums (bias gradients): db[n] += sum_i dY[i, n]
-__global__ void colsum_kernel(const float* __restrict__ dY, int64_t lddy, int64_t M, int N, float* db) {
-    __shared__ float sm[8][33];
-    const int n = blockIdx.x * 32 + threadIdx.x;
-    const int64_t chunk = (M + gridDim.y - 1) / gridDim.y;
-    const int64_t r0 = (int64_t)blockIdx.y * chunk, r1 = min(M, r0 + chunk);
-    float acc = 0.f;
-    if (n < N)
-        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += __ldg(dY + r * lddy + n);
-    sm[threadIdx.y][threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.y == 0 && n < N) {
-        float t = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
-        atomicAdd(db + n, t);
-    }
-}
-extern "C" int gnn_colsum_accum(const float* dY, int64_t lddy, int64_t M, int N, float* db, void* stream) {
-    if (M < 0 || N < 1) return GNN_ERR_BAD_ARG;
-    if (M == 0) return 0;
-    int64_t ysplit = gnn_ceil_div(M, 2048);
-    if (ysplit > 1024) ysplit = 1024;
-    dim3 grid((unsigned)gnn_ceil_div(N, 32), (unsigned)ysplit);
-    colsum_kernel<<<grid, dim3(32, 8), 0, gnn_stream(stream)>>>(dY, lddy, M, N, db);
-    return gnn_launch_status();
-}
-
 // ------------------------------------------------------------------ PNA post stage on tensor cores
 static SegOperand seg_cat5(const float* x, const float* A, int64_t n, int F, int towers) {   // [x | A_t], group = tower
     SegOperand op{};
@@ -1774,7 +1750,7 @@ static int post_fwd_impl(const float* x, const float* A, const float* scal, cons
     if (FoP > 64) FoP = 64;
     const int tiles = (F_out + FoP - 1) / FoP;
     SegOperand aop = seg_cat5(x, A, n, F, towers);
-    VPostWeight bl{wpost, wpost_tower_stride, F, F_out, FoP, vx};
+    VPostWeight bl{wpost, wpost_tower_stride, F, F_out, FoP, vx, 0};
     EPostCombine ep{O, scal, bpost, bpost_tower_stride, F_out, FoP, towers, 0, act,
                     (F_out % 4 == 0) && is_vec(O, 0) && is_vec(bpost, bpost_tower_stride)};
     DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, tiles * 3 * FoP, 3 * FoP, 5 * (int64_t)F,
@@ -1797,6 +1773,39 @@ extern "C" int gnn_tc_pna_postf_fwd(const float* x, const float* A, const float*
     REQUIRE_VEC(Vx, F);
     return post_fwd_impl(x, A, scal, Vx, wpost, wpost_tower_stride, bpost, bpost_tower_stride, n, F, F_out, towers, act,
                          O, precision, pack_ws, pack_ws_bytes, stream);
+}
+
+// Folded post forward with the aggregates computed by the GEMM's producers (AggSrc): Psrc / tab / CSR in, O out; the
+// aggregates reach HBM only when A_out != NULL (training).  TF32x3 only; F % 8 == 0.
+extern "C" int gnn_tc_pna_postf_agg_fwd(const float* x, const float* Psrc, const float* tab, const int32_t* rowptr,
+                                        const int32_t* col_src, const uint8_t* col_code, const float* scal,
+                                        const float* Vx, const float* wpost, int64_t wpost_tower_stride,
+                                        const float* bpost, int64_t bpost_tower_stride, int64_t n, int F, int F_out,
+                                        int towers, int act, float* O, float* A_out, int precision, void* pack_ws,
+                                        int64_t pack_ws_bytes, void* stream) {
+    if (n < 0 || F < 8 || (F & 7) || F_out < 1 || towers < 1 || Vx == nullptr) return GNN_ERR_BAD_ARG;
+    if (precision != 0) return GNN_ERR_UNSUPPORTED;
+    const int C = towers * F;
+    if ((int64_t)n * C >= (1ll << 31)) return GNN_ERR_TOO_LARGE;        // 32-bit row offsets in the gather
+    REQUIRE_VEC(x, F);
+    REQUIRE_VEC(Psrc, (int64_t)C);
+    REQUIRE_VEC(tab, (int64_t)C);
+    REQUIRE_VEC(Vx, F);
+    if (A_out != nullptr) REQUIRE_VEC(A_out, 4 * (int64_t)F);
+    int FoP = (F_out + 15) / 16 * 16;
+    if (FoP > 64) FoP = 64;
+    const int tiles = (F_out + FoP - 1) / FoP;
+    if (tiles > 1 && A_out != nullptr) return GNN_ERR_UNSUPPORTED;      // every n tile would store the aggregates again
+    const int xpad = (F + 31) / 32 * 32;
+    SegOperand aop = seg_plain(x, F, n, F);
+    VPostWeight bl{wpost, wpost_tower_stride, F, F_out, FoP, Vx, xpad};
+    EPostCombine ep{O, scal, bpost, bpost_tower_stride, F_out, FoP, towers, 0, act,
+                    (F_out % 4 == 0) && is_vec(O, 0) && is_vec(bpost, bpost_tower_stride)};
+    AggSrc ag{Psrc, tab, rowptr, col_src, col_code, A_out, F, C, xpad};
+    const int64_t K = xpad + 4 * (int64_t)F;
+    return (launch<MODE_TF32X3, false, false>(aop, bl, ep, n, tiles * 3 * FoP, 3 * FoP, K, K, 1, towers,
+                                               gnn_stream(stream), pack_ws, pack_ws_bytes,
+                                               ColSum{nullptr, 0, 0, 0, 1}, ag));
 }
 
 extern "C" int gnn_tc_pna_post_dgrad(const float* dO, const float* scal, const float* wpost, int64_t wpost_tower_stride,
@@ -2032,13 +2041,16 @@ static int post_wgrad_impl(const float* dO, const float* x, const float* A, cons
     return 0;
 }
 
-// debug: 16 x uint64 device buffer that receives per-role cycle counters of subsequent tensor-core GEMM launches
-// (NULL disables).  [0] producer wait-for-stage, [1] produce, [2] fence+arrive, [3] #k-blocks (per group leader),
-// [4] MMA wait-for-operands, [5] #k-blocks, [6] epilogue wait, [7] epilogue work, [8] #items, [9] CTA cycles, [10] #CTAs
+#ifdef GNN_B200_PROFILE
+// debug build only: 16 x uint64 device buffer that receives per-role cycle counters of subsequent tensor-core GEMM
+// launches (NULL disables).  [0] producer wait-for-stage, [1] produce, [2] fence+arrive, [3] #k-blocks (per group
+// leader), [4] MMA wait-for-operands, [5] #k-blocks, [6] epilogue wait, [7] epilogue work, [8] #items, [9] CTA cycles,
+// [10] #CTAs
 extern "C" int gnn_tc_set_profile_buffer(void* buf) {
     tc::g_prof = reinterpret_cast<unsigned long long*>(buf);
     return 0;
 }
+#endif
 
 extern "C" int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const float* scal, int64_t n,
                                      int F, int F_out, int towers, float* dwpost, int64_t wpost_tower_stride,

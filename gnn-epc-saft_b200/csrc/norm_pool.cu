@@ -515,17 +515,6 @@ extern "C" int gnn_fill_zero(void* ptr, int64_t bytes, void* stream) {
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-__global__ void add_inplace_kernel(float* __restrict__ acc, const float* __restrict__ src, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) acc[i] += __ldg(src + i);
-}
-extern "C" int gnn_add_inplace(float* acc, const float* src, int64_t numel, void* stream) {
-    if (numel <= 0) return 0;
-    add_inplace_kernel<<<ew_grid(numel, 256), 256, 0, gnn_stream(stream)>>>(acc, src, numel);
-    return gnn_launch_status();
-}
-
 __global__ void relu_bwd_kernel(float* __restrict__ dY, const float* __restrict__ Yact, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;

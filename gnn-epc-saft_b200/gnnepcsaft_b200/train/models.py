@@ -34,6 +34,12 @@ DEFAULT_MATMUL = "tf32x3"
 # source projections only.  Needs pre_layers == 1, self-loops (every node has an in-edge) and a tensor-core matmul mode;
 # GNN_B200_FOLD=0 keeps the [Pdst | Psrc] formulation everywhere.
 FOLD_DST = os.environ.get("GNN_B200_FOLD", "1") != "0"
+# Compute the aggregates inside the post GEMM's operand producers (gnn_tc_pna_postf_agg_fwd) instead of in a separate
+# kernel that writes them to HBM (folded formulation + TF32x3 only).  "infer" (default): forward passes that keep
+# nothing for a backward pass - the aggregates then never reach HBM (154 vs 162 us per layer on 4096 graphs, 0.1 GB
+# instead of 0.5 GB of DRAM traffic); "all": training forwards too (the kernel then also stores the aggregates:
+# 183 us, slower than the two-kernel path); "off": never.
+FUSE_AGG = os.environ.get("GNN_B200_FUSE_AGG", "infer")
 
 
 @dataclasses.dataclass
@@ -155,7 +161,7 @@ def _c(name, *args):
 
 
 # dense-stage dispatch: which kernel family runs the Linear layers
-MATMUL_MODES = {"simt": -1, "tf32x3": 0, "tf32c": 1, "bf16": 2}
+MATMUL_MODES = {"simt": -1, "tf32x3": 0, "bf16": 2}
 
 
 def _al(t, *dims):
@@ -366,7 +372,6 @@ class PNAPCSAFT(nn.Module):
         self._arena_offsets: List[int] = []
         self._row_off = None
         # dense stages: "tf32x3" = tcgen05 with fp32 operands split into tf32 hi+lo (fp32-level accuracy),
-        # "tf32c" = tf32 hi*hi + one K-doubled bf16 MMA for the cross terms (2 instead of 3 MMAs, ~2e-6 per product),
         # "bf16" = tcgen05 bf16 operands / fp32 accumulate (torch "medium" matmul precision, which the
         # reference itself sets at train.py:319), "simt" = plain fp32 FMA kernels
         self.matmul_precision = os.environ.get("GNN_B200_MATMUL", DEFAULT_MATMUL)
@@ -612,9 +617,14 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
                 b = conv.pre_nns[t][0].bias
                 _lin_fwd(mm_proj, x, H, w, 3 * F, b, n, F, F, 0, P[:, t * F:], 2 * C)
                 _lin_fwd(mm_proj, x, H, w[:, F:], 3 * F, None, n, F, F, 0, P[:, C + t * F:], 2 * C)
-        A = torch.empty(n, T * 4 * F, **f32)
+        fuse_agg = (fold and mm == 0 and n > 0 and Fo <= 64 and
+                    (FUSE_AGG == "all" or (FUSE_AGG == "infer" and not save)))
+        # the aggregates only reach HBM when the backward pass needs them
+        A = torch.empty(n, T * 4 * F, **f32) if (save or not fuse_agg) else None
         rec.P = P
-        if fold:
+        if fuse_agg:
+            pass                                    # aggregated by the producers of the post GEMM below
+        elif fold:
             _c("gnn_pna_aggregate_src_fwd", P, tab[l], g.rowptr, g.col_src, g.col_code, n, T, F, A)
         elif pp.pre_layers == 1:
             _c("gnn_pna_aggregate_fwd", P, tab[l], g.rowptr, g.col_src, g.col_code, n, T, F, A)
@@ -640,7 +650,12 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         rec.scal = scal
         # post_nns (virtual 13F concat) -> lin
         O = torch.empty(n, H, **f32)
-        if fold:
+        if fuse_agg:
+            ws = _pack_ws(dev)
+            _c("gnn_tc_pna_postf_agg_fwd", x, P, tab[l], g.rowptr, g.col_src, g.col_code, scal, rec.Vx,
+               conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T,
+               1 if pp.post_layers > 1 else 0, O, A, mm, ws, ws.numel())
+        elif fold:
             ws = _pack_ws(dev)
             _c("gnn_tc_pna_postf_fwd", x, A, scal, rec.Vx, conv.post_nns[0][0].weight, tower_stride_post,
                conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O, mm, ws,

@@ -10,7 +10,8 @@
  *  - the caller owns all memory; nothing is allocated inside; workspaces are sized by the
  *    *_workspace_bytes() queries
  *  - launches are enqueued on `stream` (a cudaStream_t passed as void*) and return
- *    immediately; no global state, so calls are thread-safe per stream
+ *    immediately; no global state and no environment variables are read, so calls are
+ *    thread-safe per stream (the only cache is the SM count per device ordinal)
  *  - return value: 0 = ok, >0 = cudaError_t of the launch, <0 = argument error
  *    (GNN_ERR_*); gnn_error_string() renders either
  *  - float tensors are fp32 row-major; `ld*` are leading dimensions in elements
@@ -240,12 +241,10 @@ int gnn_pna_post_wgrad(const float* dO, const float* x, const float* A, const fl
 /* ---------------------------------------------------------------- dense stages (tcgen05 / TMEM)
  * The same contractions on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
  * `precision`: 0 = TF32x3 (fp32 operands split into tf32 hi+lo, 3 MMAs: fp32-level accuracy, the
- * parity path), 1 = TF32+BF16C (the hi*hi product on the tf32 path plus one bf16 MMA whose doubled K
- * carries both cross terms: 2 MMAs, ~2^-19 relative error per product, still inside the 1e-5 parity
- * bar), 2 = BF16 operands, fp32 accumulate (the reference's own
+ * parity path), 2 = BF16 operands, fp32 accumulate (the reference's own
  * torch.set_float32_matmul_precision("medium"), train.py:319).  Semantics equal the gnn_linear_* /
  * gnn_pna_post_* entry points above (bias gradients are column sums taken by the operand producers of the
- * weight-gradient kernels; gnn_colsum_accum is the stand-alone version).  Operands must be 128-bit
+ * weight-gradient kernels).  Operands must be 128-bit
  * accessible (16-byte aligned, leading dimensions and K / N multiples of 4), else GNN_ERR_UNSUPPORTED.
  * gnn_tc_pna_post_dgrad: dx may be NULL (then only gA is produced and the x part goes through
  * gnn_tc_pna_dx_dgrad).
@@ -261,7 +260,6 @@ int gnn_tc_linear_dgrad(const float* dY, int64_t lddy, const float* W, int64_t l
                         int64_t pack_ws_bytes, void* stream);
 int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X, int64_t ldx, int64_t M, int N,
                         int K, float* dW, int64_t lddw, float* db, int precision, void* stream);
-int gnn_colsum_accum(const float* dY, int64_t lddy, int64_t M, int N, float* db, void* stream);
 int gnn_tc_pna_post_fwd(const float* x, const float* A, const float* scal, const float* wpost,
                         int64_t wpost_tower_stride, const float* bpost, int64_t bpost_tower_stride,
                         int64_t num_nodes, int F, int F_out, int towers, int act, float* O,
@@ -274,10 +272,6 @@ int gnn_tc_pna_post_wgrad(const float* dO, const float* x, const float* A, const
                           int64_t num_nodes, int F, int F_out, int towers, float* dwpost,
                           int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride,
                           int precision, void* stream);
-
-/* Debug aid: 16 x uint64 device buffer that receives per-role cycle counters (producers / MMA issuer /
- * epilogue) of subsequent tensor-core GEMM launches; NULL disables.  Process-global, not for production. */
-int gnn_tc_set_profile_buffer(void* buf);
 
 /* Fused projection stage of PNAConv (pre_nns[t][0], first two thirds of its input), all towers in one
  * launch.  wpre / bpre point at tower 0 of the layer, towers are *_tower_stride floats apart.
@@ -309,6 +303,19 @@ int gnn_tc_pna_postf_fwd(const float* x, const float* A, const float* scal, cons
                          const float* wpost, int64_t wpost_tower_stride, const float* bpost,
                          int64_t bpost_tower_stride, int64_t num_nodes, int F, int F_out, int towers, int act,
                          float* O, int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream);
+/* postf_fwd with the aggregates computed inside the GEMM (replaces the pair gnn_pna_aggregate_src_fwd +
+ * gnn_tc_pna_postf_fwd, i.e. PyG MessagePassing._collect / message / MultiAggregation + post_nns of PNAConv at
+ * reference models.py:128, in ONE kernel): the operand producers gather Psrc[src] + tab[code] over each node's CSR
+ * segment, reduce mean / min / max / std in registers (the arithmetic of gnn_pna_aggregate_src_fwd, bit-identical)
+ * and write them straight into the shared-memory operand tiles, so the [N, T, 4, F] aggregates are not read from
+ * HBM and - with A_out == NULL (inference) - never written either.  A_out != NULL (training) receives them for the
+ * backward pass.  precision must be 0 (TF32x3); F % 8 == 0. */
+int gnn_tc_pna_postf_agg_fwd(const float* x, const float* Psrc, const float* tab, const int32_t* rowptr,
+                             const int32_t* col_src, const uint8_t* col_code, const float* scal,
+                             const float* Vx, const float* wpost, int64_t wpost_tower_stride,
+                             const float* bpost, int64_t bpost_tower_stride, int64_t num_nodes, int F,
+                             int F_out, int towers, int act, float* O, float* A_out, int precision,
+                             void* pack_ws, int64_t pack_ws_bytes, void* stream);
 int gnn_tc_pna_postf_wgrad(const float* dO, const float* x, const float* A, const float* scal,
                            int64_t num_nodes, int F, int F_out, int towers, float* dwpost,
                            int64_t wpost_tower_stride, float* dbpost, int64_t bpost_tower_stride, float* dVx,
@@ -371,8 +378,6 @@ int gnn_adamw_amsgrad_step(float* param, const float* grad, float* exp_avg, floa
                            int64_t t0_restart, float grad_scale, void* stream);
 int gnn_step_increment(int64_t* step_count, void* stream);
 int gnn_fill_zero(void* ptr, int64_t bytes, void* stream);
-/* out[i] = a[i] + b[i] (fp32) — skip-connection gradient merge */
-int gnn_add_inplace(float* acc, const float* src, int64_t numel, void* stream);
 
 #ifdef __cplusplus
 }

@@ -436,10 +436,6 @@ def gnn_tc_linear_wgrad(dY, lddy, X, ldx, M, N, K, dW, lddw, db, precision, stre
     gnn_linear_wgrad(dY, lddy, X, ldx, M, N, K, dW, lddw, db)
 
 
-def gnn_colsum_accum(dY, lddy, M, N, db, stream=None):
-    _flat(db, N).add_(_mat(dY, M, N, lddy).sum(0))
-
-
 def gnn_tc_pna_post_fwd(x, A, scal, wpost, wts, bpost, bts, n, f, f_out, towers, act, O, precision, pack_ws=None,
                         pack_ws_bytes=0, stream=None):
     gnn_pna_post_fwd(x, A, scal, wpost, wts, bpost, bts, n, f, f_out, towers, act, O)
@@ -509,6 +505,14 @@ def gnn_tc_pna_postf_fwd(x, A, scal, Vx, wpost, wts, bpost, bts, n, f, f_out, to
         w = torch.cat([v[t, 0], v[t, 1], v[t, 2], wp[:, f:]], dim=1)
         o = _postf_cat(x, A, scal, n, f, towers, t) @ w.t() + _flat(bpost, f_out, t * bts)
         O[:n, t * f_out:(t + 1) * f_out] = o.clamp(min=0) if act else o
+
+
+def gnn_tc_pna_postf_agg_fwd(x, Psrc, tab, rowptr, col_src, col_code, scal, Vx, wpost, wts, bpost, bts, n, f, f_out, towers,
+                             act, O, A_out, precision, pack_ws=None, pack_ws_bytes=0, stream=None):
+    """aggregate (gnn_pna_aggregate_src_fwd) + folded post forward (gnn_tc_pna_postf_fwd) in one call."""
+    A = A_out if A_out is not None else torch.zeros(n, towers * 4 * f, dtype=x.dtype)
+    gnn_pna_aggregate_src_fwd(Psrc, tab, rowptr, col_src, col_code, n, towers, f, A)
+    gnn_tc_pna_postf_fwd(x, A, scal, Vx, wpost, wts, bpost, bts, n, f, f_out, towers, act, O, precision)
 
 
 def gnn_tc_pna_postf_wgrad(dO, x, A, scal, n, f, f_out, towers, dwpost, wts, dbpost, bts, dVx, precision,
@@ -654,11 +658,6 @@ def gnn_fill_zero(ptr, nbytes, stream=None):
     ptr.view(torch.uint8).reshape(-1)[:nbytes] = 0
 
 
-def gnn_add_inplace(acc, src, numel, stream=None):
-    _flat(acc, numel).add_(_flat(src, numel))
-
-
-# ------------------------------------------------------------------ test hook
 def install(monkeypatch, lib_module, models_module):
     """Route the product's ctypes dispatcher to this module (CPU host-logic tests only)."""
     here = globals()

@@ -96,9 +96,48 @@ def zero_grad_bias_mask(model):
 # bf16 node-update GEMMs (matmul_precision = "bf16", the reference's own torch "medium" matmul precision,
 # train.py:319): (forward max-normalised error vs the fp64 oracle, gradient global rel-L2) bars = 2 x the values
 # measured on B200 (listed in DESIGN.md section 2); the projection GEMM stays TF32x3 in this mode.
+# Measured on B200 (round 2): default 7.5e-3 / 0.224, pre2_post2 1.1e-2 / 0.174, wide_small 7.4e-3 / 0.216,
+# wide (H 256, L 6) 2.4e-2 (train-mode forward) / 0.300.  The gradient figures are what bf16 operand rounding does to
+# THIS architecture (min / max / std selections flip): the fp64 oracle with the same operands rounded to bf16 measures
+# 0.218 / 0.131 / 0.189 / 0.242 - the tests additionally require the CUDA path to stay within 2x that floor.
 BF16_BARS = {
-    "default": (3e-2, 3e-1),
-    "pre2_post2": (3e-2, 3e-1),
-    "wide_small": (3e-2, 3e-1),
-    "wide": (3e-2, 3e-1),
+    "default": (1.5e-2, 4.5e-1),
+    "pre2_post2": (2.2e-2, 3.5e-1),
+    "wide_small": (1.5e-2, 4.4e-1),
+    "wide": (5e-2, 6e-1),
 }
+
+
+class bf16_operand_rounding:
+    """Context manager: the Linear layers that `matmul_precision = "bf16"` runs with bf16 operands (post_nns, lin,
+    the extra pre_nns layers and the MLP head - not the first pre_nns layer / edge_encoder, whose projections stay
+    TF32x3) round their input and weight to bf16 and accumulate in the module's dtype.  Applied to the fp64 oracle
+    this isolates the effect of bf16 operand rounding on the reference arithmetic: the floor any bf16-operand
+    implementation sits on, against which the CUDA bf16 path is held (factor 2)."""
+
+    def __init__(self, model):
+        self.model, self.saved = model, []
+
+    @staticmethod
+    def _rounded(lin):
+        def fwd(x):
+            xr = x.to(torch.bfloat16).to(x.dtype)
+            wr = lin.weight.to(torch.bfloat16).to(lin.weight.dtype)
+            return torch.nn.functional.linear(xr, wr, lin.bias)
+        return fwd
+
+    def __enter__(self):
+        for name, mod in self.model.named_modules():
+            if not isinstance(mod, torch.nn.Linear):
+                continue
+            first_pre = ".pre_nns." in name and name.endswith(".0")
+            if "edge_encoder" in name or first_pre:
+                continue
+            self.saved.append(mod)
+            mod.forward = self._rounded(mod)
+        return self.model
+
+    def __exit__(self, *exc):
+        for mod in self.saved:
+            del mod.forward
+        return False

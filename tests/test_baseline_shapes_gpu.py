@@ -15,7 +15,7 @@ from gnnepcsaft_b200.data.synth import batch_from_packed, make_packed_graphs
 from gnnepcsaft_b200.train import models as M
 from gnnepcsaft_b200.train.utils import wide_config
 from oracle import pna_oracle as O
-from tests.helpers import BF16_BARS, cfg, flat_grads, make_pair, zero_grad_bias_mask
+from tests.helpers import BF16_BARS, bf16_operand_rounding, cfg, flat_grads, make_pair, zero_grad_bias_mask
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -83,6 +83,8 @@ def test_config5_wide_model_skewed_graphs(precision):
         mod.eval()
     with torch.no_grad():
         y64, y32, y = o64(batch), o32(batch), m(batch.to(DEV))
+        with bf16_operand_rounding(o64):        # (before any train-mode pass touches the running statistics)
+            f_e = _norm_err(o64(batch), y64)
     e_m, e_o = _norm_err(y, y64), _norm_err(y32, y64)
     for mod in (o32, o64, m):
         mod.train()
@@ -97,9 +99,20 @@ def test_config5_wide_model_skewed_graphs(precision):
     print(f"config5 wide/{precision}: eval fwd {e_m:.2e} (oracle32 {e_o:.2e}); train fwd {t_m:.2e} (oracle32 {t_o:.2e}); "
           f"loss {l:.6f} vs {l64:.6f}; grad rel-L2 {rel:.2e} (oracle32 {rel_o:.2e})")
     if precision == "bf16":
+        # floor: the fp64 oracle with the same Linear operands rounded to bf16
+        with bf16_operand_rounding(o64):
+            ytb, _ = _train_pass(o64, batch, c.num_para)
+            f_t = _norm_err(ytb, yt64)
+            f_g = float((flat_grads(o64) - g64)[mask].norm() / g64[mask].norm())
+        print(f"config5 wide/bf16 floor (fp64 oracle, bf16-rounded operands): eval fwd {f_e:.2e}, train fwd {f_t:.2e}, "
+              f"grad rel-L2 {f_g:.2e}")
         fwd_bar, grad_bar = BF16_BARS["wide"]
         assert e_m <= fwd_bar and t_m <= fwd_bar and rel <= grad_bar
+        assert e_m <= 2 * f_e and t_m <= 2 * f_t and rel <= 2 * f_g, "bf16 path worse than 2x the operand-rounding floor"
     else:
         assert e_m <= max(1e-5, 2 * e_o + 1e-6)
         assert t_m <= max(2 * t_o, 2e-4)
-        assert rel <= max(2e-3, 2 * rel_o)
+        # the wide model's fp32-vs-fp64 gradient floor is set by min / max / std selection flips and is chaotic: on four
+        # variants of this config (with / without self-loops, post_layers 1 / 2, depth 2 / 6) the reference arithmetic in
+        # fp32 (oracle32) measured 0.9e-3 ... 4.2e-3 against fp64, the CUDA path 1.0e-3 ... 4.1e-3 (tools/grad_diag.py)
+        assert rel <= max(5e-3, 2 * rel_o)
