@@ -5,7 +5,10 @@
 #include "common.cuh"
 
 // ------------------------------------------------------------------ AtomEncoder forward
-__global__ void atom_embed_fwd_kernel(const int64_t* __restrict__ x, int64_t n, const float* __restrict__ tables,
+// IDX = int64_t (the reference's PyG batches) or uint8_t (compact batches of the device store: every OGB atom feature
+// is < 119)
+template <class IDX>
+__global__ void atom_embed_fwd_kernel(const IDX* __restrict__ x, int64_t n, const float* __restrict__ tables,
                                       const int* __restrict__ row_off, int total_rows, int H,
                                       float* __restrict__ out, int* err_flag) {
     const int H4 = H >> 2;
@@ -18,7 +21,7 @@ __global__ void atom_embed_fwd_kernel(const int64_t* __restrict__ x, int64_t n, 
     for (int k = 0; k < GNN_NUM_ATOM_FEATS; ++k) {
         int lo = __ldg(row_off + k);
         int hi = (k + 1 < GNN_NUM_ATOM_FEATS) ? __ldg(row_off + k + 1) : total_rows;
-        int64_t v = __ldg(x + i * GNN_NUM_ATOM_FEATS + k);
+        int64_t v = (int64_t)__ldg(x + i * GNN_NUM_ATOM_FEATS + k);
         if ((v < 0 || v >= hi - lo) && err_flag != nullptr && c == 0) atomicOr(err_flag, GNN_INPUT_ERR_ATOM_FEATURE);   // torch would raise IndexError
         int row = lo + (int)(v < 0 ? 0 : (v >= hi - lo ? hi - lo - 1 : v));
         float4 e = ldg4(tables + (int64_t)row * H + c);
@@ -27,21 +30,30 @@ __global__ void atom_embed_fwd_kernel(const int64_t* __restrict__ x, int64_t n, 
     st4(out + i * H + c, acc);
 }
 
-extern "C" int gnn_atom_embed_fwd(const int64_t* x, int64_t n, const float* tables, const int32_t* row_off,
-                                  int32_t total_rows, int hidden, float* out, int32_t* err_flag, void* stream) {
+template <class IDX>
+static int atom_embed_fwd_launch(const IDX* x, int64_t n, const float* tables, const int32_t* row_off, int32_t total_rows,
+                                 int hidden, float* out, int32_t* err_flag, void* stream) {
     if (n < 0 || hidden < 4 || (hidden & 3)) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
     int64_t work = n * (hidden >> 2);
-    atom_embed_fwd_kernel<<<(unsigned)gnn_ceil_div(work, 256), 256, 0, gnn_stream(stream)>>>(x, n, tables, row_off,
-                                                                                             total_rows, hidden, out, err_flag);
+    atom_embed_fwd_kernel<IDX><<<(unsigned)gnn_ceil_div(work, 256), 256, 0, gnn_stream(stream)>>>(
+        x, n, tables, row_off, total_rows, hidden, out, err_flag);
     return gnn_launch_status();
+}
+extern "C" int gnn_atom_embed_fwd(const int64_t* x, int64_t n, const float* tables, const int32_t* row_off,
+                                  int32_t total_rows, int hidden, float* out, int32_t* err_flag, void* stream) {
+    return atom_embed_fwd_launch(x, n, tables, row_off, total_rows, hidden, out, err_flag, stream);
+}
+extern "C" int gnn_atom_embed_u8_fwd(const uint8_t* x, int64_t n, const float* tables, const int32_t* row_off,
+                                     int32_t total_rows, int hidden, float* out, int32_t* err_flag, void* stream) {
+    return atom_embed_fwd_launch(x, n, tables, row_off, total_rows, hidden, out, err_flag, stream);
 }
 
 // ------------------------------------------------------------------ AtomEncoder backward
 // CTA-private copy of the (small) table gradient in shared memory, flushed once per CTA.
-template <bool SMEM>
+template <bool SMEM, class IDX>
 __global__ void __launch_bounds__(256)
-atom_embed_bwd_kernel(const int64_t* __restrict__ x, int64_t n, const float* __restrict__ dout,
+atom_embed_bwd_kernel(const IDX* __restrict__ x, int64_t n, const float* __restrict__ dout,
                       const int* __restrict__ row_off, int total_rows, int H, float* dtables) {
     extern __shared__ float s_tab[];
     if (SMEM) {
@@ -57,7 +69,7 @@ atom_embed_bwd_kernel(const int64_t* __restrict__ x, int64_t n, const float* __r
         if (lane < GNN_NUM_ATOM_FEATS) {
             int lo = __ldg(row_off + lane);
             int hi = (lane + 1 < GNN_NUM_ATOM_FEATS) ? __ldg(row_off + lane + 1) : total_rows;
-            int64_t v = __ldg(x + i * GNN_NUM_ATOM_FEATS + lane);
+            int64_t v = (int64_t)__ldg(x + i * GNN_NUM_ATOM_FEATS + lane);
             row = lo + (int)(v < 0 ? 0 : (v >= hi - lo ? hi - lo - 1 : v));
         }
         int rows[GNN_NUM_ATOM_FEATS];
@@ -78,15 +90,16 @@ atom_embed_bwd_kernel(const int64_t* __restrict__ x, int64_t n, const float* __r
     }
 }
 
-extern "C" int gnn_atom_embed_bwd(const int64_t* x, int64_t n, const float* dout, const int32_t* row_off,
-                                  int32_t total_rows, int hidden, float* dtables, void* stream) {
+template <class IDX>
+static int atom_embed_bwd_launch(const IDX* x, int64_t n, const float* dout, const int32_t* row_off, int32_t total_rows,
+                                 int hidden, float* dtables, void* stream) {
     if (n < 0 || hidden < 1) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
     cudaStream_t st = gnn_stream(stream);
     size_t smem = (size_t)total_rows * hidden * sizeof(float);
     int64_t blocks = gnn_ceil_div(n, 8 * 16);
     if (smem <= 200 * 1024) {
-        auto kern = atom_embed_bwd_kernel<true>;
+        auto kern = atom_embed_bwd_kernel<true, IDX>;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
@@ -102,9 +115,17 @@ extern "C" int gnn_atom_embed_bwd(const int64_t* x, int64_t n, const float* dout
         int64_t cap = (int64_t)gnn_sm_count() * 8;
         if (blocks > cap) blocks = cap;
         if (blocks < 1) blocks = 1;
-        atom_embed_bwd_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, n, dout, row_off, total_rows, hidden, dtables);
+        atom_embed_bwd_kernel<false, IDX><<<(unsigned)blocks, 256, 0, st>>>(x, n, dout, row_off, total_rows, hidden, dtables);
     }
     return gnn_launch_status();
+}
+extern "C" int gnn_atom_embed_bwd(const int64_t* x, int64_t n, const float* dout, const int32_t* row_off,
+                                  int32_t total_rows, int hidden, float* dtables, void* stream) {
+    return atom_embed_bwd_launch(x, n, dout, row_off, total_rows, hidden, dtables, stream);
+}
+extern "C" int gnn_atom_embed_u8_bwd(const uint8_t* x, int64_t n, const float* dout, const int32_t* row_off,
+                                     int32_t total_rows, int hidden, float* dtables, void* stream) {
+    return atom_embed_bwd_launch(x, n, dout, row_off, total_rows, hidden, dtables, stream);
 }
 
 // ------------------------------------------------------------------ bond-code table

@@ -407,3 +407,204 @@ extern "C" int gnn_collate_gather(const int64_t* ids, int64_t nb, const int64_t*
                                                             edge_attr, batch);
     return gnn_launch_status();
 }
+
+// ------------------------------------------------------------------ compact collate: store CSR -> batch CSR
+// The device store keeps ONE destination CSR over the whole dataset (built once by gnn_build_csr on the concatenated
+// graphs: no edge crosses a graph, so a graph's nodes / CSR slots are contiguous ranges).  A batch is then a pure
+// segment gather with re-based indices - no sort, no scan over edges - that emits what the model kernels consume
+// directly: uint8 atom features, int32 CSR, uint8 bond codes, node -> graph map, graph_ptr.  Replaces the PyG
+// DataLoader / Collater (reference train.py:74-79) AND add_self_loops + the scatter index handling (models.py:118-121)
+// for batches drawn from the store; the int64 PyG-layout path (gnn_collate_gather + gnn_build_csr) stays for batches
+// that arrive as PyG tensors.
+// Padding: the outputs are sized (pad_nodes, pad_slots) >= (N, E'); the surplus forms one extra graph (index B) of
+// isolated nodes that carry the surplus CSR slots as self-edges, so every batch of a shape bucket runs the same
+// launches (CUDA-graph replay).  valid = {N, B, E'} tells the BatchNorm kernels which rows are real.
+__global__ void __launch_bounds__(1024)
+compact_offsets_kernel(const int64_t* __restrict__ ids, int64_t nb, int64_t num_store_graphs,
+                       const int* __restrict__ node_off, const int* __restrict__ slot_off, int* __restrict__ nptr,
+                       int* __restrict__ sptr, int* err) {
+    __shared__ int wn[32], ws[32];
+    __shared__ int carry_n, carry_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        carry_n = 0;
+        carry_s = 0;
+        nptr[0] = 0;
+        sptr[0] = 0;
+    }
+    __syncthreads();
+    for (int64_t base = 0; base < nb; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        int cn = 0, cs = 0;
+        if (i < nb) {
+            int64_t g = ids[i];
+            if (g < 0 || g >= num_store_graphs) {
+                if (err) atomicOr(err, GNN_INPUT_ERR_BATCH_RANGE);
+                g = 0;
+            }
+            cn = node_off[g + 1] - node_off[g];
+            cs = slot_off[g + 1] - slot_off[g];
+        }
+        int sn = cn, ss = cs;                       // inclusive warp scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int tn = __shfl_up_sync(GNN_FULL_MASK, sn, o), ts = __shfl_up_sync(GNN_FULL_MASK, ss, o);
+            if (lane >= o) {
+                sn += tn;
+                ss += ts;
+            }
+        }
+        if (lane == 31) {
+            wn[warp] = sn;
+            ws[warp] = ss;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int a = wn[lane], b = ws[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ta = __shfl_up_sync(GNN_FULL_MASK, a, o), tb = __shfl_up_sync(GNN_FULL_MASK, b, o);
+                if (lane >= o) {
+                    a += ta;
+                    b += tb;
+                }
+            }
+            wn[lane] = a;
+            ws[lane] = b;
+        }
+        __syncthreads();
+        const int pn = carry_n + (warp > 0 ? wn[warp - 1] : 0), ps = carry_s + (warp > 0 ? ws[warp - 1] : 0);
+        if (i < nb) {
+            nptr[i + 1] = pn + sn;
+            sptr[i + 1] = ps + ss;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            carry_n = pn + sn;
+            carry_s = ps + ss;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+compact_gather_kernel(const int64_t* __restrict__ ids, int64_t nb, int64_t num_store_graphs,
+                      const int* __restrict__ node_off, const int* __restrict__ slot_off,
+                      const uint8_t* __restrict__ sx, const int* __restrict__ s_rowptr, const int* __restrict__ s_col_src,
+                      const uint8_t* __restrict__ s_col_code, const float* __restrict__ s_para, int num_para,
+                      const int* __restrict__ nptr, const int* __restrict__ sptr, int64_t pad_nodes, int64_t pad_slots,
+                      uint8_t* __restrict__ x, int* __restrict__ rowptr, int* __restrict__ col_src,
+                      uint8_t* __restrict__ col_code, int* __restrict__ node_graph, int* __restrict__ graph_ptr,
+                      float* __restrict__ para, int* err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+    const bool fits = nptr[nb] <= pad_nodes && sptr[nb] <= pad_slots;
+    if (!fits) {
+        if (err && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, GNN_INPUT_ERR_EDGE_INDEX);
+        return;
+    }
+    for (int64_t i = warp0; i < nb; i += nwarps) {
+        int64_t g = ids[i];
+        if (g < 0 || g >= num_store_graphs) g = 0;
+        const int n0 = node_off[g], cn = node_off[g + 1] - n0, s0 = slot_off[g], cs = slot_off[g + 1] - s0;
+        const int on = nptr[i], os = sptr[i];
+        for (int k = lane; k < cn * GNN_NUM_ATOM_FEATS; k += 32)
+            x[(int64_t)on * GNN_NUM_ATOM_FEATS + k] = __ldg(sx + (int64_t)n0 * GNN_NUM_ATOM_FEATS + k);
+        for (int k = lane; k < cn; k += 32) {
+            rowptr[on + k] = __ldg(s_rowptr + n0 + k) - s0 + os;
+            node_graph[on + k] = (int)i;
+        }
+        for (int k = lane; k < cs; k += 32) {
+            col_src[os + k] = __ldg(s_col_src + s0 + k) - n0 + on;
+            col_code[os + k] = __ldg(s_col_code + s0 + k);
+        }
+        if (lane == 0) graph_ptr[i] = on;
+        if (para != nullptr)
+            for (int k = lane; k < num_para; k += 32) para[i * num_para + k] = __ldg(s_para + g * num_para + k);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+compact_pad_kernel(int64_t nb, const int* __restrict__ nptr, const int* __restrict__ sptr, int64_t pad_nodes,
+                   int64_t pad_slots, int num_para, uint8_t* __restrict__ x, int* __restrict__ rowptr,
+                   int* __restrict__ col_src, uint8_t* __restrict__ col_code, int* __restrict__ node_graph,
+                   int* __restrict__ graph_ptr, float* __restrict__ para, int* __restrict__ valid, int* err) {
+    const int n = nptr[nb], e = sptr[nb];
+    if (n > pad_nodes || e > pad_slots) return;          // reported by the gather kernel
+    const int nd = (int)pad_nodes - n, d = (int)pad_slots - e;      // padding nodes / surplus slots
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rowptr[pad_nodes] = (int)pad_slots;
+        graph_ptr[nb] = n;
+        graph_ptr[nb + 1] = (int)pad_nodes;
+        valid[0] = n;
+        valid[1] = (int)nb;
+        valid[2] = e;
+        valid[3] = 0;
+        if (nd == 0 && d != 0 && err) atomicOr(err, GNN_INPUT_ERR_EDGE_INDEX);   // surplus slots need a padding node
+        if (para != nullptr)
+            for (int k = 0; k < num_para; ++k) para[nb * num_para + k] = 1.0f;    // target of the padding graph (unused)
+    }
+    if (nd == 0) return;
+    const int base = d / nd, rem = d % nd;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x) {
+        const int node = n + k, start = e + k * base + min(k, rem), cnt = base + (k < rem ? 1 : 0);
+        for (int j = 0; j < GNN_NUM_ATOM_FEATS; ++j) x[(int64_t)node * GNN_NUM_ATOM_FEATS + j] = 0;
+        rowptr[node] = start;
+        node_graph[node] = (int)nb;
+        for (int j = 0; j < cnt; ++j) {
+            col_src[start + j] = node;
+            col_code[start + j] = 0;
+        }
+    }
+}
+
+extern "C" int64_t gnn_compact_collate_workspace_bytes(int64_t num_ids) {
+    return gnn_align_up(2 * (num_ids + 1) * (int64_t)sizeof(int), 256);
+}
+extern "C" int gnn_compact_collate(const int64_t* ids, int64_t nb, int64_t num_store_graphs, const int32_t* node_off,
+                                   const int32_t* slot_off, const uint8_t* store_x, const int32_t* store_rowptr,
+                                   const int32_t* store_col_src, const uint8_t* store_col_code, const float* store_para,
+                                   int num_para, int64_t pad_nodes, int64_t pad_slots, uint8_t* x, int32_t* rowptr,
+                                   int32_t* col_src, uint8_t* col_code, int32_t* node_graph, int32_t* graph_ptr,
+                                   float* para, int32_t* valid, int32_t* err_flag, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+    if (nb < 1 || num_store_graphs < 1 || pad_nodes < 0 || pad_slots < 0 || num_para < 0) return GNN_ERR_BAD_ARG;
+    if (pad_nodes >= (1ll << 31) || pad_slots >= (1ll << 31)) return GNN_ERR_TOO_LARGE;
+    if (workspace_bytes < gnn_compact_collate_workspace_bytes(nb)) return GNN_ERR_WORKSPACE;
+    cudaStream_t st = gnn_stream(stream);
+    int* nptr = reinterpret_cast<int*>(workspace);
+    int* sptr = nptr + nb + 1;
+    if (err_flag) cudaMemsetAsync(err_flag, 0, sizeof(int), st);
+    compact_offsets_kernel<<<1, 1024, 0, st>>>(ids, nb, num_store_graphs, node_off, slot_off, nptr, sptr, err_flag);
+    int64_t blocks = gnn_ceil_div(nb, 8);
+    int64_t cap = (int64_t)gnn_sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    compact_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(ids, nb, num_store_graphs, node_off, slot_off, store_x,
+                                                            store_rowptr, store_col_src, store_col_code, store_para,
+                                                            num_para, nptr, sptr, pad_nodes, pad_slots, x, rowptr, col_src,
+                                                            col_code, node_graph, graph_ptr, para, err_flag);
+    compact_pad_kernel<<<32, 256, 0, st>>>(nb, nptr, sptr, pad_nodes, pad_slots, num_para, x, rowptr, col_src, col_code,
+                                           node_graph, graph_ptr, para, valid, err_flag);
+    return gnn_launch_status();
+}
+
+// int64 [N, 9] OGB atom features -> uint8 (store build); values outside [0, 255] are reported
+__global__ void x_to_u8_kernel(const int64_t* __restrict__ x, int64_t total, uint8_t* __restrict__ out, int* err) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        const int64_t v = x[i];
+        if ((v < 0 || v > 255) && err) atomicOr(err, GNN_INPUT_ERR_ATOM_FEATURE);
+        out[i] = (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+    }
+}
+extern "C" int gnn_atom_features_to_u8(const int64_t* x, int64_t num_nodes, uint8_t* out, int32_t* err_flag, void* stream) {
+    if (num_nodes < 0) return GNN_ERR_BAD_ARG;
+    if (num_nodes == 0) return 0;
+    const int64_t total = num_nodes * GNN_NUM_ATOM_FEATS;
+    int64_t blocks = gnn_ceil_div(total, 256);
+    int64_t cap = (int64_t)gnn_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    x_to_u8_kernel<<<(unsigned)blocks, 256, 0, gnn_stream(stream)>>>(x, total, out, err_flag);
+    return gnn_launch_status();
+}

@@ -25,6 +25,14 @@ extern "C" int64_t gnn_bn_workspace_bytes(int64_t rows, int C) {
 }
 
 __device__ __forceinline__ int64_t ceil_div_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+// Padded batches (shape buckets of the CUDA-graph-captured step): only the first *valid_rows rows are real; the
+// statistics, the backward sums and their 1/n use that count, and the gradient of the padding rows is zero.  The count
+// lives in device memory so that one captured graph serves every batch of a bucket.
+__device__ __forceinline__ int64_t bn_valid(int64_t rows, const int* valid_rows) {
+    if (valid_rows == nullptr) return rows;
+    const int64_t v = (int64_t)__ldg(valid_rows);
+    return v < rows ? (v < 0 ? 0 : v) : rows;
+}
 
 // mode 0: (y, y*y)            -> batch statistics
 // mode 1: (dz, dz*yhat)       -> BN backward sums, dz = dOut * [relu ? z>0 : 1]
@@ -32,11 +40,11 @@ template <int MODE>
 __global__ void __launch_bounds__(RED_TX * RED_TY)
 bn_partial_kernel(const float* __restrict__ Y, const float* __restrict__ dOut, const float* __restrict__ stats,
                   const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int C, int relu,
-                  double* __restrict__ partial) {
+                  double* __restrict__ partial, const int* __restrict__ valid_rows) {
     __shared__ double s0[RED_TY][RED_TX + 1], s1[RED_TY][RED_TX + 1];
     const int64_t chunk = ceil_div_dev(rows, gridDim.x);
     const int64_t r0 = (int64_t)blockIdx.x * chunk;
-    const int64_t r1 = min(rows, r0 + chunk);
+    const int64_t r1 = min(bn_valid(rows, valid_rows), r0 + chunk);
     for (int cb = 0; cb < C; cb += RED_TX) {
         const int c = cb + threadIdx.x;
         double a0 = 0.0, a1 = 0.0;
@@ -85,13 +93,13 @@ template <int MODE>
 __global__ void __launch_bounds__(BN4_THREADS)
 bn_partial4_kernel(const float* __restrict__ Y, const float* __restrict__ dOut, const float* __restrict__ stats,
                    const float* __restrict__ gamma, const float* __restrict__ beta, int64_t rows, int C, int relu,
-                   double* __restrict__ partial) {
+                   double* __restrict__ partial, const int* __restrict__ valid_rows) {
     extern __shared__ double sred[];                 // [BN4_THREADS][8]
     const int TX = C >> 2, TY = BN4_THREADS / TX;
     const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
     const int c = tx * 4;
     const int64_t chunk = ceil_div_dev(rows, gridDim.x);
-    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
+    const int64_t r0 = (int64_t)blockIdx.x * chunk, r1 = min(bn_valid(rows, valid_rows), r0 + chunk);
     double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), rs = mu, ga = mu, be = mu;
     if (MODE == 1) {
@@ -176,7 +184,9 @@ __device__ __forceinline__ void reduce_parts(const double* __restrict__ partial,
 
 __global__ void bn_stats_finalize_kernel(const double* __restrict__ partial, int nparts, int64_t rows, int C,
                                          int training, float eps, float momentum, float* running_mean,
-                                         float* running_var, int64_t* num_batches_tracked, float* stats) {
+                                         float* running_var, int64_t* num_batches_tracked, float* stats,
+                                         const int* __restrict__ valid_rows) {
+    rows = bn_valid(rows, valid_rows);
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0.0, ss = 0.0;
     if (training) reduce_parts(partial, nparts, C, c, s, ss);
@@ -188,8 +198,8 @@ __global__ void bn_stats_finalize_kernel(const double* __restrict__ partial, int
         stats[C + c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
         return;
     }
-    double mean = s / (double)rows;
-    double var = ss / (double)rows - mean * mean;
+    double mean = s / (double)(rows > 0 ? rows : 1);
+    double var = ss / (double)(rows > 0 ? rows : 1) - mean * mean;
     if (var < 0.0) var = 0.0;
     stats[c] = (float)mean;
     stats[C + c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -202,7 +212,7 @@ __global__ void bn_stats_finalize_kernel(const double* __restrict__ partial, int
 
 extern "C" int gnn_bn_stats(const float* Y, int64_t rows, int C, int training, float eps, float momentum,
                             float* running_mean, float* running_var, int64_t* num_batches_tracked, float* stats,
-                            void* workspace, int64_t workspace_bytes, void* stream) {
+                            const int32_t* valid_rows, void* workspace, int64_t workspace_bytes, void* stream) {
     if (rows < 0 || C < 1) return GNN_ERR_BAD_ARG;
     if (!training && (!running_mean || !running_var)) return GNN_ERR_BAD_ARG;
     if (training && workspace_bytes < gnn_bn_workspace_bytes(rows, C)) return GNN_ERR_WORKSPACE;
@@ -213,13 +223,14 @@ extern "C" int gnn_bn_stats(const float* Y, int64_t rows, int C, int training, f
     if (training) {
         if (bn_vec_ok(C))
             bn_partial4_kernel<0><<<parts, BN4_THREADS, BN4_THREADS * 8 * sizeof(double), st>>>(Y, nullptr, nullptr, nullptr, nullptr,
-                                                                                rows, C, 0, partial);
+                                                                                rows, C, 0, partial, valid_rows);
         else
             bn_partial_kernel<0><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, nullptr, nullptr, nullptr, nullptr, rows, C,
-                                                                          0, partial);
+                                                                          0, partial, valid_rows);
     }
     bn_stats_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_TY), 0, st>>>(partial, parts, rows, C, training, eps, momentum,
-                                                              running_mean, running_var, num_batches_tracked, stats);
+                                                              running_mean, running_var, num_batches_tracked, stats,
+                                                              valid_rows);
     return gnn_launch_status();
 }
 
@@ -296,12 +307,18 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int n
 __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dOut, const float* __restrict__ Y,
                                         const float* __restrict__ stats, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, const float* __restrict__ sums,
-                                        int64_t rows, int C, int relu, int training, float* __restrict__ dY) {
+                                        int64_t rows, int C, int relu, int training, float* __restrict__ dY,
+                                        const int* __restrict__ valid_rows) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t total = rows * C;
-    const float inv_n = 1.0f / (float)rows;
+    const int64_t vrows = bn_valid(rows, valid_rows), vtotal = vrows * C;
+    const float inv_n = 1.0f / (float)(vrows > 0 ? vrows : 1);
     for (; i < total; i += stride) {
+        if (i >= vtotal) {
+            dY[i] = 0.f;
+            continue;
+        }
         int c = (int)(i % C);
         float mu = __ldg(stats + c), rs = __ldg(stats + C + c), ga = __ldg(gamma + c);
         float yh = (__ldg(Y + i) - mu) * rs;
@@ -315,13 +332,19 @@ __global__ void bn_act_bwd_apply_kernel(const float* __restrict__ dOut, const fl
 __global__ void bn_act_bwd_apply4_kernel(const float* __restrict__ dOut, const float* __restrict__ Y,
                                          const float* __restrict__ stats, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, const float* __restrict__ sums,
-                                         int64_t rows, int C, int relu, int training, float* __restrict__ dY) {
+                                         int64_t rows, int C, int relu, int training, float* __restrict__ dY,
+                                         const int* __restrict__ valid_rows) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t total4 = rows * C / 4;
     const int C4 = C >> 2;
-    const float inv_n = 1.0f / (float)rows;
+    const int64_t vrows = bn_valid(rows, valid_rows), vtotal4 = vrows * C4;
+    const float inv_n = 1.0f / (float)(vrows > 0 ? vrows : 1);
     for (; i < total4; i += stride) {
+        if (i >= vtotal4) {
+            st4(dY + 4 * i, make_float4(0.f, 0.f, 0.f, 0.f));
+            continue;
+        }
         const int c = (int)(i % C4) * 4;
         const float4 mu = ldg4(stats + c), rs = ldg4(stats + C + c), ga = ldg4(gamma + c), be = ldg4(beta + c);
         const float4 s0 = ldg4(sums + c), s1 = ldg4(sums + C + c);
@@ -343,7 +366,8 @@ __global__ void bn_act_bwd_apply4_kernel(const float* __restrict__ dOut, const f
 
 extern "C" int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* stats, const float* gamma,
                               const float* beta, int64_t rows, int C, int relu, int training, float* dY,
-                              float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes, void* stream) {
+                              float* dgamma, float* dbeta, const int32_t* valid_rows, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
     if (rows < 0 || C < 1) return GNN_ERR_BAD_ARG;
     if (rows == 0) return 0;
     if (workspace_bytes < gnn_bn_workspace_bytes(rows, C)) return GNN_ERR_WORKSPACE;
@@ -353,16 +377,17 @@ extern "C" int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* st
     float* sums = reinterpret_cast<float*>(partial + (int64_t)parts * 2 * C);
     if (bn_vec_ok(C))
         bn_partial4_kernel<1><<<parts, BN4_THREADS, BN4_THREADS * 8 * sizeof(double), st>>>(Y, dOut, stats, gamma, beta, rows, C, relu,
-                                                                            partial);
+                                                                            partial, valid_rows);
     else
-        bn_partial_kernel<1><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, dOut, stats, gamma, beta, rows, C, relu, partial);
+        bn_partial_kernel<1><<<parts, dim3(RED_TX, RED_TY), 0, st>>>(Y, dOut, stats, gamma, beta, rows, C, relu, partial,
+                                                                     valid_rows);
     bn_bwd_finalize_kernel<<<(C + 31) / 32, dim3(32, FIN_TY), 0, st>>>(partial, parts, C, sums, dgamma, dbeta);
     if ((C & 3) == 0)
         bn_act_bwd_apply4_kernel<<<ew_grid(rows * C / 4, 256), 256, 0, st>>>(dOut, Y, stats, gamma, beta, sums, rows, C,
-                                                                             relu, training, dY);
+                                                                             relu, training, dY, valid_rows);
     else
         bn_act_bwd_apply_kernel<<<ew_grid(rows * C, 256), 256, 0, st>>>(dOut, Y, stats, gamma, beta, sums, rows, C, relu,
-                                                                        training, dY);
+                                                                        training, dY, valid_rows);
     return gnn_launch_status();
 }
 
@@ -429,11 +454,19 @@ extern "C" int gnn_segment_pool_bwd(const float* dout, const int32_t* node_graph
 
 // ------------------------------------------------------------------ MAPE (single CTA, deterministic)
 __global__ void __launch_bounds__(1024)
-mape_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t numel, float grad_scale,
-            float* loss, float* dpred) {
+mape_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t total, float grad_scale,
+            float* loss, float* dpred, const int* __restrict__ valid_rows, int row_len) {
     __shared__ double sw[32];
     double acc = 0.0;
-    const float inv = 1.0f / (float)numel;
+    // padded batches: only the first *valid_rows rows (graphs) are real; the padding graph gets a zero gradient
+    int64_t numel = total;
+    if (valid_rows != nullptr) {
+        const int64_t v = (int64_t)__ldg(valid_rows) * row_len;
+        numel = v < total ? (v < 0 ? 0 : v) : total;
+    }
+    const float inv = 1.0f / (float)(numel > 0 ? numel : 1);
+    if (dpred)
+        for (int64_t i = numel + threadIdx.x; i < total; i += blockDim.x) dpred[i] = 0.f;
     for (int64_t i = threadIdx.x; i < numel; i += blockDim.x) {
         float p = pred[i], t = target[i];
         float den = fmaxf(fabsf(t), 1.17e-06f);
@@ -449,13 +482,13 @@ mape_kernel(const float* __restrict__ pred, const float* __restrict__ target, in
         double v = threadIdx.x < (blockDim.x >> 5) ? sw[threadIdx.x] : 0.0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(GNN_FULL_MASK, v, o);
-        if (threadIdx.x == 0 && loss) loss[0] = (float)(v / (double)numel);
+        if (threadIdx.x == 0 && loss) loss[0] = (float)(v / (double)(numel > 0 ? numel : 1));
     }
 }
 extern "C" int gnn_mape_fwd_bwd(const float* pred, const float* target, int64_t numel, float grad_scale, float* loss,
-                                float* dpred, void* stream) {
-    if (numel < 1) return GNN_ERR_BAD_ARG;
-    mape_kernel<<<1, 1024, 0, gnn_stream(stream)>>>(pred, target, numel, grad_scale, loss, dpred);
+                                float* dpred, const int32_t* valid_rows, int row_len, void* stream) {
+    if (numel < 1 || (valid_rows != nullptr && row_len < 1)) return GNN_ERR_BAD_ARG;
+    mape_kernel<<<1, 1024, 0, gnn_stream(stream)>>>(pred, target, numel, grad_scale, loss, dpred, valid_rows, row_len);
     return gnn_launch_status();
 }
 

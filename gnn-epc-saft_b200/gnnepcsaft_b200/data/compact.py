@@ -1,0 +1,289 @@
+"""Compact, store-resident batches: dataset residency + sampler.
+
+Replaces the reference's `InMemoryDataset` + PyG `DataLoader(batch_size, shuffle, num_workers=os.cpu_count())`
+(gnnepcsaft/data/graphdataset.py:48,137 and gnnepcsaft/train/train.py:74-79) and, for batches drawn from the store,
+also `add_self_loops` and the scatter index handling of every layer (models.py:118-121): the dataset is uploaded ONCE
+in compact dtypes (uint8 atom features, int32 CSR, uint8 bond codes) together with one destination CSR built over all
+of it, and a batch is a single segment-gather launch (`gnn_compact_collate`) that emits exactly what the model kernels
+consume.  The same compact batch can be assembled on the host into pinned memory (`host_batch`) for feeds that must
+cross PCIe: 5 MB per 4096 graphs instead of the 16.4 MB of the int64 PyG layout.
+
+Shape buckets: `bucket(N, E')` rounds a batch's node / slot counts up; the surplus becomes one extra "padding graph" of
+isolated nodes, so all batches of a bucket issue identical kernel launches and `TrainEngine` replays one captured CUDA
+graph per bucket.  `valid = [N, B, E', 0]` (device int32) tells the BatchNorm kernels which rows are real.
+"""
+
+from __future__ import annotations
+
+from typing import Iterator, Optional, Tuple
+
+import torch
+
+from .. import _lib
+from .synth import PackedGraphs
+
+MIN_PAD_NODES = 16          # every padded batch has at least this many padding nodes ...
+MAX_SURPLUS_PER_NODE = 128  # ... and no padding node carries more than this many surplus CSR slots (as self-edges)
+
+
+class CompactBatch:
+    """x uint8 [Np,9] | rowptr i32 [Np+1] | col_src i32 [Ep] | col_code u8 [Ep] | node_graph i32 [Np] |
+    graph_ptr i32 [B+2] | para f32 [(B+1) P] | valid i32 [4] = {N, B, E', 0}.  Graph B is the padding graph."""
+
+    FIELDS = ("x", "rowptr", "col_src", "col_code", "node_graph", "graph_ptr", "para", "valid")
+    is_compact = True
+
+    def __init__(self, num_graphs: int, pad_nodes: int, pad_slots: int, self_loops: bool, **tensors):
+        self.num_graphs = int(num_graphs)           # real graphs B (outputs have B + 1 rows; use [:B])
+        self.pad_nodes, self.pad_slots = int(pad_nodes), int(pad_slots)
+        self.self_loops = bool(self_loops)
+        for k in self.FIELDS:
+            setattr(self, k, tensors.get(k))
+        self.err = tensors.get("err")
+
+    # graph-structure view consumed by the model kernels (same attribute names as models.GraphStructure)
+    @property
+    def n(self):
+        return self.pad_nodes
+
+    @property
+    def ep(self):
+        return self.pad_slots
+
+    @property
+    def b(self):
+        return self.num_graphs + 1
+
+    srcptr = None
+    src_slot = None
+
+    @property
+    def device(self):
+        return self.x.device
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, k).numel() * getattr(self, k).element_size() for k in self.FIELDS
+                   if getattr(self, k) is not None)
+
+    def _apply(self, fn):
+        kw = {k: (fn(getattr(self, k)) if getattr(self, k) is not None else None) for k in self.FIELDS}
+        kw["err"] = fn(self.err) if self.err is not None else None
+        return CompactBatch(self.num_graphs, self.pad_nodes, self.pad_slots, self.self_loops, **kw)
+
+    def to(self, *args, **kwargs):
+        return self._apply(lambda t: t.to(*args, **kwargs))
+
+    def pin_memory(self):
+        return self._apply(lambda t: t.pin_memory())
+
+    def defer_check(self):
+        pass                                        # store-built batches were validated when the store was built
+
+    def copy_from(self, other: "CompactBatch"):
+        """Copy another batch of the same bucket (e.g. a pinned host batch) into these buffers, stream-ordered."""
+        if (other.num_graphs, other.pad_nodes, other.pad_slots) != (self.num_graphs, self.pad_nodes, self.pad_slots):
+            raise ValueError("copy_from: the batches belong to different shape buckets")
+        for k in self.FIELDS:
+            dst, src = getattr(self, k), getattr(other, k)
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        return self
+
+    def __repr__(self):
+        return (f"CompactBatch(graphs={self.num_graphs}, pad_nodes={self.pad_nodes}, pad_slots={self.pad_slots}, "
+                f"device={self.x.device})")
+
+
+def bucket(num_nodes: int, num_slots: int, quantum_nodes: Optional[int] = None,
+           quantum_slots: Optional[int] = None) -> Tuple[int, int]:
+    """Padded (nodes, slots) of a batch: quanta of about 1/64 of the size (powers of two, >= 128 / 256), at least
+    MIN_PAD_NODES padding nodes and at most MAX_SURPLUS_PER_NODE surplus slots per padding node."""
+    def pow2_at_least(v, lo):
+        q = lo
+        while q * 64 < v:
+            q *= 2
+        return q
+    qn = quantum_nodes or pow2_at_least(num_nodes, 128)
+    qs = quantum_slots or pow2_at_least(num_slots, 256)
+    pn = (num_nodes + MIN_PAD_NODES + qn - 1) // qn * qn
+    ps = (num_slots + qs - 1) // qs * qs
+    while (ps - num_slots) > MAX_SURPLUS_PER_NODE * (pn - num_nodes):
+        pn += qn
+    return pn, ps
+
+
+class CompactGraphStore:
+    """Device-resident dataset in compact dtypes + one destination CSR over all graphs."""
+
+    def __init__(self, packed: PackedGraphs, device="cuda", self_loops: bool = True, keep_host_mirror: bool = True):
+        dev = torch.device(device)
+        from ..train import models as _models
+        from ..train.models import _WS, _c, _device_guard, _raise_input_error
+        _models._require_cuda(torch.empty(0, device=dev), "CompactGraphStore")     # no CPU path
+        self.device, self.self_loops = dev, bool(self_loops)
+        self.num_graphs = packed.num_graphs
+        g = self.num_graphs
+        sum_n, sum_e = int(packed.node_slices[-1]), int(packed.edge_slices[-1])
+        if sum_n >= 2 ** 31 or sum_e + sum_n >= 2 ** 31:
+            raise ValueError("CompactGraphStore: the store is indexed with int32 (split the dataset into shards)")
+        n_cnt = (packed.node_slices[1:] - packed.node_slices[:-1])
+        e_cnt = (packed.edge_slices[1:] - packed.edge_slices[:-1])
+        s_cnt = e_cnt + (n_cnt if self.self_loops else 0)
+        self.num_para = int(packed.para.shape[1]) if packed.para.dim() == 2 else 0
+        # host copies of the per-graph sizes: batch / bucket planning never touches the device
+        self.node_count, self.slot_count = n_cnt.clone(), s_cnt.clone()
+        i32 = dict(dtype=torch.int32, device=dev)
+        with _device_guard(dev):
+            self.node_off = packed.node_slices.to(torch.int32).to(dev)
+            slot_off = torch.zeros(g + 1, dtype=torch.int64)
+            slot_off[1:] = torch.cumsum(s_cnt, 0)
+            self.slot_off = slot_off.to(torch.int32).to(dev)
+            # one CSR over the whole dataset (graph-local edge ids -> store-global node ids)
+            node_of_edge = torch.repeat_interleave(packed.node_slices[:-1], e_cnt)
+            ei = (packed.edge_index + node_of_edge).to(dev).contiguous()
+            ea = packed.edge_attr.to(dev).contiguous()
+            ep = sum_e + (sum_n if self.self_loops else 0)
+            self.rowptr = torch.empty(sum_n + 1, **i32)
+            self.col_src = torch.empty(max(ep, 1), **i32)
+            self.col_code = torch.empty(max(ep, 1), dtype=torch.uint8, device=dev)
+            col_eid = torch.empty(max(ep, 1), **i32)
+            srcptr = torch.empty(sum_n + 1, **i32)
+            src_slot = torch.empty(max(ep, 1), **i32)
+            err = torch.zeros(1, **i32)
+            nbytes = _lib.query("gnn_build_csr_workspace_bytes", sum_n, sum_e)
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+            _c("gnn_build_csr", ei, ea, sum_n, sum_e, 1 if self.self_loops else 0, self.rowptr, self.col_src,
+               self.col_code, col_eid, srcptr, src_slot, err, ws, ws.numel())
+            self.x = torch.empty(sum_n, 9, dtype=torch.uint8, device=dev)
+            x64 = packed.x.to(dev).contiguous()
+            err2 = torch.zeros(1, **i32)
+            _c("gnn_atom_features_to_u8", x64, sum_n, self.x, err2)
+            self.para = packed.para.to(dev).contiguous() if self.num_para else None
+            _raise_input_error(int(err.item()) | int(err2.item()))
+            del ei, ea, x64, col_eid, srcptr, src_slot, ws
+        self._ws = None
+        self._host = None
+        if keep_host_mirror:
+            self._host = dict(x=self.x.cpu(), rowptr=self.rowptr.cpu(), col_src=self.col_src.cpu(),
+                              col_code=self.col_code.cpu(), node_off=self.node_off.cpu().long(),
+                              slot_off=self.slot_off.cpu().long(),
+                              para=self.para.cpu() if self.para is not None else None)
+
+    # ---- planning (host) -----------------------------------------------------------------------
+    def sizes(self, ids: torch.Tensor) -> Tuple[int, int]:
+        """(nodes, CSR slots) of the batch `ids` (host int64 tensor) - no device access."""
+        ids = ids.cpu() if ids.is_cuda else ids
+        return int(self.node_count[ids].sum()), int(self.slot_count[ids].sum())
+
+    def in_degree_histogram(self) -> torch.Tensor:
+        """`calc_deg` (reference train/utils.py:26-49) from the store's CSR: in-degrees WITHOUT the self-loops."""
+        deg = (self.rowptr[1:] - self.rowptr[:-1]).long() - (1 if self.self_loops else 0)
+        return torch.bincount(deg.cpu())
+
+    def epoch(self, batch_size: int, shuffle: bool = True, generator: Optional[torch.Generator] = None,
+              drop_last: bool = False, rank: int = 0, world: int = 1) -> Iterator[torch.Tensor]:
+        """Graph-id batches of one epoch (host int64), `DistributedSampler`-style strided over ranks."""
+        order = (torch.randperm(self.num_graphs, generator=generator) if shuffle
+                 else torch.arange(self.num_graphs))
+        order = order[rank::world]
+        for i in range(0, order.numel(), batch_size):
+            ids = order[i:i + batch_size]
+            if ids.numel() < batch_size and (drop_last or ids.numel() == 0):
+                return
+            yield ids
+
+    # ---- device collate -------------------------------------------------------------------------
+    def allocate(self, num_graphs: int, pad_nodes: int, pad_slots: int) -> CompactBatch:
+        """Batch buffers of one shape bucket (static inputs of a captured CUDA graph)."""
+        dev = self.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        u8 = dict(dtype=torch.uint8, device=dev)
+        para = torch.zeros((num_graphs + 1) * self.num_para, dtype=torch.float32, device=dev) if self.num_para else None
+        return CompactBatch(num_graphs, pad_nodes, pad_slots, self.self_loops,
+                            x=torch.zeros(max(pad_nodes, 1), 9, **u8), rowptr=torch.zeros(pad_nodes + 1, **i32),
+                            col_src=torch.zeros(max(pad_slots, 1), **i32), col_code=torch.zeros(max(pad_slots, 1), **u8),
+                            node_graph=torch.zeros(max(pad_nodes, 1), **i32), graph_ptr=torch.zeros(num_graphs + 2, **i32),
+                            para=para, valid=torch.zeros(4, **i32), err=torch.zeros(1, **i32))
+
+    def batch(self, ids: torch.Tensor, pad=True, out: Optional[CompactBatch] = None,
+              ids_device: Optional[torch.Tensor] = None) -> CompactBatch:
+        """Device batch of the graphs `ids`.  pad=True: bucketed shape; pad=False: exact shape; pad=(Np, Ep): given
+        shape.  `out`: write into these (bucket-static) buffers instead of allocating."""
+        from ..train.models import _c, _device_guard
+        nb = int(ids.numel())
+        if out is not None:
+            pn, ps = out.pad_nodes, out.pad_slots
+        elif isinstance(pad, tuple):
+            pn, ps = pad
+        else:
+            n, s = self.sizes(ids)
+            pn, ps = bucket(n, s) if pad else (n, s)
+        with _device_guard(self.device):
+            if ids_device is None:
+                ids_device = ids.to(self.device, non_blocking=True) if not ids.is_cuda else ids
+            ids_device = ids_device.to(torch.int64).contiguous()
+            if out is None:
+                out = self.allocate(nb, pn, ps)
+            nbytes = _lib.query("gnn_compact_collate_workspace_bytes", nb)
+            if self._ws is None or self._ws.numel() < nbytes:
+                self._ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=self.device)
+            _c("gnn_compact_collate", ids_device, nb, self.num_graphs, self.node_off, self.slot_off, self.x, self.rowptr,
+               self.col_src, self.col_code, self.para, self.num_para, pn, ps, out.x, out.rowptr, out.col_src,
+               out.col_code, out.node_graph, out.graph_ptr, out.para, out.valid, out.err, self._ws, self._ws.numel())
+        return out
+
+    # ---- host assembly (feeds that cross PCIe) ---------------------------------------------------
+    def host_batch(self, ids: torch.Tensor, pad=True, pin: bool = True) -> CompactBatch:
+        """The same batch assembled on the host (vectorised torch ops on the host mirror) into pinned memory."""
+        if self._host is None:
+            raise RuntimeError("CompactGraphStore was built with keep_host_mirror=False")
+        h = self._host
+        ids = ids.cpu().long()
+        nb = int(ids.numel())
+        n_cnt, s_cnt = self.node_count[ids], self.slot_count[ids]
+        n, s = int(n_cnt.sum()), int(s_cnt.sum())
+        pn, ps = pad if isinstance(pad, tuple) else (bucket(n, s) if pad else (n, s))
+        if pn < n or ps < s:
+            raise ValueError(f"bucket ({pn}, {ps}) smaller than the batch ({n}, {s})")
+        nptr = torch.zeros(nb + 1, dtype=torch.int64)
+        nptr[1:] = torch.cumsum(n_cnt, 0)
+        sptr = torch.zeros(nb + 1, dtype=torch.int64)
+        sptr[1:] = torch.cumsum(s_cnt, 0)
+        g_of_node = torch.repeat_interleave(torch.arange(nb), n_cnt)
+        g_of_slot = torch.repeat_interleave(torch.arange(nb), s_cnt)
+        n0, s0 = h["node_off"][ids], h["slot_off"][ids]
+        node_src = n0[g_of_node] + (torch.arange(n) - nptr[:-1][g_of_node])
+        slot_src = s0[g_of_slot] + (torch.arange(s) - sptr[:-1][g_of_slot])
+        x = torch.zeros(max(pn, 1), 9, dtype=torch.uint8)
+        x[:n] = h["x"][node_src]
+        rowptr = torch.zeros(pn + 1, dtype=torch.int32)
+        rowptr[:n] = (h["rowptr"][node_src].long() - s0[g_of_node] + sptr[:-1][g_of_node]).to(torch.int32)
+        col_src = torch.zeros(max(ps, 1), dtype=torch.int32)
+        col_src[:s] = (h["col_src"][slot_src].long() - n0[g_of_slot] + nptr[:-1][g_of_slot]).to(torch.int32)
+        col_code = torch.zeros(max(ps, 1), dtype=torch.uint8)
+        col_code[:s] = h["col_code"][slot_src]
+        node_graph = torch.full((max(pn, 1),), nb, dtype=torch.int32)
+        node_graph[:n] = g_of_node.to(torch.int32)
+        graph_ptr = torch.zeros(nb + 2, dtype=torch.int32)
+        graph_ptr[:nb + 1] = nptr.to(torch.int32)
+        graph_ptr[nb + 1] = pn
+        nd, d = pn - n, ps - s
+        if nd > 0:
+            base, rem = d // nd, d % nd
+            k = torch.arange(nd)
+            start = s + k * base + torch.clamp(k, max=rem)
+            cnt = base + (k < rem).long()
+            rowptr[n:pn] = start.to(torch.int32)
+            col_src[s:ps] = (n + torch.repeat_interleave(k, cnt)).to(torch.int32)
+        elif d != 0:
+            raise ValueError("surplus CSR slots need at least one padding node")
+        rowptr[pn] = ps
+        para = None
+        if self.num_para:
+            para = torch.ones((nb + 1) * self.num_para, dtype=torch.float32)
+            para[:nb * self.num_para] = h["para"][ids].reshape(-1)
+        valid = torch.tensor([n, nb, s, 0], dtype=torch.int32)
+        out = CompactBatch(nb, pn, ps, self.self_loops, x=x, rowptr=rowptr, col_src=col_src, col_code=col_code,
+                           node_graph=node_graph, graph_ptr=graph_ptr, para=para, valid=valid,
+                           err=torch.zeros(1, dtype=torch.int32))
+        return out.pin_memory() if pin else out

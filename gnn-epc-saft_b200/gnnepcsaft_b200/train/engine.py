@@ -9,7 +9,12 @@ Reproduces the step the reference runs through Lightning (reference gnnepcsaft/t
     reference train.py:132-156); the loss scalar rides in the same buffer (replaces the
     `sync_dist=True` scalar all-reduce of models.py:195-201);
   * the optimizer + LR schedule fused into one kernel over the arena;
-  * BatchNorm statistics per rank (the reference has no SyncBatchNorm).
+  * BatchNorm statistics per rank (the reference has no SyncBatchNorm);
+  * store-resident training (`step_from_store`, `fit_epoch`): the batch is gathered on the device by
+    `gnn_compact_collate` into the static buffers of a shape bucket and the whole step (forward, loss, backward,
+    NCCL all-reduce, optimizer) is ONE captured CUDA graph per bucket - no per-step allocation, ~125 C-ABI calls and
+    ~290 launches replaced by one `cudaGraphLaunch` (the reference's 512-graph batches, configs/default.py:22, are
+    otherwise bound by host dispatch).
 No autograd graph is built on this path.
 """
 
@@ -51,6 +56,13 @@ class TrainEngine:
             dist.broadcast(arena, src=0, group=process_group)
             for b in self.net.buffers():
                 dist.broadcast(b, src=0, group=process_group)
+        # captured CUDA graphs, one per (mode, graphs, padded nodes, padded slots) shape bucket; all share one memory
+        # pool (they never run concurrently)
+        self.use_cuda_graphs = True
+        self._buckets = {}
+        self._pool = None
+        self._warm = False
+        self.graph_replays = 0
 
     @classmethod
     def from_config(cls, model, config, **kw):
@@ -72,10 +84,19 @@ class TrainEngine:
         net.train()
         arena = net.arena()
         models.check_input_errors(block=False)
-        batchvec = getattr(batch, "batch", None)
-        num_graphs = batch.num_graphs if batchvec is not None else 1
-        out, sv = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs), save=True)
+        compact = getattr(batch, "is_compact", False)
+        valid = None
+        if compact:     # store-resident compact batch (padded: graph `num_graphs` is the padding graph)
+            out, sv = _forward_impl(net, None, None, None, None, batch.b, save=True, graph=batch)
+            valid = batch.valid[1:2]
+        else:
+            batchvec = getattr(batch, "batch", None)
+            num_graphs = batch.num_graphs if batchvec is not None else 1
+            out, sv = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs),
+                                    save=True)
         target = batch.para
+        if target is None:
+            raise ValueError("TrainEngine.step: the batch has no `para` targets")
         _require_cuda(target, "batch.para")
         if target.dtype != torch.float32:
             target = target.float()
@@ -85,7 +106,7 @@ class TrainEngine:
         dpred = torch.empty_like(out)
         _c("gnn_fill_zero", self.grad, self.grad.numel() * 4)
         loss = self.grad[self.numel:self.numel + 1]
-        _c("gnn_mape_fwd_bwd", out, target, out.numel(), 1.0, loss, dpred)
+        _c("gnn_mape_fwd_bwd", out, target, out.numel(), 1.0, loss, dpred, valid, int(out.shape[1]))
         _backward_impl(net, sv, dpred, self.grad)
         if self.world > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
@@ -103,13 +124,107 @@ class TrainEngine:
         net.eval()
         try:
           with models._device_guard(self.grad.device):
-            batchvec = getattr(batch, "batch", None)
-            num_graphs = batch.num_graphs if batchvec is not None else 1
-            out, _ = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs),
-                                   save=False)
+            out = self._predict(batch)
         finally:
             net.train(was_training)
         return out
+
+    def _predict(self, batch) -> torch.Tensor:
+        net = self.net
+        if getattr(batch, "is_compact", False):
+            out, _ = _forward_impl(net, None, None, None, None, batch.b, save=False, graph=batch)
+            return out          # [num_graphs + 1, P]: the last row is the padding graph
+        batchvec = getattr(batch, "batch", None)
+        num_graphs = batch.num_graphs if batchvec is not None else 1
+        out, _ = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs), save=False)
+        return out
+
+    # ---- store-resident path: compact device collate + one captured CUDA graph per shape bucket --------------
+    def _bucket(self, mode: str, store, nb: int, pn: int, ps: int):
+        key = (mode, id(store), nb, pn, ps)
+        ent = self._buckets.get(key)
+        if ent is None:
+            ent = {"batch": store.allocate(nb, pn, ps), "graph": None, "out": None}
+            self._buckets[key] = ent
+        return ent
+
+    def _run_bucket(self, ent, fn):
+        """Run `fn(static batch)` for a bucket: eagerly until the process is warm (lazy constants, workspaces and
+        kernel attributes exist), then captured once and replayed."""
+        if not self.use_cuda_graphs:
+            return fn(ent["batch"])
+        if ent["graph"] is None:
+            if not self._warm:
+                self._warm = True
+                return fn(ent["batch"])
+            torch.cuda.synchronize(self.grad.device)
+            g = torch.cuda.CUDAGraph()
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            with torch.cuda.graph(g, pool=self._pool):
+                ent["out"] = fn(ent["batch"])
+            ent["graph"] = g
+        ent["graph"].replay()
+        self.graph_replays += 1
+        return ent["out"]
+
+    @torch.no_grad()
+    def step_from_store(self, store, ids: torch.Tensor, ids_device: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step on the graphs `ids` (host int64 tensor) of a `CompactGraphStore`.  Returns the loss
+        as a device scalar that the NEXT step of the same bucket overwrites (read or clone it before)."""
+        from ..data.compact import bucket
+        with models._device_guard(self.grad.device):
+            self.net.train()
+            self.net.arena()
+            n, s = store.sizes(ids)
+            pn, ps = bucket(n, s)
+            ent = self._bucket("train", store, int(ids.numel()), pn, ps)
+            store.batch(ids, out=ent["batch"], ids_device=ids_device)
+            return self._run_bucket(ent, self._step)
+
+    @torch.no_grad()
+    def step_from_host(self, store, host_batch) -> torch.Tensor:
+        """The same for a compact batch assembled on the host (`store.host_batch(ids)`, pinned): one H2D copy per
+        field into the bucket's static buffers, then the captured step."""
+        with models._device_guard(self.grad.device):
+            self.net.train()
+            self.net.arena()
+            ent = self._bucket("train", store, host_batch.num_graphs, host_batch.pad_nodes, host_batch.pad_slots)
+            ent["batch"].copy_from(host_batch)
+            return self._run_bucket(ent, self._step)
+
+    @torch.no_grad()
+    def predict_from_store(self, store, ids: torch.Tensor, ids_device: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Eval-mode forward of the graphs `ids` of a `CompactGraphStore`: [len(ids), P] (a view of the bucket's
+        static output, overwritten by the next call on the same bucket)."""
+        from ..data.compact import bucket
+        net = self.net
+        was_training = net.training
+        net.eval()
+        try:
+            with models._device_guard(self.grad.device):
+                net.arena()
+                n, s = store.sizes(ids)
+                pn, ps = bucket(n, s)
+                ent = self._bucket("eval", store, int(ids.numel()), pn, ps)
+                store.batch(ids, out=ent["batch"], ids_device=ids_device)
+                out = self._run_bucket(ent, self._predict)
+        finally:
+            net.train(was_training)
+        return out[:int(ids.numel())]
+
+    def fit_epoch(self, store, batch_size: int, shuffle: bool = True, generator=None, drop_last: bool = False,
+                  rank: int = 0, world: Optional[int] = None):
+        """One epoch over the store (the reference's `trainer.fit` inner loop, train.py:186-201): returns the mean of
+        the per-step losses as a python float (one synchronisation per epoch)."""
+        world = self.world if world is None else world
+        total = torch.zeros(1, dtype=torch.float32, device=self.grad.device)
+        steps = 0
+        for ids in store.epoch(batch_size, shuffle=shuffle, generator=generator, drop_last=drop_last, rank=rank,
+                               world=world):
+            total += self.step_from_store(store, ids)
+            steps += 1
+        return float(total) / max(steps, 1)
 
     def optimizer_state_dict(self):
         """torch.optim.AdamW-style state for the legacy `.pth` checkpoints (reference train/utils.py:109-119)."""

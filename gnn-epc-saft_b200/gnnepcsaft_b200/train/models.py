@@ -494,21 +494,25 @@ class _Saved:
     pass
 
 
-def _bn_forward(y, bn: nn.BatchNorm1d, training: bool, skip, relu: bool):
+def _bn_forward(y, bn: nn.BatchNorm1d, training: bool, skip, relu: bool, valid=None):
+    """`valid` (device int32[1]): padded batch, only the first *valid rows enter the statistics."""
     rows, ch = y.shape
     dev = y.device
     stats = torch.empty(2 * ch, dtype=torch.float32, device=dev)
     use_batch = training or bn.running_mean is None
     nbytes = _lib.query("gnn_bn_workspace_bytes", rows, ch)
     ws = _WS.get("bn", nbytes, dev)
-    if use_batch and rows == 1:
+    if use_batch and rows == 1 and valid is None:
         raise ValueError(f"Expected more than 1 value per channel when training, got input size {tuple(y.shape)}")
     if bn.momentum is None:     # torch: cumulative moving average, factor 1 / num_batches_tracked (after the increment)
+        if y.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("gnnepcsaft_b200: BatchNorm momentum=None reads num_batches_tracked on the host and "
+                               "cannot be captured in a CUDA graph (use the eager step)")
         momentum = 1.0 / (int(bn.num_batches_tracked) + 1) if (use_batch and bn.num_batches_tracked is not None) else 0.0
     else:
         momentum = bn.momentum
     _c("gnn_bn_stats", y, rows, ch, 1 if use_batch else 0, float(bn.eps), float(momentum), bn.running_mean,
-       bn.running_var, bn.num_batches_tracked if use_batch else None, stats, ws, ws.numel())
+       bn.running_var, bn.num_batches_tracked if use_batch else None, stats, valid, ws, ws.numel())
     out = torch.empty_like(y)
     _c("gnn_bn_act_fwd", y, stats, bn.weight, bn.bias, skip, rows, ch, 1 if relu else 0, out)
     return out, stats, use_batch
@@ -534,8 +538,22 @@ def _lin_bn_eval(mm, X, lin: nn.Linear, bn: nn.BatchNorm1d, skip, relu: bool):
 
 
 def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_graphs, save: bool, graph=None):
-    _check_inputs(x_idx, edge_index, edge_attr, batch)
+    """The forward kernel chain.  `graph`: a prebuilt `GraphStructure`, or a compact store batch
+    (`data.compact.CompactBatch`: uint8 atom features + int32 CSR straight from `gnn_compact_collate`, possibly padded
+    to a shape bucket - then x_idx / edge_index / edge_attr / batch are ignored and the output has one extra row, the
+    padding graph)."""
+    compact = graph is not None and getattr(graph, "is_compact", False)
     pp, mp = model.pna_params, model.mlp_params
+    valid_nodes = valid_graphs = None
+    if compact:
+        if bool(graph.self_loops) != bool(pp.self_loops):
+            raise ValueError("the compact batch was built with self_loops=%s but the model has self_loops=%s"
+                             % (graph.self_loops, pp.self_loops))
+        x_idx, num_graphs = graph.x, graph.b
+        _require_cuda(x_idx, "the compact batch")
+        valid_nodes, valid_graphs = graph.valid[0:1], graph.valid[1:2]
+    else:
+        _check_inputs(x_idx, edge_index, edge_attr, batch)
     if model.training and (pp.dropout > 0.0 or mp.dropout > 0.0):
         raise NotImplementedError("gnnepcsaft_b200: dropout > 0 in training mode is not implemented "
                                   "(the reference configs use dropout_rate = 0.0)")
@@ -546,11 +564,12 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
     C = T * F
     L = pp.propagation_depth
     x_idx = x_idx.contiguous()
-    edge_index = edge_index.contiguous()
-    edge_attr = edge_attr.contiguous()
-    if batch is not None:
-        batch = batch.contiguous()
-    n = int(x_idx.shape[0])
+    if not compact:
+        edge_index = edge_index.contiguous()
+        edge_attr = edge_attr.contiguous()
+        if batch is not None:
+            batch = batch.contiguous()
+    n = int(graph.n) if compact else int(x_idx.shape[0])
     training = model.training
     f32 = dict(dtype=torch.float32, device=dev)
 
@@ -563,7 +582,8 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
     atom_tab = model.node_embed.atom_embedding_list[0].weight
     total_rows = sum(ATOM_FEATURE_DIMS)
     x = torch.empty(n, H, **f32)
-    _c("gnn_atom_embed_fwd", x_idx, n, atom_tab, row_off, total_rows, H, x, g.err)
+    _c("gnn_atom_embed_u8_fwd" if compact else "gnn_atom_embed_fwd", x_idx, n, atom_tab, row_off, total_rows, H, x,
+       g.err)
     if graph is None:
         g.defer_check()
 
@@ -683,7 +703,8 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
             y = torch.empty(n, H, **f32)
             _lin_fwd(mm, O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H)
             rec.y = y
-            x, rec.stats, rec.bn_batch = _bn_forward(y, bn, training, rec.x_in if pp.skip_connections else None, True)
+            x, rec.stats, rec.bn_batch = _bn_forward(y, bn, training, rec.x_in if pp.skip_connections else None, True,
+                                                     valid_nodes)
         if save:
             layers.append(rec)
 
@@ -709,7 +730,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
            lin.out_features, lin.in_features, 0, z, lin.out_features)
         rec.z = z
         if bn is not None:
-            hcur, rec.stats, rec.bn_batch = _bn_forward(z, bn, training, None, True)
+            hcur, rec.stats, rec.bn_batch = _bn_forward(z, bn, training, None, True, valid_graphs)
         else:
             hcur = z
         head.append(rec)
@@ -727,6 +748,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         sv.x_idx, sv.x_final, sv.n, sv.num_graphs = x_idx, x, n, num_graphs
         sv.layer_stride, sv.tower_stride_pre = layer_stride, tower_stride_pre
         sv.training, sv.mm, sv.fold = training, mm, fold
+        sv.compact, sv.valid_nodes, sv.valid_graphs = compact, valid_nodes, valid_graphs
     return out, sv
 
 
@@ -748,13 +770,13 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
         off = model._offset_of(p)
         return grad_arena[off:off + p.numel()].view(p.shape)
 
-    def bn_backward(dOut, rec_y, stats, bn, relu, use_batch):
+    def bn_backward(dOut, rec_y, stats, bn, relu, use_batch, valid):
         rows, ch = rec_y.shape
         nbytes = _lib.query("gnn_bn_workspace_bytes", rows, ch)
         ws = _WS.get("bn", nbytes, dev)
         dY = torch.empty_like(rec_y)
         _c("gnn_bn_act_bwd", dOut, rec_y, stats, bn.weight, bn.bias, rows, ch, 1 if relu else 0,
-           1 if use_batch else 0, dY, gview(bn.weight), gview(bn.bias), ws, ws.numel())
+           1 if use_batch else 0, dY, gview(bn.weight), gview(bn.bias), valid, ws, ws.numel())
         return dY
 
     # ---- head
@@ -762,7 +784,7 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
     for rec in reversed(sv.head):
         lin = rec.lin
         if rec.bn is not None:
-            d = bn_backward(d, rec.z, rec.stats, rec.bn, True, rec.bn_batch)
+            d = bn_backward(d, rec.z, rec.stats, rec.bn, True, rec.bn_batch, sv.valid_graphs)
         rows = rec.inp.shape[0]
         _lin_wgrad(mm, d, lin.out_features, rec.inp, lin.in_features, rows, lin.out_features,
            lin.in_features, gview(lin.weight), lin.in_features, gview(lin.bias))
@@ -780,7 +802,7 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
         conv, bn = model.convs[l], model.batch_norms[l].module
         rec = sv.layers[l]
         x_in = rec.x_in
-        dy = bn_backward(dx, rec.y, rec.stats, bn, True, rec.bn_batch)
+        dy = bn_backward(dx, rec.y, rec.stats, bn, True, rec.bn_batch, sv.valid_nodes)
         if not pp.skip_connections:
             dx = torch.zeros(n, H, **f32)        # else: dx (the skip gradient) keeps accumulating
         # lin
@@ -854,7 +876,8 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
 
     # ---- encoders
     atom_tab = model.node_embed.atom_embedding_list[0].weight
-    _c("gnn_atom_embed_bwd", sv.x_idx, n, dx, model._consts(dev), sum(ATOM_FEATURE_DIMS), H, gview(atom_tab))
+    _c("gnn_atom_embed_u8_bwd" if sv.compact else "gnn_atom_embed_bwd", sv.x_idx, n, dx, model._consts(dev),
+       sum(ATOM_FEATURE_DIMS), H, gview(atom_tab))
     if L > 0:
         conv0 = model.convs[0]
         if sv.fold:     # dVx of all layers -> post_nns / pre_nns (destination third) weight gradients, one launch

@@ -92,12 +92,43 @@ int gnn_collate_gather(const int64_t* ids, int64_t num_ids, const int64_t* node_
                        int64_t* x, int64_t* edge_index, int64_t* edge_attr, int64_t* batch,
                        void* stream);
 
+/* Compact device store -> batch (dataset residency).  The store holds ONE destination CSR over the
+ * whole dataset (gnn_build_csr on the concatenated graphs, once): node_off / slot_off int32 [G+1] are the node and
+ * CSR-slot ranges of every graph, store_x uint8 [sumN, 9] (gnn_atom_features_to_u8), store_rowptr int32 [sumN+1],
+ * store_col_src int32 (store-global node ids) / store_col_code uint8 [sumE'], store_para float [G, P] (may be NULL).
+ * For graph ids int64 [B] it writes what the model kernels consume, with no sort and no scan over edges:
+ *   x uint8 [Np, 9], rowptr int32 [Np+1], col_src int32 [Ep], col_code uint8 [Ep], node_graph int32 [Np],
+ *   graph_ptr int32 [B+2], para float [(B+1) P], valid int32 [4] = {N, B, E', 0}
+ * Np = pad_nodes >= N and Ep = pad_slots >= E' (else GNN_INPUT_ERR_EDGE_INDEX in err_flag): the surplus becomes graph
+ * B, isolated padding nodes holding the surplus slots as self-edges, so every batch of a (Np, Ep, B) shape bucket
+ * issues identical launches and one captured CUDA graph serves the bucket.  pad = exact sizes gives an empty graph B.
+ * Replaces PyG DataLoader / Collater (train.py:74-79) + add_self_loops (models.py:118-121) for store-resident data. */
+int64_t gnn_compact_collate_workspace_bytes(int64_t num_ids);
+int gnn_compact_collate(const int64_t* ids, int64_t num_ids, int64_t num_store_graphs,
+                        const int32_t* node_off, const int32_t* slot_off, const uint8_t* store_x,
+                        const int32_t* store_rowptr, const int32_t* store_col_src,
+                        const uint8_t* store_col_code, const float* store_para, int num_para,
+                        int64_t pad_nodes, int64_t pad_slots, uint8_t* x, int32_t* rowptr,
+                        int32_t* col_src, uint8_t* col_code, int32_t* node_graph, int32_t* graph_ptr,
+                        float* para, int32_t* valid, int32_t* err_flag, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+/* int64 [N, 9] OGB atom features -> uint8 (values outside [0, 255]: GNN_INPUT_ERR_ATOM_FEATURE) */
+int gnn_atom_features_to_u8(const int64_t* x, int64_t num_nodes, uint8_t* out, int32_t* err_flag,
+                            void* stream);
+
 /* ---------------------------------------------------------------- encoders
  * OGB AtomEncoder (models.py:65,122): out[i,:] = sum_k table[row_off[k] + x[i,k], :].
  * `tables` is the 9 embedding weights stacked along rows (174 rows), row_off int32[9]. */
 int gnn_atom_embed_fwd(const int64_t* x, int64_t num_nodes, const float* tables,
                        const int32_t* row_off, int32_t total_rows, int hidden, float* out,
                        int32_t* err_flag, void* stream);
+/* the same on compact uint8 features (device store / compact batches; every OGB atom feature is < 119) */
+int gnn_atom_embed_u8_fwd(const uint8_t* x, int64_t num_nodes, const float* tables,
+                          const int32_t* row_off, int32_t total_rows, int hidden, float* out,
+                          int32_t* err_flag, void* stream);
+int gnn_atom_embed_u8_bwd(const uint8_t* x, int64_t num_nodes, const float* dout,
+                          const int32_t* row_off, int32_t total_rows, int hidden, float* dtables,
+                          void* stream);
 /* d tables[row] += sum_i dout[i,:] (tables gradient must be zeroed by the caller) */
 int gnn_atom_embed_bwd(const int64_t* x, int64_t num_nodes, const float* dout,
                        const int32_t* row_off, int32_t total_rows, int hidden, float* dtables,
@@ -332,19 +363,24 @@ int gnn_tc_pna_projsrc_wgrad(const float* dPsrc, const float* x, int64_t num_nod
  * Replaces PyG BatchNorm / torch BatchNorm1d + F.relu + skip (models.py:128-131, head BN).
  * Training: batch statistics (biased var for normalisation, unbiased for running_var,
  * momentum 0.1), num_batches_tracked += 1.  stats = [mean[C] | rstd[C]] is written for
- * backward.  Eval: stats derived from running_mean / running_var. */
+ * backward.  Eval: stats derived from running_mean / running_var.
+ * valid_rows (device int32[1], may be NULL): padded batches - only the first *valid_rows rows are real (the rest
+ * belongs to the padding graph of a shape bucket, see gnn_compact_collate): statistics, backward sums and their
+ * 1/n use that count and the gradient rows of the padding are written as zero.  The count is read on the device
+ * so that one captured CUDA graph serves every batch of a bucket. */
 int64_t gnn_bn_workspace_bytes(int64_t rows, int C);
 int gnn_bn_stats(const float* Y, int64_t rows, int C, int training, float eps, float momentum,
                  float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                 float* stats, void* workspace, int64_t workspace_bytes, void* stream);
+                 float* stats, const int32_t* valid_rows, void* workspace, int64_t workspace_bytes,
+                 void* stream);
 /* out = relu(gamma*(Y-mean)*rstd+beta) [+ skip]  (relu: 0/1, skip may be NULL) */
 int gnn_bn_act_fwd(const float* Y, const float* stats, const float* gamma, const float* beta,
                    const float* skip, int64_t rows, int C, int relu, float* out, void* stream);
 /* dY from dOut; also dgamma[C] += , dbeta[C] += .  training=0 uses the eval formula. */
 int gnn_bn_act_bwd(const float* dOut, const float* Y, const float* stats, const float* gamma,
                    const float* beta, int64_t rows, int C, int relu, int training, float* dY,
-                   float* dgamma, float* dbeta, void* workspace, int64_t workspace_bytes,
-                   void* stream);
+                   float* dgamma, float* dbeta, const int32_t* valid_rows, void* workspace,
+                   int64_t workspace_bytes, void* stream);
 
 /* Inference fast path: eval-mode BatchNorm folded into the preceding Linear, then Linear + ReLU + skip add in
  * one tensor-core GEMM (replaces lin -> BatchNorm -> relu -> x + x_prev of models.py:128-131 and the head's
@@ -366,9 +402,11 @@ int gnn_segment_pool_fwd(const float* x, const int32_t* graph_ptr, int64_t num_g
 int gnn_segment_pool_bwd(const float* dout, const int32_t* node_graph, int64_t num_nodes, int C,
                          int accumulate, float* dx, void* stream);
 /* torchmetrics MAPE (models.py:194): loss[0] = mean(|p-t| / max(|t|,1.17e-6));
- * dpred = d loss / d pred * grad_scale.  loss_accum (optional) += loss. */
+ * dpred = d loss / d pred * grad_scale.  valid_rows (device int32[1], may be NULL) with row_len = num_para:
+ * padded batches - only the first *valid_rows rows of pred / target are real graphs; the mean runs over those and
+ * the gradient rows of the padding graph are written as zero (see gnn_compact_collate). */
 int gnn_mape_fwd_bwd(const float* pred, const float* target, int64_t numel, float grad_scale,
-                     float* loss, float* dpred, void* stream);
+                     float* loss, float* dpred, const int32_t* valid_rows, int row_len, void* stream);
 /* AdamW(amsgrad=True) + CosineAnnealingWarmRestarts(T_0) stepped per step
  * (models.py:162-188).  step_count int64[1] on device is read (t = step_count before this
  * step), the caller bumps it with gnn_step_increment.  grad_scale multiplies grads (1/world). */

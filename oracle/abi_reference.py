@@ -117,6 +117,63 @@ def gnn_collate_gather(ids, nb, node_slices, edge_slices, sx, sei, store_e, sea,
         ei[:, oe: oe + e1 - e0] = sei[:, e0:e1] + on
 
 
+def gnn_compact_collate_workspace_bytes(nb):
+    return 256
+
+
+def gnn_compact_collate(ids, nb, num_store_graphs, node_off, slot_off, sx, s_rowptr, s_col_src, s_col_code, s_para,
+                        num_para, pad_nodes, pad_slots, x, rowptr, col_src, col_code, node_graph, graph_ptr, para, valid,
+                        err_flag=None, workspace=None, workspace_bytes=0, stream=None):
+    if err_flag is not None:
+        err_flag.zero_()
+    on, os_ = 0, 0
+    sizes = [(int(node_off[g + 1] - node_off[g]), int(slot_off[g + 1] - slot_off[g])) for g in ids[:nb].tolist()]
+    tot_n, tot_s = sum(a for a, _ in sizes), sum(b for _, b in sizes)
+    if tot_n > pad_nodes or tot_s > pad_slots:
+        if err_flag is not None:
+            err_flag |= 1
+        return
+    for i, g in enumerate(ids[:nb].tolist()):
+        n0, s0 = int(node_off[g]), int(slot_off[g])
+        cn, cs = sizes[i]
+        x[on:on + cn] = sx[n0:n0 + cn]
+        rowptr[on:on + cn] = s_rowptr[n0:n0 + cn] - s0 + os_
+        node_graph[on:on + cn] = i
+        col_src[os_:os_ + cs] = s_col_src[s0:s0 + cs] - n0 + on
+        col_code[os_:os_ + cs] = s_col_code[s0:s0 + cs]
+        graph_ptr[i] = on
+        if para is not None:
+            para[i * num_para:(i + 1) * num_para] = s_para.reshape(-1)[g * num_para:(g + 1) * num_para]
+        on += cn
+        os_ += cs
+    nd, d = pad_nodes - on, pad_slots - os_
+    rowptr[pad_nodes] = pad_slots
+    graph_ptr[nb] = on
+    graph_ptr[nb + 1] = pad_nodes
+    valid[0], valid[1], valid[2], valid[3] = on, nb, os_, 0
+    if para is not None:
+        para[nb * num_para:(nb + 1) * num_para] = 1.0
+    if nd == 0:
+        if d != 0 and err_flag is not None:
+            err_flag |= 1
+        return
+    base, rem = d // nd, d % nd
+    for k in range(nd):
+        node, start, cnt = on + k, os_ + k * base + min(k, rem), base + (1 if k < rem else 0)
+        x[node] = 0
+        rowptr[node] = start
+        node_graph[node] = nb
+        col_src[start:start + cnt] = node
+        col_code[start:start + cnt] = 0
+
+
+def gnn_atom_features_to_u8(x, n, out, err_flag=None, stream=None):
+    v = x[:n]
+    if err_flag is not None and bool(((v < 0) | (v > 255)).any()):
+        err_flag |= 16
+    out[:n] = v.clamp(0, 255).to(torch.uint8)
+
+
 # ------------------------------------------------------------------ encoders
 def gnn_atom_embed_fwd(x, n, tables, row_off, total_rows, hidden, out, err_flag=None, stream=None):
     tab = _mat(tables, total_rows, hidden, hidden)
@@ -128,6 +185,14 @@ def gnn_atom_embed_fwd(x, n, tables, row_off, total_rows, hidden, out, err_flag=
             err_flag |= 16
         acc = acc + tab[row_off[k].long() + v.clamp(0, hi - 1)]
     out[:n] = acc
+
+
+def gnn_atom_embed_u8_fwd(x, n, tables, row_off, total_rows, hidden, out, err_flag=None, stream=None):
+    gnn_atom_embed_fwd(x.long(), n, tables, row_off, total_rows, hidden, out, err_flag)
+
+
+def gnn_atom_embed_u8_bwd(x, n, dout, row_off, total_rows, hidden, dtables, stream=None):
+    gnn_atom_embed_bwd(x.long(), n, dout, row_off, total_rows, hidden, dtables)
 
 
 def gnn_atom_embed_bwd(x, n, dout, row_off, total_rows, hidden, dtables, stream=None):
@@ -554,8 +619,10 @@ def gnn_bn_workspace_bytes(rows, c):
     return 256
 
 
-def gnn_bn_stats(Y, rows, c, training, eps, momentum, running_mean, running_var, nbt, stats, workspace,
+def gnn_bn_stats(Y, rows, c, training, eps, momentum, running_mean, running_var, nbt, stats, valid_rows, workspace,
                  workspace_bytes, stream=None):
+    if valid_rows is not None:          # padded batch: only the first valid_rows rows are real
+        rows = max(min(rows, int(valid_rows)), 0)
     if training:
         y = Y[:rows].double()
         mean = y.mean(0)
@@ -582,8 +649,11 @@ def gnn_bn_act_fwd(Y, stats, gamma, beta, skip, rows, c, relu, out, stream=None)
     out[:rows] = v
 
 
-def gnn_bn_act_bwd(dOut, Y, stats, gamma, beta, rows, c, relu, training, dY, dgamma, dbeta, workspace,
+def gnn_bn_act_bwd(dOut, Y, stats, gamma, beta, rows, c, relu, training, dY, dgamma, dbeta, valid_rows, workspace,
                    workspace_bytes, stream=None):
+    if valid_rows is not None:
+        dY[:rows] = 0
+        rows = max(min(rows, int(valid_rows)), 0)
     ga, be = _flat(gamma, c), _flat(beta, c)
     yh = (Y[:rows] - stats[:c]) * stats[c:2 * c]
     dz = dOut[:rows].clone()
@@ -626,13 +696,17 @@ def gnn_segment_pool_bwd(dout, node_graph, n, c, accumulate, dx, stream=None):
     dx[:n] = dx[:n] + v if accumulate else v
 
 
-def gnn_mape_fwd_bwd(pred, target, numel, grad_scale, loss, dpred, stream=None):
+def gnn_mape_fwd_bwd(pred, target, numel, grad_scale, loss, dpred, valid_rows=None, row_len=1, stream=None):
+    if valid_rows is not None:          # padded batch: the padding graph has no loss and a zero gradient
+        if dpred is not None:
+            dpred.reshape(-1)[:numel] = 0
+        numel = max(min(numel, int(valid_rows) * row_len), 0)
     p, t = pred.reshape(-1)[:numel], target.reshape(-1)[:numel]
     den = t.abs().clamp(min=1.17e-06)
     if loss is not None:
-        loss[0] = ((p - t).abs() / den).sum() / numel
+        loss[0] = ((p - t).abs() / den).sum() / max(numel, 1)
     if dpred is not None:
-        dpred.reshape(-1)[:numel] = torch.sign(p - t) / den / numel * grad_scale
+        dpred.reshape(-1)[:numel] = torch.sign(p - t) / den / max(numel, 1) * grad_scale
 
 
 def gnn_adamw_amsgrad_step(param, grad, m, v, vmax, numel, step_count, lr0, beta1, beta2, eps, wd, t0, grad_scale,

@@ -371,7 +371,7 @@ def test_batchnorm_fwd_bwd(rows, C):
         nbt = torch.tensor([3], dtype=torch.int64)
         stats = torch.zeros(2 * C)
         ws = torch.zeros(nbytes, dtype=torch.uint8)
-        cpu, gpu = run_both("gnn_bn_stats", Y, rows, C, training, 1e-5, 0.1, rm, rv, nbt, stats, ws, nbytes)
+        cpu, gpu = run_both("gnn_bn_stats", Y, rows, C, training, 1e-5, 0.1, rm, rv, nbt, stats, None, ws, nbytes)
         for i, what in ((6, "running_mean"), (7, "running_var"), (9, "stats")):
             close(gpu[i], cpu[i], 1e-5, what)
         assert int(gpu[8].item()) == int(cpu[8].item()) == (4 if training else 3)
@@ -393,7 +393,7 @@ def test_batchnorm_fwd_bwd(rows, C):
         dOut = torch.randn(rows, C, generator=g)
         ref_out.backward(dOut)
         dY, dga, dbe = torch.zeros(rows, C), torch.zeros(C), torch.zeros(C)
-        cpu, gpu = run_both("gnn_bn_act_bwd", dOut, Y, stats, gamma, beta, rows, C, 1, training, dY, dga, dbe, ws,
+        cpu, gpu = run_both("gnn_bn_act_bwd", dOut, Y, stats, gamma, beta, rows, C, 1, training, dY, dga, dbe, None, ws,
                             nbytes)
         # normalise by the scale of the incoming gradient: with very few rows the BN backward is
         # dominated by cancellation and the result is orders of magnitude below its inputs
@@ -402,6 +402,42 @@ def test_batchnorm_fwd_bwd(rows, C):
         assert err <= 2e-5, f"bn backward vs torch autograd: {err:.2e}"
         close(gpu[10], bn.weight.grad, 2e-5, "dgamma")
         close(gpu[11], bn.bias.grad, 2e-5, "dbeta")
+
+
+@pytest.mark.parametrize("rows,valid,C", [(5000, 4321, 64), (40, 37, 16), (300, 300, 32), (9, 2, 8)])
+def test_batchnorm_padded_rows(rows, valid, C):
+    """valid_rows: a padded batch must give exactly the statistics / gradients of its first `valid` rows (whatever the
+    padding rows contain) and zero gradient rows for the padding."""
+    g = torch.Generator().manual_seed(rows + C)
+    Y = torch.randn(rows, C, generator=g) * 2 + 0.5
+    Y[valid:] = 1e6                                  # garbage in the padding must not leak into anything
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    nbytes = _lib.query("gnn_bn_workspace_bytes", rows, C)
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+    vr = torch.tensor([valid], dtype=torch.int32, device=DEV)
+    dOut = torch.randn(rows, C, generator=g)
+    dOut[valid:] = -1e6
+    res = {}
+    for name, r, v in (("padded", rows, vr), ("plain", valid, None)):
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        nbt = torch.zeros(1, dtype=torch.int64, device=DEV)
+        stats = torch.zeros(2 * C, device=DEV)
+        Yd, dOd = Y[:r].contiguous().to(DEV), dOut[:r].contiguous().to(DEV)
+        _lib.call("gnn_bn_stats", Yd, r, C, 1, 1e-5, 0.1, rm, rv, nbt, stats, v, ws, nbytes, _lib.stream_ptr())
+        dY = torch.full((r, C), 3.0, device=DEV)
+        dga, dbe = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        _lib.call("gnn_bn_act_bwd", dOd, Yd, stats, gamma.to(DEV), beta.to(DEV), r, C, 1, 1, dY, dga, dbe, v, ws, nbytes,
+                  _lib.stream_ptr())
+        torch.cuda.synchronize()
+        res[name] = [t.cpu() for t in (stats, rm, rv, dY, dga, dbe)]
+    for a, b, what in zip(res["padded"], res["plain"], ("stats", "running_mean", "running_var", "dY", "dgamma", "dbeta")):
+        if what == "dY":
+            assert torch.all(a[valid:] == 0), "gradient of the padding rows must be zero"
+            a = a[:valid]
+        close(a, b, 1e-6, what)
+    cpu, gpu = run_both("gnn_bn_stats", Y, rows, C, 1, 1e-5, 0.1, torch.zeros(C), torch.ones(C),
+                        torch.zeros(1, dtype=torch.int64), torch.zeros(2 * C), vr.cpu(), ws.cpu(), nbytes)
+    close(gpu[9], cpu[9], 1e-5, "padded stats vs reference")
 
 
 def test_pool_mape():
@@ -423,7 +459,7 @@ def test_pool_mape():
     pred, tgt = torch.randn(700, 5, generator=g), torch.rand(700, 5, generator=g) * 4 + 0.5
     tgt[0, 0] = 0.0                                       # exercises the 1.17e-6 clamp
     loss, dpred = torch.zeros(1), torch.zeros(700, 5)
-    cpu, gpu = run_both("gnn_mape_fwd_bwd", pred, tgt, 3500, 0.5, loss, dpred)
+    cpu, gpu = run_both("gnn_mape_fwd_bwd", pred, tgt, 3500, 0.5, loss, dpred, None, 5)
     close(gpu[-2], cpu[-2], 1e-6, "mape")
     close(gpu[-1], cpu[-1], 1e-6, "dmape")
 

@@ -21,9 +21,9 @@ ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 s = _lib.stream_ptr()
 calls = {
-    "bn_stats": lambda: _lib.call("gnn_bn_stats", Y, rows, C, 1, 1e-5, 0.1, rm, rv, nbt, stats, ws, wsb, s),
+    "bn_stats": lambda: _lib.call("gnn_bn_stats", Y, rows, C, 1, 1e-5, 0.1, rm, rv, nbt, stats, None, ws, wsb, s),
     "bn_act_fwd": lambda: _lib.call("gnn_bn_act_fwd", Y, stats, ga, be, dO, rows, C, 1, out, s),
-    "bn_act_bwd": lambda: _lib.call("gnn_bn_act_bwd", dO, Y, stats, ga, be, rows, C, 1, 1, dY, dg, db, ws, wsb, s),
+    "bn_act_bwd": lambda: _lib.call("gnn_bn_act_bwd", dO, Y, stats, ga, be, rows, C, 1, 1, dY, dg, db, None, ws, wsb, s),
 }
 for name, fn in calls.items():
     for cold in (0, 1):
