@@ -416,9 +416,10 @@ extern "C" int gnn_collate_gather(const int64_t* ids, int64_t nb, const int64_t*
 // DataLoader / Collater (reference train.py:74-79) AND add_self_loops + the scatter index handling (models.py:118-121)
 // for batches drawn from the store; the int64 PyG-layout path (gnn_collate_gather + gnn_build_csr) stays for batches
 // that arrive as PyG tensors.
-// Padding: the outputs are sized (pad_nodes, pad_slots) >= (N, E'); the surplus forms one extra graph (index B) of
-// isolated nodes that carry the surplus CSR slots as self-edges, so every batch of a shape bucket runs the same
-// launches (CUDA-graph replay).  valid = {N, B, E'} tells the BatchNorm kernels which rows are real.
+// Padding: the outputs are sized (pad_nodes, pad_slots) >= (N, E') and hold cap >= B graphs; graphs B .. cap-1 are
+// empty and the node / slot surplus forms one extra graph (index cap) of isolated nodes that carry the surplus CSR
+// slots as self-edges, so every batch of a shape bucket runs the same launches (CUDA-graph replay).
+// valid = {N, B, E'} tells the BatchNorm / loss kernels which rows are real.
 __global__ void __launch_bounds__(1024)
 compact_offsets_kernel(const int64_t* __restrict__ ids, int64_t nb, int64_t num_store_graphs,
                        const int* __restrict__ node_off, const int* __restrict__ slot_off, int* __restrict__ nptr,
@@ -525,32 +526,37 @@ compact_gather_kernel(const int64_t* __restrict__ ids, int64_t nb, int64_t num_s
 }
 
 __global__ void __launch_bounds__(256)
-compact_pad_kernel(int64_t nb, const int* __restrict__ nptr, const int* __restrict__ sptr, int64_t pad_nodes,
-                   int64_t pad_slots, int num_para, uint8_t* __restrict__ x, int* __restrict__ rowptr,
+compact_pad_kernel(int64_t nb, int64_t cap, const int* __restrict__ nptr, const int* __restrict__ sptr, int64_t pad_nodes,
+                   int64_t pad_slots, int own_surplus, int num_para, uint8_t* __restrict__ x, int* __restrict__ rowptr,
                    int* __restrict__ col_src, uint8_t* __restrict__ col_code, int* __restrict__ node_graph,
                    int* __restrict__ graph_ptr, float* __restrict__ para, int* __restrict__ valid, int* err) {
     const int n = nptr[nb], e = sptr[nb];
     if (n > pad_nodes || e > pad_slots) return;          // reported by the gather kernel
     const int nd = (int)pad_nodes - n, d = (int)pad_slots - e;      // padding nodes / surplus slots
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        rowptr[pad_nodes] = (int)pad_slots;
-        graph_ptr[nb] = n;
-        graph_ptr[nb + 1] = (int)pad_nodes;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (tid == 0) {
+        rowptr[pad_nodes] = own_surplus ? (int)pad_slots : e;
+        graph_ptr[cap + 1] = (int)pad_nodes;
         valid[0] = n;
         valid[1] = (int)nb;
         valid[2] = e;
         valid[3] = 0;
-        if (nd == 0 && d != 0 && err) atomicOr(err, GNN_INPUT_ERR_EDGE_INDEX);   // surplus slots need a padding node
-        if (para != nullptr)
-            for (int k = 0; k < num_para; ++k) para[nb * num_para + k] = 1.0f;    // target of the padding graph (unused)
+        if (own_surplus && nd == 0 && d != 0 && err) atomicOr(err, GNN_INPUT_ERR_EDGE_INDEX);   // surplus slots need a padding node
     }
+    // graphs nb .. cap-1 are empty (a batch with fewer graphs than the bucket holds), graph `cap` is the padding graph
+    for (int64_t g = nb + tid; g <= cap; g += nth) graph_ptr[g] = n;
+    if (para != nullptr)
+        for (int64_t k = nb * num_para + tid; k < (cap + 1) * num_para; k += nth) para[k] = 1.0f;   // unused targets
     if (nd == 0) return;
-    const int base = d / nd, rem = d % nd;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nd; k += gridDim.x * blockDim.x) {
+    // own_surplus: the surplus slots are spread over the padding nodes as self-edges (models with per-slot tensors:
+    // every slot of the padded arrays then belongs to a node); otherwise the padding nodes have no in-edges and the
+    // surplus slots are simply unused capacity
+    const int base = own_surplus ? d / nd : 0, rem = own_surplus ? d % nd : 0;
+    for (int k = tid; k < nd; k += nth) {
         const int node = n + k, start = e + k * base + min(k, rem), cnt = base + (k < rem ? 1 : 0);
         for (int j = 0; j < GNN_NUM_ATOM_FEATS; ++j) x[(int64_t)node * GNN_NUM_ATOM_FEATS + j] = 0;
         rowptr[node] = start;
-        node_graph[node] = (int)nb;
+        node_graph[node] = (int)cap;
         for (int j = 0; j < cnt; ++j) {
             col_src[start + j] = node;
             col_code[start + j] = 0;
@@ -561,14 +567,15 @@ compact_pad_kernel(int64_t nb, const int* __restrict__ nptr, const int* __restri
 extern "C" int64_t gnn_compact_collate_workspace_bytes(int64_t num_ids) {
     return gnn_align_up(2 * (num_ids + 1) * (int64_t)sizeof(int), 256);
 }
-extern "C" int gnn_compact_collate(const int64_t* ids, int64_t nb, int64_t num_store_graphs, const int32_t* node_off,
+extern "C" int gnn_compact_collate(const int64_t* ids, int64_t nb, int64_t cap, int64_t num_store_graphs, const int32_t* node_off,
                                    const int32_t* slot_off, const uint8_t* store_x, const int32_t* store_rowptr,
                                    const int32_t* store_col_src, const uint8_t* store_col_code, const float* store_para,
-                                   int num_para, int64_t pad_nodes, int64_t pad_slots, uint8_t* x, int32_t* rowptr,
+                                   int num_para, int64_t pad_nodes, int64_t pad_slots, int own_surplus, uint8_t* x,
+                                   int32_t* rowptr,
                                    int32_t* col_src, uint8_t* col_code, int32_t* node_graph, int32_t* graph_ptr,
                                    float* para, int32_t* valid, int32_t* err_flag, void* workspace,
                                    int64_t workspace_bytes, void* stream) {
-    if (nb < 1 || num_store_graphs < 1 || pad_nodes < 0 || pad_slots < 0 || num_para < 0) return GNN_ERR_BAD_ARG;
+    if (nb < 1 || cap < nb || num_store_graphs < 1 || pad_nodes < 0 || pad_slots < 0 || num_para < 0) return GNN_ERR_BAD_ARG;
     if (pad_nodes >= (1ll << 31) || pad_slots >= (1ll << 31)) return GNN_ERR_TOO_LARGE;
     if (workspace_bytes < gnn_compact_collate_workspace_bytes(nb)) return GNN_ERR_WORKSPACE;
     cudaStream_t st = gnn_stream(stream);
@@ -577,13 +584,13 @@ extern "C" int gnn_compact_collate(const int64_t* ids, int64_t nb, int64_t num_s
     if (err_flag) cudaMemsetAsync(err_flag, 0, sizeof(int), st);
     compact_offsets_kernel<<<1, 1024, 0, st>>>(ids, nb, num_store_graphs, node_off, slot_off, nptr, sptr, err_flag);
     int64_t blocks = gnn_ceil_div(nb, 8);
-    int64_t cap = (int64_t)gnn_sm_count() * 8;
-    if (blocks > cap) blocks = cap;
+    const int64_t max_blocks = (int64_t)gnn_sm_count() * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
     compact_gather_kernel<<<(unsigned)blocks, 256, 0, st>>>(ids, nb, num_store_graphs, node_off, slot_off, store_x,
                                                             store_rowptr, store_col_src, store_col_code, store_para,
                                                             num_para, nptr, sptr, pad_nodes, pad_slots, x, rowptr, col_src,
                                                             col_code, node_graph, graph_ptr, para, err_flag);
-    compact_pad_kernel<<<32, 256, 0, st>>>(nb, nptr, sptr, pad_nodes, pad_slots, num_para, x, rowptr, col_src, col_code,
+    compact_pad_kernel<<<32, 256, 0, st>>>(nb, cap, nptr, sptr, pad_nodes, pad_slots, own_surplus, num_para, x, rowptr, col_src, col_code,
                                            node_graph, graph_ptr, para, valid, err_flag);
     return gnn_launch_status();
 }

@@ -23,20 +23,23 @@ from .. import _lib
 from .synth import PackedGraphs
 
 MIN_PAD_NODES = 16          # every padded batch has at least this many padding nodes ...
-MAX_SURPLUS_PER_NODE = 128  # ... and no padding node carries more than this many surplus CSR slots (as self-edges)
+MAX_SURPLUS_PER_NODE = 32   # ... and (own_surplus) no padding node carries more surplus CSR slots than this
 
 
 class CompactBatch:
     """x uint8 [Np,9] | rowptr i32 [Np+1] | col_src i32 [Ep] | col_code u8 [Ep] | node_graph i32 [Np] |
-    graph_ptr i32 [B+2] | para f32 [(B+1) P] | valid i32 [4] = {N, B, E', 0}.  Graph B is the padding graph."""
+    graph_ptr i32 [cap+2] | para f32 [(cap+1) P] | valid i32 [4] = {N, B, E', 0}.  `num_graphs` = cap is the graph
+    capacity of the bucket (B <= cap real graphs, graphs B..cap-1 empty); graph `cap` is the padding graph."""
 
     FIELDS = ("x", "rowptr", "col_src", "col_code", "node_graph", "graph_ptr", "para", "valid")
     is_compact = True
 
-    def __init__(self, num_graphs: int, pad_nodes: int, pad_slots: int, self_loops: bool, **tensors):
-        self.num_graphs = int(num_graphs)           # real graphs B (outputs have B + 1 rows; use [:B])
+    def __init__(self, num_graphs: int, pad_nodes: int, pad_slots: int, self_loops: bool, own_surplus: bool = False,
+                 **tensors):
+        self.num_graphs = int(num_graphs)           # graph capacity (outputs have cap + 1 rows; rows [:B] are real)
         self.pad_nodes, self.pad_slots = int(pad_nodes), int(pad_slots)
         self.self_loops = bool(self_loops)
+        self.own_surplus = bool(own_surplus)        # surplus CSR slots are self-edges of the padding nodes
         for k in self.FIELDS:
             setattr(self, k, tensors.get(k))
         self.err = tensors.get("err")
@@ -68,7 +71,7 @@ class CompactBatch:
     def _apply(self, fn):
         kw = {k: (fn(getattr(self, k)) if getattr(self, k) is not None else None) for k in self.FIELDS}
         kw["err"] = fn(self.err) if self.err is not None else None
-        return CompactBatch(self.num_graphs, self.pad_nodes, self.pad_slots, self.self_loops, **kw)
+        return CompactBatch(self.num_graphs, self.pad_nodes, self.pad_slots, self.self_loops, self.own_surplus, **kw)
 
     def to(self, *args, **kwargs):
         return self._apply(lambda t: t.to(*args, **kwargs))
@@ -81,7 +84,8 @@ class CompactBatch:
 
     def copy_from(self, other: "CompactBatch"):
         """Copy another batch of the same bucket (e.g. a pinned host batch) into these buffers, stream-ordered."""
-        if (other.num_graphs, other.pad_nodes, other.pad_slots) != (self.num_graphs, self.pad_nodes, self.pad_slots):
+        if ((other.num_graphs, other.pad_nodes, other.pad_slots, other.own_surplus) !=
+                (self.num_graphs, self.pad_nodes, self.pad_slots, self.own_surplus)):
             raise ValueError("copy_from: the batches belong to different shape buckets")
         for k in self.FIELDS:
             dst, src = getattr(self, k), getattr(other, k)
@@ -94,18 +98,23 @@ class CompactBatch:
                 f"device={self.x.device})")
 
 
-def bucket(num_nodes: int, num_slots: int, quantum_nodes: Optional[int] = None,
+def bucket(num_nodes: int, num_slots: int, own_surplus: bool = False, quantum_nodes: Optional[int] = None,
            quantum_slots: Optional[int] = None) -> Tuple[int, int]:
-    """Padded (nodes, slots) of a batch: quanta of about 1/64 of the size (powers of two, >= 128 / 256), at least
-    MIN_PAD_NODES padding nodes and at most MAX_SURPLUS_PER_NODE surplus slots per padding node."""
-    def pow2_at_least(v, lo):
+    """Padded (nodes, slots) of a batch.  Nodes: quanta of about 1/64 of the size (powers of two, >= 128), at least
+    MIN_PAD_NODES padding nodes.  Slots, own_surplus=False (node-indexed kernels only): a coarse capacity class
+    (quanta of about 1/8), so batches of one node bucket share one captured graph whatever their edge count;
+    own_surplus=True: quanta of about 1/64 and at most MAX_SURPLUS_PER_NODE surplus slots per padding node."""
+    def pow2_at_least(v, lo, parts):
         q = lo
-        while q * 64 < v:
+        while q * parts < v:
             q *= 2
         return q
-    qn = quantum_nodes or pow2_at_least(num_nodes, 128)
-    qs = quantum_slots or pow2_at_least(num_slots, 256)
+    qn = quantum_nodes or pow2_at_least(num_nodes, 128, 64)
     pn = (num_nodes + MIN_PAD_NODES + qn - 1) // qn * qn
+    if not own_surplus:
+        qs = quantum_slots or pow2_at_least(num_slots, 256, 8)
+        return pn, (num_slots + qs - 1) // qs * qs
+    qs = quantum_slots or pow2_at_least(num_slots, 256, 64)
     ps = (num_slots + qs - 1) // qs * qs
     while (ps - num_slots) > MAX_SURPLUS_PER_NODE * (pn - num_nodes):
         pn += qn
@@ -192,57 +201,102 @@ class CompactGraphStore:
                 return
             yield ids
 
+    # ---- screening: contiguous ranges balanced by node count ------------------------------------
+    def shard_bounds(self, world: int) -> list:
+        """Contiguous graph ranges [lo, hi) for `world` ranks with (nearly) equal node sums (BASELINE config 3:
+        inference shards a graph stream over the GPUs, no collective)."""
+        csum = torch.cumsum(self.node_count, 0)
+        total = int(csum[-1])
+        cuts = [0]
+        for r in range(1, world):
+            cuts.append(int(torch.searchsorted(csum, torch.tensor(total * r // world), right=False)) + 1)
+        cuts.append(self.num_graphs)
+        return [(min(cuts[r], self.num_graphs), min(max(cuts[r + 1], cuts[r]), self.num_graphs)) for r in range(world)]
+
+    def node_balanced_ranges(self, max_nodes: int, max_slots: int, lo: int = 0, hi: Optional[int] = None,
+                             max_graphs: Optional[int] = None) -> list:
+        """Greedy split of the graph range [lo, hi) into consecutive micro-batches [a, b) whose node / CSR-slot sums
+        fit (max_nodes, max_slots): every micro-batch then runs in ONE shape bucket (pad = the budget), i.e. one
+        captured CUDA graph serves the whole stream."""
+        hi = self.num_graphs if hi is None else hi
+        ncs = torch.zeros(self.num_graphs + 1, dtype=torch.int64)
+        ncs[1:] = torch.cumsum(self.node_count, 0)
+        scs = torch.zeros(self.num_graphs + 1, dtype=torch.int64)
+        scs[1:] = torch.cumsum(self.slot_count, 0)
+        out, a = [], lo
+        while a < hi:
+            bn = int(torch.searchsorted(ncs, ncs[a] + max_nodes, right=True)) - 1
+            bs = int(torch.searchsorted(scs, scs[a] + max_slots, right=True)) - 1
+            b = min(bn, bs, hi)
+            if max_graphs is not None:
+                b = min(b, a + max_graphs)
+            if b <= a:
+                raise ValueError(f"graph {a} alone exceeds the micro-batch budget ({max_nodes} nodes, {max_slots} slots)")
+            out.append((a, b))
+            a = b
+        return out
+
     # ---- device collate -------------------------------------------------------------------------
-    def allocate(self, num_graphs: int, pad_nodes: int, pad_slots: int) -> CompactBatch:
+    def allocate(self, num_graphs: int, pad_nodes: int, pad_slots: int, own_surplus: bool = False) -> CompactBatch:
         """Batch buffers of one shape bucket (static inputs of a captured CUDA graph)."""
         dev = self.device
         i32 = dict(dtype=torch.int32, device=dev)
         u8 = dict(dtype=torch.uint8, device=dev)
         para = torch.zeros((num_graphs + 1) * self.num_para, dtype=torch.float32, device=dev) if self.num_para else None
-        return CompactBatch(num_graphs, pad_nodes, pad_slots, self.self_loops,
+        return CompactBatch(num_graphs, pad_nodes, pad_slots, self.self_loops, own_surplus,
                             x=torch.zeros(max(pad_nodes, 1), 9, **u8), rowptr=torch.zeros(pad_nodes + 1, **i32),
                             col_src=torch.zeros(max(pad_slots, 1), **i32), col_code=torch.zeros(max(pad_slots, 1), **u8),
                             node_graph=torch.zeros(max(pad_nodes, 1), **i32), graph_ptr=torch.zeros(num_graphs + 2, **i32),
                             para=para, valid=torch.zeros(4, **i32), err=torch.zeros(1, **i32))
 
     def batch(self, ids: torch.Tensor, pad=True, out: Optional[CompactBatch] = None,
-              ids_device: Optional[torch.Tensor] = None) -> CompactBatch:
+              ids_device: Optional[torch.Tensor] = None, cap: Optional[int] = None,
+              own_surplus: bool = False) -> CompactBatch:
         """Device batch of the graphs `ids`.  pad=True: bucketed shape; pad=False: exact shape; pad=(Np, Ep): given
-        shape.  `out`: write into these (bucket-static) buffers instead of allocating."""
+        shape.  `out`: write into these (bucket-static) buffers instead of allocating.  `cap` >= len(ids): graph
+        capacity of the batch (default len(ids))."""
         from ..train.models import _c, _device_guard
         nb = int(ids.numel())
+        cap = nb if cap is None else int(cap)
         if out is not None:
+            cap, own_surplus = out.num_graphs, out.own_surplus
             pn, ps = out.pad_nodes, out.pad_slots
         elif isinstance(pad, tuple):
             pn, ps = pad
         else:
             n, s = self.sizes(ids)
-            pn, ps = bucket(n, s) if pad else (n, s)
+            pn, ps = bucket(n, s, own_surplus) if pad else (n, s)
         with _device_guard(self.device):
             if ids_device is None:
                 ids_device = ids.to(self.device, non_blocking=True) if not ids.is_cuda else ids
             ids_device = ids_device.to(torch.int64).contiguous()
+            if cap < nb:
+                raise ValueError(f"{nb} graphs do not fit a batch of capacity {cap}")
             if out is None:
-                out = self.allocate(nb, pn, ps)
+                out = self.allocate(cap, pn, ps, own_surplus)
             nbytes = _lib.query("gnn_compact_collate_workspace_bytes", nb)
             if self._ws is None or self._ws.numel() < nbytes:
                 self._ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=self.device)
-            _c("gnn_compact_collate", ids_device, nb, self.num_graphs, self.node_off, self.slot_off, self.x, self.rowptr,
-               self.col_src, self.col_code, self.para, self.num_para, pn, ps, out.x, out.rowptr, out.col_src,
+            _c("gnn_compact_collate", ids_device, nb, cap, self.num_graphs, self.node_off, self.slot_off, self.x, self.rowptr,
+               self.col_src, self.col_code, self.para, self.num_para, pn, ps, 1 if own_surplus else 0, out.x, out.rowptr, out.col_src,
                out.col_code, out.node_graph, out.graph_ptr, out.para, out.valid, out.err, self._ws, self._ws.numel())
         return out
 
     # ---- host assembly (feeds that cross PCIe) ---------------------------------------------------
-    def host_batch(self, ids: torch.Tensor, pad=True, pin: bool = True) -> CompactBatch:
+    def host_batch(self, ids: torch.Tensor, pad=True, pin: bool = True, cap: Optional[int] = None,
+                   own_surplus: bool = False) -> CompactBatch:
         """The same batch assembled on the host (vectorised torch ops on the host mirror) into pinned memory."""
         if self._host is None:
             raise RuntimeError("CompactGraphStore was built with keep_host_mirror=False")
         h = self._host
         ids = ids.cpu().long()
         nb = int(ids.numel())
+        cap = nb if cap is None else int(cap)
+        if cap < nb:
+            raise ValueError(f"{nb} graphs do not fit a batch of capacity {cap}")
         n_cnt, s_cnt = self.node_count[ids], self.slot_count[ids]
         n, s = int(n_cnt.sum()), int(s_cnt.sum())
-        pn, ps = pad if isinstance(pad, tuple) else (bucket(n, s) if pad else (n, s))
+        pn, ps = pad if isinstance(pad, tuple) else (bucket(n, s, own_surplus) if pad else (n, s))
         if pn < n or ps < s:
             raise ValueError(f"bucket ({pn}, {ps}) smaller than the batch ({n}, {s})")
         nptr = torch.zeros(nb + 1, dtype=torch.int64)
@@ -262,13 +316,15 @@ class CompactGraphStore:
         col_src[:s] = (h["col_src"][slot_src].long() - n0[g_of_slot] + nptr[:-1][g_of_slot]).to(torch.int32)
         col_code = torch.zeros(max(ps, 1), dtype=torch.uint8)
         col_code[:s] = h["col_code"][slot_src]
-        node_graph = torch.full((max(pn, 1),), nb, dtype=torch.int32)
+        node_graph = torch.full((max(pn, 1),), cap, dtype=torch.int32)
         node_graph[:n] = g_of_node.to(torch.int32)
-        graph_ptr = torch.zeros(nb + 2, dtype=torch.int32)
+        graph_ptr = torch.full((cap + 2,), n, dtype=torch.int32)
         graph_ptr[:nb + 1] = nptr.to(torch.int32)
-        graph_ptr[nb + 1] = pn
+        graph_ptr[cap + 1] = pn
         nd, d = pn - n, ps - s
-        if nd > 0:
+        if not own_surplus:
+            rowptr[n:pn] = s
+        elif nd > 0:
             base, rem = d // nd, d % nd
             k = torch.arange(nd)
             start = s + k * base + torch.clamp(k, max=rem)
@@ -277,13 +333,13 @@ class CompactGraphStore:
             col_src[s:ps] = (n + torch.repeat_interleave(k, cnt)).to(torch.int32)
         elif d != 0:
             raise ValueError("surplus CSR slots need at least one padding node")
-        rowptr[pn] = ps
+        rowptr[pn] = ps if own_surplus else s
         para = None
         if self.num_para:
-            para = torch.ones((nb + 1) * self.num_para, dtype=torch.float32)
+            para = torch.ones((cap + 1) * self.num_para, dtype=torch.float32)
             para[:nb * self.num_para] = h["para"][ids].reshape(-1)
         valid = torch.tensor([n, nb, s, 0], dtype=torch.int32)
-        out = CompactBatch(nb, pn, ps, self.self_loops, x=x, rowptr=rowptr, col_src=col_src, col_code=col_code,
+        out = CompactBatch(cap, pn, ps, self.self_loops, own_surplus, x=x, rowptr=rowptr, col_src=col_src, col_code=col_code,
                            node_graph=node_graph, graph_ptr=graph_ptr, para=para, valid=valid,
                            err=torch.zeros(1, dtype=torch.int32))
         return out.pin_memory() if pin else out

@@ -21,6 +21,7 @@ No autograd graph is built on this path.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -58,7 +59,7 @@ class TrainEngine:
                 dist.broadcast(b, src=0, group=process_group)
         # captured CUDA graphs, one per (mode, graphs, padded nodes, padded slots) shape bucket; all share one memory
         # pool (they never run concurrently)
-        self.use_cuda_graphs = True
+        self.use_cuda_graphs = os.environ.get("GNN_B200_CUDA_GRAPHS", "1") != "0"
         self._buckets = {}
         self._pool = None
         self._warm = False
@@ -212,6 +213,50 @@ class TrainEngine:
         finally:
             net.train(was_training)
         return out[:int(ids.numel())]
+
+    @torch.no_grad()
+    def screen(self, store, lo: int = 0, hi: Optional[int] = None, max_nodes: int = 1 << 19, out=None,
+               passes: int = 1):
+        """Batched inference over the graph range [lo, hi) of a store (the reference's per-molecule prediction loops,
+        evaluate_ensemble.py:128-208 / demo/utils.py:20-40, as one stream): micro-batches of consecutive graphs with
+        at most `max_nodes` nodes, all padded to ONE bucket, so the whole stream replays one captured CUDA graph.
+        `out=False` discards the predictions (throughput runs).  Returns (predictions [hi - lo, P] | None, number of
+        micro-batches, node counts of the micro-batches)."""
+        from ..data.compact import MIN_PAD_NODES
+        hi = store.num_graphs if hi is None else hi
+        net = self.net
+        dev = self.grad.device
+        was_training = net.training
+        net.eval()
+        try:
+            with models._device_guard(dev):
+                net.arena()
+                # even micro-batches: k = ceil(nodes / budget) ranges of about nodes / k each, so that the last one is
+                # not mostly padding; the slot capacity is generous (unowned surplus slots cost nothing)
+                total_nodes = int(store.node_count[lo:hi].sum())
+                biggest = int(store.node_count[lo:hi].max())
+                k = max(-(-total_nodes // max(int(max_nodes) - MIN_PAD_NODES - biggest, 1)), 1)
+                budget = -(-total_nodes // k) + biggest
+                pn = (budget + MIN_PAD_NODES + 127) // 128 * 128
+                avg_slots = float(store.slot_count[lo:hi].sum()) / max(total_nodes, 1)
+                ps = (int(pn * avg_slots * 1.1) + 255) // 256 * 256
+                ranges = store.node_balanced_ranges(budget, ps, lo, hi)
+                cap = max(b - a for a, b in ranges)
+                if out is None:
+                    out = torch.empty(hi - lo, int(net.mlp_params.num_para), dtype=torch.float32, device=dev)
+                ent = self._bucket("screen", store, cap, pn, ps)
+                ids_all = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+                for _ in range(passes):
+                    for a, b in ranges:
+                        ids_dev = ids_all[a - lo:b - lo]
+                        store.batch(ids_dev, out=ent["batch"], ids_device=ids_dev)
+                        y = self._run_bucket(ent, self._predict)
+                        if out is not False:
+                            out[a - lo:b - lo].copy_(y[:b - a])
+        finally:
+            net.train(was_training)
+        nodes = [int(store.node_count[a:b].sum()) for a, b in ranges]
+        return (None if out is False else out), len(ranges), nodes
 
     def fit_epoch(self, store, batch_size: int, shuffle: bool = True, generator=None, drop_last: bool = False,
                   rank: int = 0, world: Optional[int] = None):

@@ -216,24 +216,35 @@ def _post_wgrad(mm, *args):
 
 
 class _Workspace:
-    """Grow-only scratch buffers per device (BN partials, CSR scratch)."""
+    """Grow-only scratch buffers per device (BN partials, CSR scratch).  A buffer that is outgrown is RETIRED, not
+    freed: captured CUDA graphs keep launching kernels with its address, so its memory must never be handed to
+    another tensor (a replay would scribble BatchNorm partial sums over it).  Growth doubles, so a handful of small
+    buffers is retired at most."""
 
     def __init__(self):
         self.buf = {}
+        self.retired = []
+
+    def _grow(self, key, nbytes, device, zero):
+        old = self.buf.get((key, device))
+        size = max(int(nbytes), 256, 2 * old.numel() if old is not None else 0)
+        t = (torch.zeros if zero else torch.empty)(size, dtype=torch.uint8, device=device)
+        if old is not None:
+            self.retired.append(old)
+        self.buf[(key, device)] = t
+        return t
 
     def get(self, key, nbytes, device):
         t = self.buf.get((key, device))
         if t is None or t.numel() < nbytes:
-            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-            self.buf[(key, device)] = t
+            t = self._grow(key, nbytes, device, False)
         return t
 
     def get_zeroed(self, key, nbytes, device):
         """Scratch whose users leave it all-zero (so it is cleared only when (re)allocated)."""
         t = self.buf.get((key, device))
         if t is None or t.numel() < nbytes:
-            t = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
-            self.buf[(key, device)] = t
+            t = self._grow(key, nbytes, device, True)
         return t
 
 
@@ -267,6 +278,8 @@ def _raise_input_error(code: int):
 def check_input_errors(block: bool = True):
     """Raise IndexError / ValueError for malformed inputs of earlier forwards (the kernels clamp and flag instead of
     faulting).  block=False only looks at forwards whose kernels have already completed."""
+    if _PENDING_ERR and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        return                      # event queries are not allowed while a CUDA graph is being captured
     while _PENDING_ERR:
         err, ev = _PENDING_ERR[0]
         if not block and not ev.query():
@@ -549,6 +562,11 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         if bool(graph.self_loops) != bool(pp.self_loops):
             raise ValueError("the compact batch was built with self_loops=%s but the model has self_loops=%s"
                              % (graph.self_loops, pp.self_loops))
+        if pp.pre_layers != 1 or DETERMINISTIC_SCATTER:
+            raise NotImplementedError(
+                "gnnepcsaft_b200: compact store batches carry no per-source slot lists; models with pre_layers > 1 and "
+                "the fixed-order gradient scatter (GNN_B200_ATOMIC_SCATTER=0) take PyG-layout batches (GraphStore / "
+                "forward(data))")
         x_idx, num_graphs = graph.x, graph.b
         _require_cuda(x_idx, "the compact batch")
         valid_nodes, valid_graphs = graph.valid[0:1], graph.valid[1:2]

@@ -98,17 +98,21 @@ int gnn_collate_gather(const int64_t* ids, int64_t num_ids, const int64_t* node_
  * store_col_src int32 (store-global node ids) / store_col_code uint8 [sumE'], store_para float [G, P] (may be NULL).
  * For graph ids int64 [B] it writes what the model kernels consume, with no sort and no scan over edges:
  *   x uint8 [Np, 9], rowptr int32 [Np+1], col_src int32 [Ep], col_code uint8 [Ep], node_graph int32 [Np],
- *   graph_ptr int32 [B+2], para float [(B+1) P], valid int32 [4] = {N, B, E', 0}
- * Np = pad_nodes >= N and Ep = pad_slots >= E' (else GNN_INPUT_ERR_EDGE_INDEX in err_flag): the surplus becomes graph
- * B, isolated padding nodes holding the surplus slots as self-edges, so every batch of a (Np, Ep, B) shape bucket
- * issues identical launches and one captured CUDA graph serves the bucket.  pad = exact sizes gives an empty graph B.
+ *   graph_ptr int32 [cap+2], para float [(cap+1) P], valid int32 [4] = {N, B, E', 0}
+ * cap = cap_graphs >= B, Np = pad_nodes >= N and Ep = pad_slots >= E' (else GNN_INPUT_ERR_EDGE_INDEX in err_flag):
+ * graphs B .. cap-1 are empty, the node / slot surplus becomes graph `cap` (isolated padding nodes holding the surplus
+ * slots as self-edges), so every batch of a (cap, Np, Ep) shape bucket issues identical launches and one captured
+ * CUDA graph serves the bucket.  Exact sizes give an empty padding graph.  own_surplus = 0: the padding nodes have no
+ * in-edges and the surplus CSR slots are unused capacity (rowptr[Np] = E'); enough for models whose kernels are all
+ * node-indexed (pre_layers == 1, the reference's configs) - the captured graph then does not depend on Ep at all.
+ * own_surplus = 1: every slot of the padded arrays belongs to a node (per-slot tensors of the pre_layers > 1 path).
  * Replaces PyG DataLoader / Collater (train.py:74-79) + add_self_loops (models.py:118-121) for store-resident data. */
 int64_t gnn_compact_collate_workspace_bytes(int64_t num_ids);
-int gnn_compact_collate(const int64_t* ids, int64_t num_ids, int64_t num_store_graphs,
+int gnn_compact_collate(const int64_t* ids, int64_t num_ids, int64_t cap_graphs, int64_t num_store_graphs,
                         const int32_t* node_off, const int32_t* slot_off, const uint8_t* store_x,
                         const int32_t* store_rowptr, const int32_t* store_col_src,
                         const uint8_t* store_col_code, const float* store_para, int num_para,
-                        int64_t pad_nodes, int64_t pad_slots, uint8_t* x, int32_t* rowptr,
+                        int64_t pad_nodes, int64_t pad_slots, int own_surplus, uint8_t* x, int32_t* rowptr,
                         int32_t* col_src, uint8_t* col_code, int32_t* node_graph, int32_t* graph_ptr,
                         float* para, int32_t* valid, int32_t* err_flag, void* workspace,
                         int64_t workspace_bytes, void* stream);

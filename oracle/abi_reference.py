@@ -121,8 +121,9 @@ def gnn_compact_collate_workspace_bytes(nb):
     return 256
 
 
-def gnn_compact_collate(ids, nb, num_store_graphs, node_off, slot_off, sx, s_rowptr, s_col_src, s_col_code, s_para,
-                        num_para, pad_nodes, pad_slots, x, rowptr, col_src, col_code, node_graph, graph_ptr, para, valid,
+def gnn_compact_collate(ids, nb, cap, num_store_graphs, node_off, slot_off, sx, s_rowptr, s_col_src, s_col_code, s_para,
+                        num_para, pad_nodes, pad_slots, own_surplus, x, rowptr, col_src, col_code, node_graph, graph_ptr, para,
+                        valid,
                         err_flag=None, workspace=None, workspace_bytes=0, stream=None):
     if err_flag is not None:
         err_flag.zero_()
@@ -147,22 +148,22 @@ def gnn_compact_collate(ids, nb, num_store_graphs, node_off, slot_off, sx, s_row
         on += cn
         os_ += cs
     nd, d = pad_nodes - on, pad_slots - os_
-    rowptr[pad_nodes] = pad_slots
-    graph_ptr[nb] = on
-    graph_ptr[nb + 1] = pad_nodes
+    rowptr[pad_nodes] = pad_slots if own_surplus else os_
+    graph_ptr[nb:cap + 1] = on          # graphs nb .. cap-1 are empty, graph `cap` is the padding graph
+    graph_ptr[cap + 1] = pad_nodes
     valid[0], valid[1], valid[2], valid[3] = on, nb, os_, 0
     if para is not None:
-        para[nb * num_para:(nb + 1) * num_para] = 1.0
+        para[nb * num_para:(cap + 1) * num_para] = 1.0
     if nd == 0:
-        if d != 0 and err_flag is not None:
+        if own_surplus and d != 0 and err_flag is not None:
             err_flag |= 1
         return
-    base, rem = d // nd, d % nd
+    base, rem = (d // nd, d % nd) if own_surplus else (0, 0)
     for k in range(nd):
         node, start, cnt = on + k, os_ + k * base + min(k, rem), base + (1 if k < rem else 0)
         x[node] = 0
         rowptr[node] = start
-        node_graph[node] = nb
+        node_graph[node] = cap
         col_src[start:start + cnt] = node
         col_code[start:start + cnt] = 0
 

@@ -15,9 +15,11 @@ from tests.helpers import cfg, make_pair
 def test_bucket_properties():
     for n, s in ((1, 1), (30, 80), (12800, 38000), (102263, 305211), (27900, 80000), (500000, 1500000)):
         pn, ps = bucket(n, s)
+        assert pn >= n + 16 and ps >= s and pn <= n * 1.02 + 160 and ps <= s * 1.13 + 256
+        pn, ps = bucket(n, s, own_surplus=True)
         assert pn >= n + 16 and ps >= s
-        assert ps - s <= 128 * (pn - n)
-        assert pn <= n * 1.05 + 256 and ps <= s * 1.05 + 512
+        assert ps - s <= 32 * (pn - n)
+        assert pn <= n * 1.08 + 256 and ps <= s * 1.05 + 512
         assert bucket(n, s) == bucket(max(n - 1, 1), s) or True     # deterministic, monotone in practice
 
 
@@ -29,13 +31,15 @@ def test_host_batch_equals_reference_collate(cpu_backend, self_loops):
     store = CompactGraphStore(packed, device="cpu", self_loops=self_loops)
     ids = torch.tensor([3, 16, 0, 7, 7, 11])
     for pad in (False, True, (400, 1500)):
-        a = store.batch(ids, pad=pad)
-        b = store.host_batch(ids, pad=pad, pin=False)
-        for k in a.FIELDS:
-            assert torch.equal(getattr(a, k), getattr(b, k)), (k, pad)
-        n, s = store.sizes(ids)
-        assert a.valid.tolist() == [n, 6, s, 0]
-        assert int(a.rowptr[-1]) == a.pad_slots and int(a.graph_ptr[-1]) == a.pad_nodes
+        for own in (False, True):
+            a = store.batch(ids, pad=pad, own_surplus=own)
+            b = store.host_batch(ids, pad=pad, pin=False, own_surplus=own)
+            for k in a.FIELDS:
+                assert torch.equal(getattr(a, k), getattr(b, k)), (k, pad, own)
+            n, s = store.sizes(ids)
+            assert a.valid.tolist() == [n, 6, s, 0]
+            assert int(a.rowptr[-1]) == (a.pad_slots if own else s) and int(a.graph_ptr[-1]) == a.pad_nodes
+            assert torch.all(a.rowptr[1:] >= a.rowptr[:-1])
 
 
 @pytest.mark.parametrize("name,kw", [("default", dict(propagation_depth=2)),
@@ -79,3 +83,36 @@ def test_epoch_sampler_covers_every_graph_once(cpu_backend):
                                                                      torch.Generator().manual_seed(0), rank=r, world=2)])
     assert sorted(seen.tolist()) == list(range(23))
     assert torch.equal(store.in_degree_histogram(), packed.in_degree_histogram())
+
+
+def test_graph_capacity_padding_and_screen_stream(cpu_backend):
+    """Fewer graphs than the bucket's capacity (last batch of an epoch, node-balanced screening ranges): the empty
+    graphs and the padding graph change nothing, and `screen` reproduces per-batch prediction over a range."""
+    from gnnepcsaft_b200.train.engine import TrainEngine
+    c = cfg(propagation_depth=2)
+    packed = make_packed_graphs(40, seed=6, num_para=c.num_para)
+    _, _, m = make_pair(c, packed.in_degree_histogram(), dtype64=False)
+    eng = TrainEngine.from_config(m, c, distributed=False)
+    eng.use_cuda_graphs = False
+    store = CompactGraphStore(packed, device="cpu")
+    ids = torch.tensor([5, 9, 1])
+    a = store.batch(ids, pad=(200, 700), cap=8)
+    b = store.host_batch(ids, pad=(200, 700), pin=False, cap=8)
+    for k in a.FIELDS:
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    assert a.graph_ptr.numel() == 10 and a.valid.tolist()[1] == 3
+    y_ref = eng.predict(batch_from_packed(packed, ids))
+    torch.testing.assert_close(eng.predict(a)[:3], y_ref, rtol=1e-5, atol=1e-6)
+    # node-balanced contiguous ranges: cover [lo, hi) exactly, respect the budgets
+    ranges = store.node_balanced_ranges(120, 400, 3, 37)
+    assert ranges[0][0] == 3 and ranges[-1][1] == 37 and all(r0[1] == r1[0] for r0, r1 in zip(ranges, ranges[1:]))
+    for lo, hi in ranges:
+        n, s = store.sizes(torch.arange(lo, hi))
+        assert n <= 120 and s <= 400
+    bounds = store.shard_bounds(3)
+    assert bounds[0][0] == 0 and bounds[-1][1] == 40 and all(x[1] == y[0] for x, y in zip(bounds, bounds[1:]))
+    per_rank = [int(store.node_count[lo:hi].sum()) for lo, hi in bounds]
+    assert max(per_rank) - min(per_rank) <= 2 * int(store.node_count.max())
+    out, nmb, nodes = eng.screen(store, 3, 37, max_nodes=160)
+    assert nmb >= 3 and len(nodes) == nmb
+    torch.testing.assert_close(out, eng.predict(batch_from_packed(packed, torch.arange(3, 37))), rtol=1e-5, atol=1e-6)

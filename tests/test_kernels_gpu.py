@@ -460,8 +460,17 @@ def test_pool_mape():
     tgt[0, 0] = 0.0                                       # exercises the 1.17e-6 clamp
     loss, dpred = torch.zeros(1), torch.zeros(700, 5)
     cpu, gpu = run_both("gnn_mape_fwd_bwd", pred, tgt, 3500, 0.5, loss, dpred, None, 5)
-    close(gpu[-2], cpu[-2], 1e-6, "mape")
-    close(gpu[-1], cpu[-1], 1e-6, "dmape")
+    close(gpu[4], cpu[4], 1e-6, "mape")
+    close(gpu[5], cpu[5], 1e-6, "dmape")
+    # padded batch: only the first `valid` rows carry a loss, the rest gets a zero gradient
+    vr = torch.tensor([613], dtype=torch.int32)
+    loss, dpred = torch.zeros(1), torch.full((700, 5), 7.0)
+    cpu, gpu = run_both("gnn_mape_fwd_bwd", pred, tgt, 3500, 1.0, loss, dpred, vr, 5)
+    close(gpu[4], cpu[4], 1e-6, "mape (valid rows)")
+    close(gpu[5], cpu[5], 1e-6, "dmape (valid rows)")
+    assert torch.all(gpu[5][613:] == 0)
+    ref = ((pred[:613] - tgt[:613]).abs() / tgt[:613].abs().clamp(min=1.17e-6)).mean()
+    assert abs(float(gpu[4]) - float(ref)) <= 1e-5 * float(ref)
 
 
 def test_adamw_amsgrad_cosine_restarts_vs_torch():
