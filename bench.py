@@ -326,13 +326,21 @@ def main():
         return out
 
     def precapture(eng, st, batches, fn):
-        """Warm-up: run every planned batch's shape bucket until its CUDA graph exists (real steps, untimed)."""
-        seen = {}
+        """Warm-up: run the planned batches' shape buckets until their CUDA graphs exist (real steps, untimed).  Every
+        rank runs the SAME number of steps (max over ranks) - a training step contains a collective."""
+        todo, seen = [], {}
         for ids, ids_dev in batches:
             key = bucket(*st.sizes(ids))
             if seen.get(key, 0) < 2:
-                fn(eng, st, ids, ids_dev)
+                todo.append((ids, ids_dev))
                 seen[key] = seen.get(key, 0) + 1
+        count = len(todo)
+        if world > 1:
+            t = torch.tensor([count], dtype=torch.int64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            count = int(t.item())
+        for i in range(count):
+            fn(eng, st, *todo[i % len(todo)])
         return len(seen)
 
     train_fn = lambda eng, st, ids, ids_dev: eng.step_from_store(st, ids, ids_device=ids_dev)     # noqa: E731

@@ -12,9 +12,9 @@ Reproduces the step the reference runs through Lightning (reference gnnepcsaft/t
   * BatchNorm statistics per rank (the reference has no SyncBatchNorm);
   * store-resident training (`step_from_store`, `fit_epoch`): the batch is gathered on the device by
     `gnn_compact_collate` into the static buffers of a shape bucket and the whole step (forward, loss, backward,
-    NCCL all-reduce, optimizer) is ONE captured CUDA graph per bucket - no per-step allocation, ~125 C-ABI calls and
-    ~290 launches replaced by one `cudaGraphLaunch` (the reference's 512-graph batches, configs/default.py:22, are
-    otherwise bound by host dispatch).
+    optimizer; data parallel: up to the backward pass, the NCCL all-reduce and the optimizer kernel follow eagerly) is
+    ONE captured CUDA graph per bucket - no per-step allocation, ~125 C-ABI calls and ~290 launches replaced by one
+    `cudaGraphLaunch` (the reference's 512-graph batches, configs/default.py:22, are otherwise bound by host dispatch).
 No autograd graph is built on this path.
 """
 
@@ -59,7 +59,7 @@ class TrainEngine:
                 dist.broadcast(b, src=0, group=process_group)
         # captured CUDA graphs, one per (mode, graphs, padded nodes, padded slots) shape bucket; all share one memory
         # pool (they never run concurrently)
-        self.use_cuda_graphs = os.environ.get("GNN_B200_CUDA_GRAPHS", "1") != "0"
+        self.use_cuda_graphs = os.environ.get("GNN_B200_CUDA_GRAPHS", "1") != "0" and dev.type == "cuda"
         self._buckets = {}
         self._pool = None
         self._warm = False
@@ -81,9 +81,14 @@ class TrainEngine:
             return self._step(batch)
 
     def _step(self, batch) -> torch.Tensor:
+        loss = self._step_compute(batch)
+        return self._step_update(loss)
+
+    def _step_compute(self, batch) -> torch.Tensor:
+        """Forward, loss and backward into the flat gradient arena (everything of a step that is rank-local)."""
         net = self.net
         net.train()
-        arena = net.arena()
+        net.arena()
         models.check_input_errors(block=False)
         compact = getattr(batch, "is_compact", False)
         valid = None
@@ -109,13 +114,26 @@ class TrainEngine:
         loss = self.grad[self.numel:self.numel + 1]
         _c("gnn_mape_fwd_bwd", out, target, out.numel(), 1.0, loss, dpred, valid, int(out.shape[1]))
         _backward_impl(net, sv, dpred, self.grad)
+        return loss
+
+    def _step_update(self, loss: torch.Tensor) -> torch.Tensor:
+        """Gradient all-reduce (one flat buffer, the loss rides along) + fused AdamW / schedule."""
         if self.world > 1:
             dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
         scale = 1.0 / self.world
-        _c("gnn_adamw_amsgrad_step", arena, self.grad, self.exp_avg, self.exp_avg_sq, self.max_exp_avg_sq, self.numel,
-           self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t0, scale)
+        _c("gnn_adamw_amsgrad_step", self.net._arena, self.grad, self.exp_avg, self.exp_avg_sq, self.max_exp_avg_sq,
+           self.numel, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t0, scale)
         _c("gnn_step_increment", self.step_count)
         return loss * scale if self.world > 1 else loss
+
+    def _train_bucket(self, ent):
+        """One step on a bucket's static batch.  Single process: the whole step is one captured graph.  Data
+        parallel: the captured graph ends with the backward pass and the collective + optimizer kernels (3 launches)
+        are issued eagerly - NCCL registers the buffers of captured collectives across ranks at capture time, which
+        needs lock-step captures, but the ranks meet new shape buckets at different steps."""
+        if self.world == 1:
+            return self._run_bucket(ent, self._step)
+        return self._step_update(self._run_bucket(ent, self._step_compute))
 
     @torch.no_grad()
     def predict(self, batch) -> torch.Tensor:
@@ -162,7 +180,8 @@ class TrainEngine:
             g = torch.cuda.CUDAGraph()
             if self._pool is None:
                 self._pool = torch.cuda.graph_pool_handle()
-            with torch.cuda.graph(g, pool=self._pool):
+            # thread_local: other threads (NCCL watchdog, copy threads) may keep issuing CUDA calls while capturing
+            with torch.cuda.graph(g, pool=self._pool, capture_error_mode="thread_local"):
                 ent["out"] = fn(ent["batch"])
             ent["graph"] = g
         ent["graph"].replay()
@@ -181,7 +200,7 @@ class TrainEngine:
             pn, ps = bucket(n, s)
             ent = self._bucket("train", store, int(ids.numel()), pn, ps)
             store.batch(ids, out=ent["batch"], ids_device=ids_device)
-            return self._run_bucket(ent, self._step)
+            return self._train_bucket(ent)
 
     @torch.no_grad()
     def step_from_host(self, store, host_batch) -> torch.Tensor:
@@ -192,7 +211,7 @@ class TrainEngine:
             self.net.arena()
             ent = self._bucket("train", store, host_batch.num_graphs, host_batch.pad_nodes, host_batch.pad_slots)
             ent["batch"].copy_from(host_batch)
-            return self._run_bucket(ent, self._step)
+            return self._train_bucket(ent)
 
     @torch.no_grad()
     def predict_from_store(self, store, ids: torch.Tensor, ids_device: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -80,3 +80,54 @@ def test_two_gpu_data_parallel_step(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(result)), nprocs=2, join=True)
     text = result.read_text()
     assert text.startswith("1"), text
+
+
+def _store_worker(rank, world, port, result_path):
+    """Store-resident training with one captured CUDA graph per shape bucket on every rank: the ranks draw different
+    batches (different buckets, captures at different steps), the NCCL all-reduce is part of the captured graph."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from gnnepcsaft_b200.data.compact import CompactGraphStore
+    from gnnepcsaft_b200.data.synth import make_packed_graphs
+    from gnnepcsaft_b200.train.engine import TrainEngine
+
+    c = cfg(propagation_depth=2, warmup_steps=4)
+    packed = make_packed_graphs(3000, seed=11)
+    _, _, m = make_pair(c, packed.in_degree_histogram(), seed=rank, dtype64=False)
+    m.to(dev)
+    engine = TrainEngine.from_config(m, c)
+    store = CompactGraphStore(packed, device=dev)
+    gen = torch.Generator().manual_seed(100 + rank)
+    losses = []
+    for it in range(10):
+        nb = 256 if (it + rank) % 3 else 512            # different bucket sequences on the two ranks
+        ids = torch.randperm(3000, generator=gen)[:nb]
+        losses.append(engine.step_from_store(store, ids).clone())
+    torch.cuda.synchronize()
+    flat = torch.cat([p.data.reshape(-1) for p in m.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    ls = torch.stack(losses).reshape(-1)
+    gl = [torch.zeros_like(ls) for _ in range(world)]
+    dist.all_gather(gl, ls)
+    if rank == 0:
+        same = bool(torch.equal(gathered[0], gathered[1]))
+        same_loss = bool(torch.equal(gl[0], gl[1]))              # the loss is the rank mean on every rank
+        finite = bool(torch.isfinite(ls).all())
+        ok = same and same_loss and finite and engine.graph_replays >= 5
+        with open(result_path, "w") as f:
+            f.write(f"{int(ok)} same_params={same} same_loss={same_loss} finite={finite} replays={engine.graph_replays} "
+                    f"buckets={len(engine._buckets)} losses={[round(float(v), 5) for v in ls]}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_graphed_store_training(tmp_path):
+    result = tmp_path / "result.txt"
+    mp.spawn(_store_worker, args=(2, _free_port(), str(result)), nprocs=2, join=True)
+    text = result.read_text()
+    print(text)
+    assert text.startswith("1"), text

@@ -91,3 +91,46 @@ def test_two_rank_data_parallel_step(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), str(result)), nprocs=2, join=True)
     text = result.read_text()
     assert text.startswith("1"), text
+
+
+def _store_worker(rank, world, port, result_path):
+    """Store-resident epoch, sharded DistributedSampler-style over two ranks (padded compact batches)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gnnepcsaft_b200 import _lib
+    from gnnepcsaft_b200.data.compact import CompactGraphStore
+    from gnnepcsaft_b200.data.synth import make_packed_graphs
+    from gnnepcsaft_b200.train import engine as E
+    from gnnepcsaft_b200.train import models as M
+    from oracle import abi_reference as R
+    R.install(_Patch(), _lib, M)
+    E._require_cuda = lambda t, what: None
+
+    c = cfg(propagation_depth=1, hidden_dim=16, warmup_steps=4)
+    packed = make_packed_graphs(24, seed=3)
+    _, _, m = make_pair(c, packed.in_degree_histogram(), seed=rank, dtype64=False)
+    engine = E.TrainEngine.from_config(m, c)
+    store = CompactGraphStore(packed, device="cpu")
+    seen = [ids for ids in store.epoch(4, generator=torch.Generator().manual_seed(5), rank=rank, world=world)]
+    mean_loss = engine.fit_epoch(store, 4, generator=torch.Generator().manual_seed(5), rank=rank)
+    flat = torch.cat([p.data.reshape(-1) for p in m.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    mine = torch.cat(seen)
+    allids = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allids, mine)
+    if rank == 0:
+        ok = (torch.equal(gathered[0], gathered[1]) and sorted(torch.cat(allids).tolist()) == list(range(24))
+              and int(engine.step_count) == 3 and mean_loss == mean_loss)
+        with open(result_path, "w") as f:
+            f.write(f"{int(ok)} steps={int(engine.step_count)} loss={mean_loss}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_store_epoch(tmp_path):
+    result = tmp_path / "result.txt"
+    mp.spawn(_store_worker, args=(2, _free_port(), str(result)), nprocs=2, join=True)
+    text = result.read_text()
+    assert text.startswith("1"), text
