@@ -178,6 +178,75 @@ class CompactGraphStore:
                               slot_off=self.slot_off.cpu().long(),
                               para=self.para.cpu() if self.para is not None else None)
 
+    # ---- binary shards (pre-featurised data, read without rdkit / PyG / a CSR build) ---------------
+    SHARD_MAGIC = b"GNNB200S"
+    _SHARD_FIELDS = ("node_off", "slot_off", "x", "rowptr", "col_src", "col_code", "para")
+
+    def save(self, path: str):
+        """Write the store as one binary shard: magic, a JSON header (counts, dtypes, byte offsets) and the raw
+        little-endian arrays, each 64-byte aligned - exactly the device layout, so `load` is a memory map plus one
+        host-to-device copy per array (no featurisation, no sort, no kernel).  Replaces the processed `.pt` files of
+        the reference's `InMemoryDataset`s (data/graphdataset.py:48,137) for store-resident training / screening."""
+        import json
+        import numpy as np
+        arrays = {k: getattr(self, k) for k in self._SHARD_FIELDS if getattr(self, k) is not None}
+        meta = {"version": 1, "num_graphs": self.num_graphs, "num_para": self.num_para, "self_loops": self.self_loops,
+                "arrays": {}}
+        blobs, off = [], 0
+        for k, t in arrays.items():
+            a = t.detach().cpu().contiguous().numpy()
+            meta["arrays"][k] = {"dtype": str(a.dtype), "shape": list(a.shape), "offset": off, "nbytes": int(a.nbytes)}
+            blobs.append(a)
+            off += (a.nbytes + 63) // 64 * 64
+        header = json.dumps(meta).encode()
+        with open(path, "wb") as fh:
+            fh.write(self.SHARD_MAGIC)
+            fh.write(np.array([len(header)], dtype="<u8").tobytes())
+            fh.write(header)
+            pos = 16 + len(header)
+            base = (pos + 63) // 64 * 64
+            fh.write(b"\0" * (base - pos))
+            for a in blobs:
+                fh.write(a.tobytes())
+                fh.write(b"\0" * ((a.nbytes + 63) // 64 * 64 - a.nbytes))
+
+    @classmethod
+    def load(cls, path: str, device="cuda", keep_host_mirror: bool = True) -> "CompactGraphStore":
+        """Memory-map a shard written by `save` and upload it (the arrays ARE the device layout)."""
+        import json
+        import numpy as np
+        from ..train import models as _models
+        dev = torch.device(device)
+        _models._require_cuda(torch.empty(0, device=dev), "CompactGraphStore")
+        with open(path, "rb") as fh:
+            if fh.read(8) != cls.SHARD_MAGIC:
+                raise ValueError(f"{path} is not a gnnepcsaft_b200 store shard")
+            hlen = int(np.frombuffer(fh.read(8), dtype="<u8")[0])
+            meta = json.loads(fh.read(hlen).decode())
+        if meta.get("version") != 1:
+            raise ValueError(f"{path}: unsupported shard version {meta.get('version')}")
+        base = (16 + hlen + 63) // 64 * 64
+        self = cls.__new__(cls)
+        self.device, self.self_loops = dev, bool(meta["self_loops"])
+        self.num_graphs, self.num_para = int(meta["num_graphs"]), int(meta["num_para"])
+        self.para = None
+        host = {}
+        with _models._device_guard(dev):
+            for k, info in meta["arrays"].items():
+                mm = np.memmap(path, dtype=np.dtype(info["dtype"]), mode="r", offset=base + info["offset"],
+                               shape=tuple(info["shape"]))
+                t = torch.from_numpy(np.array(mm))              # one sequential read of the mapped range
+                host[k] = t
+                setattr(self, k, t.to(dev))
+        self.node_count = (host["node_off"][1:] - host["node_off"][:-1]).long()
+        self.slot_count = (host["slot_off"][1:] - host["slot_off"][:-1]).long()
+        self._ws = None
+        self._host = None
+        if keep_host_mirror:
+            self._host = dict(x=host["x"], rowptr=host["rowptr"], col_src=host["col_src"], col_code=host["col_code"],
+                              node_off=host["node_off"].long(), slot_off=host["slot_off"].long(), para=host.get("para"))
+        return self
+
     # ---- planning (host) -----------------------------------------------------------------------
     def sizes(self, ids: torch.Tensor) -> Tuple[int, int]:
         """(nodes, CSR slots) of the batch `ids` (host int64 tensor) - no device access."""

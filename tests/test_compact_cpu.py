@@ -116,3 +116,27 @@ def test_graph_capacity_padding_and_screen_stream(cpu_backend):
     out, nmb, nodes = eng.screen(store, 3, 37, max_nodes=160)
     assert nmb >= 3 and len(nodes) == nmb
     torch.testing.assert_close(out, eng.predict(batch_from_packed(packed, torch.arange(3, 37))), rtol=1e-5, atol=1e-6)
+
+
+def test_store_shard_roundtrip(cpu_backend, tmp_path):
+    """Binary shard: save -> memory-mapped load gives the identical store (and identical batches)."""
+    packed = make_packed_graphs(31, seed=12)
+    store = CompactGraphStore(packed, device="cpu", self_loops=False)
+    path = str(tmp_path / "shard0.gnnb")
+    store.save(path)
+    again = CompactGraphStore.load(path, device="cpu")
+    assert (again.num_graphs, again.num_para, again.self_loops) == (31, store.num_para, False)
+    for k in CompactGraphStore._SHARD_FIELDS:
+        assert torch.equal(getattr(store, k), getattr(again, k)), k
+        assert getattr(store, k).dtype == getattr(again, k).dtype
+    ids = torch.tensor([30, 2, 17])
+    a, b = store.batch(ids), again.batch(ids)
+    for k in a.FIELDS:
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    h = again.host_batch(ids, pin=False)
+    for k in a.FIELDS:
+        assert torch.equal(getattr(a, k), getattr(h, k)), k
+    with open(path, "r+b") as fh:
+        fh.write(b"XXXXXXXX")
+    with pytest.raises(ValueError):
+        CompactGraphStore.load(path, device="cpu")
