@@ -1105,6 +1105,13 @@ __global__ void __launch_bounds__(PROD_GROUP_THREADS)
 pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t* __restrict__ out) {
     constexpr int KB_ELEMS = tf32_like(MODE) ? 32 : 64;
     constexpr int PARTS = tf32_like(MODE) ? 2 : 1;
+    // Programmatic dependent launch: the GEMM that consumes this image is launched right behind this kernel with
+    // programmatic stream serialization; releasing it here lets its CTAs set up (barriers, TMEM, first activation
+    // loads) while the image is being written - only its weight fetches wait (griddepcontrol.wait) for this grid.
+    // (This kernel itself is launched the plain way, behind everything earlier, so the GEMM may read its activations
+    // at once.  Programmatic launches for EVERY kernel of the step were measured too: 4.82 vs 4.77 ms at 4096 graphs,
+    // 1.72 vs 1.62 ms at 512 - the resident waiting CTAs cost more than the overlapped launch latency saves.)
+    asm volatile("griddepcontrol.launch_dependents;");
     // blockIdx.x = k-block * row_splits + row split: a CTA writes PACK_ROWS rows (whole 8-row swizzle atoms) of a tile
     const int row_splits = (BN + PACK_ROWS - 1) / PACK_ROWS;
     const int kb = blockIdx.x / row_splits, r_begin = (blockIdx.x % row_splits) * PACK_ROWS;
@@ -1392,6 +1399,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
         const int p = tid - PROD_WARP0 * 32 - pg * PROD_GROUP_THREADS;
         const int total_kb = (int)((g.K + KB_ELEMS - 1) / KB_ELEMS);      // packed images exist only without split-K
         uint32_t it_mod = 0, my_use = 0;          // running k-block index modulo NS; k-blocks this group has produced
+        bool pack_ready = false;                  // PACKED: the pack kernel (programmatic primary) has completed
         for (int64_t item = blockIdx.x; item < g.num_items; item += gridDim.x) {
             int64_t m0, k_begin, k_end;
             int n0, grp;
@@ -1438,6 +1446,10 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 if constexpr (PACKED) {
                     // the weight operand was pre-packed as the smem image: one TMA bulk copy per k-block
                     if (p == 0) {
+                        if (!pack_ready) {          // no-op unless launched as a programmatic dependent
+                            asm volatile("griddepcontrol.wait;" ::: "memory");
+                            pack_ready = true;
+                        }
                         const uint32_t bytes = PARTS * b_plane;
                         const size_t tile_idx = ((size_t)(grp * g.n_tiles + n0 / BN) * total_kb + kb);
                         mbar_expect_tx(&full_bar[s], bytes);
@@ -1593,8 +1605,19 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            kern<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g,
-                                                                        reinterpret_cast<const uint8_t*>(pack_ws), ag);
+            // programmatic dependent of the pack kernel above (see pack_b_kernel)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3((unsigned)cta_threads(false, AGG));
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            e = cudaLaunchKernelEx(&cfg, kern, aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws), ag);
+            if (e != cudaSuccess) return (int)e;
         } else {
             auto kern = gemm_tc_kernel<MODE, false, false, SCALED, BL, EP, AG>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -15,7 +15,8 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.normpath(os.path.join(_PKG, "..", "csrc"))
-LIB_PATH = os.path.join(CSRC, "libgnnepcsaft_b200.so")
+# GNN_B200_LIB: load another build of the same ABI (A/B timing of kernel variants, the -DGNN_B200_PROFILE build)
+LIB_PATH = os.environ.get("GNN_B200_LIB") or os.path.join(CSRC, "libgnnepcsaft_b200.so")
 
 HEADER_PATH = os.path.normpath(os.path.join(_PKG, "..", "..", "include", "gnnepcsaft_b200.h"))
 
