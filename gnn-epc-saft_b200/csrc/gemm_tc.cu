@@ -2091,3 +2091,420 @@ extern "C" int gnn_tc_pna_postf_wgrad(const float* dO, const float* x, const flo
     return post_wgrad_impl(dO, x, A, scal, n, F, F_out, towers, dwpost, wpost_tower_stride, dbpost, bpost_tower_stride,
                            dVx, precision, stream);
 }
+
+// =====================================================================================================================
+// Inference "tile" kernel: the whole PNAConv stack (all layers) of a tile of <= 128 nodes made of WHOLE graphs in one
+// persistent CTA.  Replaces, for store-resident inference of the default architecture (H = 64, 2 towers, folded
+// destination projection, post_layers == 1, skip connections), the per-layer chain
+//   gnn_tc_pna_projsrc_fwd -> gnn_tc_pna_postf_agg_fwd -> gnn_bn_fold_linear + gnn_tc_linear_skip_fwd
+// i.e. PNAConv + BatchNorm(running statistics) + ReLU + skip of reference models.py:126-131, for all layers.
+// No edge leaves a graph, so a tile never needs another tile's rows: node features x (fp32 [128][64]) and the source
+// projections Psrc ([128][128]) live in shared memory for the whole stack and the CSR slice of the tile is staged
+// once; per layer only the packed weight images (589 KB, L2-resident) are streamed in by TMA bulk copies.
+// Per layer, 26 k-blocks of 32 K-columns run through one two-stage operand ring (SWIZZLE_128B, tf32 hi / lo planes,
+// three tcgen05.mma per K step = fp32-level accuracy, accumulators in TMEM):
+//   phase A  Psrc_t = x . Wsrc_t^T + b_t                 2 towers x 2 k-blocks, N = 64   -> TMEM -> Psrc (smem)
+//   phase B  [x | mean min max std of (Psrc[src] + tab[code])] . [Vx | Wagg]_t^T     2 x 10 k-blocks, N = 96
+//            the aggregates are computed by the producers from the Psrc tile (pna_agg.cuh, the arithmetic of the
+//            stand-alone kernel); epilogue: identity + amplification + attenuation groups combined with the node's
+//            degree scalers, + bias -> written straight back into the ring as the A operand of phase C
+//   phase C  x <- relu(O . Wlin'^T + b') + x             2 k-blocks, N = 64 (BatchNorm folded into Wlin', b')
+// Warps 0-15 produce operands (two groups of 256 threads, one per ring stage) and run the epilogues; warp 16 issues
+// the MMAs.  Graphs with more than 128 nodes cannot be tiled; the host only takes this path for stores that have none.
+namespace tc {
+constexpr int MK_F = 64, MK_T = 2, MK_FO = 32, MK_C = MK_T * MK_F;
+constexpr int MK_ROWS = 128;
+constexpr int MK_XLD = 68, MK_PLD = 132;               // padded row strides (floats): conflict-free row-per-lane access
+constexpr int MK_SLOTS = 1024;                         // CSR slots (in-edges incl. self-loops) per tile
+constexpr int MK_PROD = 512, MK_THREADS = MK_PROD + 32;
+constexpr uint32_t MK_APLANE = MK_ROWS * ROW_BYTES;    // 16 KB
+constexpr uint32_t MK_A_BYTES = 2 * MK_APLANE;         // hi + lo
+constexpr uint32_t MK_B_BYTES = 2 * 96 * ROW_BYTES;    // widest weight k-block (N = 96), hi + lo
+constexpr uint32_t MK_STAGE = MK_A_BYTES + MK_B_BYTES; // 56 KB
+constexpr uint32_t MK_OFF_X = 2 * MK_STAGE;
+constexpr uint32_t MK_OFF_PS = MK_OFF_X + MK_ROWS * MK_XLD * 4;
+constexpr uint32_t MK_OFF_CSR = MK_OFF_PS + MK_ROWS * MK_PLD * 4;
+constexpr uint32_t MK_CSR_BYTES = 528 + 2 * MK_SLOTS;
+constexpr uint32_t MK_SMEM = MK_OFF_CSR + MK_CSR_BYTES + 1024;      // + alignment slack
+// packed weight images of one layer: [proj (t, kb) 4 x 16 KB | post (t, kb) 20 x 24 KB | lin (kb) 2 x 16 KB]
+constexpr uint32_t MK_IMG_PROJ = 2 * 64 * ROW_BYTES, MK_IMG_POST = 2 * 96 * ROW_BYTES, MK_IMG_LIN = 2 * 64 * ROW_BYTES;
+constexpr uint32_t MK_IMG_POST_OFF = 4 * MK_IMG_PROJ, MK_IMG_LIN_OFF = MK_IMG_POST_OFF + 20 * MK_IMG_POST;
+constexpr uint32_t MK_IMG_LAYER = MK_IMG_LIN_OFF + 2 * MK_IMG_LIN;
+constexpr int MK_KB_LAYER = 26;
+static_assert(MK_SMEM <= 232448, "tile kernel shared memory");
+static_assert(MK_STAGE % 1024 == 0 && MK_A_BYTES % 1024 == 0, "operand tiles are 1024-byte aligned");
+
+struct MkParams {
+    const float* x0;
+    float* x_out;
+    const int* rowptr;
+    const int* col_src;
+    const uint8_t* col_code;
+    const int2* tiles;
+    const int* num_tiles;
+    const uint8_t* images;
+    const float* tab;               // [L, 60, C]
+    const float* bpre;              // bias of pre_nns[t][0] of layer 0 tower 0
+    int64_t bpre_ts, bpre_ls;
+    const float* bpost;
+    int64_t bpost_ts, bpost_ls;
+    const float* blin;              // [L, H]  (BatchNorm folded)
+    const float* avg_deg_log;       // [L]
+    int L, skip;
+};
+
+__device__ __forceinline__ void mk_bar_producers() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+__global__ void __launch_bounds__(MK_THREADS, 1) pna_infer_tiles_kernel(const MkParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+    float* const X = reinterpret_cast<float*>(smem + MK_OFF_X);
+    float* const PS = reinterpret_cast<float*>(smem + MK_OFF_PS);
+    int* const rp = reinterpret_cast<int*>(smem + MK_OFF_CSR);
+    uint8_t* const csrc = smem + MK_OFF_CSR + 528;
+    uint8_t* const ccode = csrc + MK_SLOTS;
+
+    if (warp == 16) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full_bar[s], 256);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&acc_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int ntiles = __ldg(p.num_tiles);
+    uint32_t kc = 0;                 // k-blocks so far (ring stage = kc & 1, use = kc >> 1); identical in every thread
+    uint32_t accph = 0;              // accumulator hand-overs so far
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int2 tr = p.tiles[tile];
+        const int n0 = tr.x, rows = tr.y - tr.x;
+        if (warp == 16) {
+            // ================================ MMA issue ================================
+            for (int l = 0; l < p.L; ++l) {
+                for (int i = 0; i < MK_KB_LAYER; ++i, ++kc) {
+                    int N, kb;
+                    uint32_t dcol;
+                    bool last;
+                    if (i < 4) { N = 64; kb = i & 1; dcol = (uint32_t)(i >> 1) * 64u; last = i == 3; }
+                    else if (i < 24) { const int j = i - 4; N = 96; kb = j % 10; dcol = 128u + (uint32_t)(j / 10) * 96u; last = i == 23; }
+                    else { N = 64; kb = i - 24; dcol = 320u; last = i == 25; }
+                    const uint32_t s = kc & 1u, use = kc >> 1;
+                    mbar_wait(&full_bar[s], use & 1u);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t idesc = instr_desc(MODE_TF32X3, N, 0);
+                        const uint32_t a_hi = smem_u32(smem + s * MK_STAGE), a_lo = a_hi + MK_APLANE;
+                        const uint32_t b_hi = a_hi + MK_A_BYTES, b_lo = b_hi + (uint32_t)N * ROW_BYTES;
+                        const uint64_t dah0 = smem_desc_sw128(a_hi), dal0 = smem_desc_sw128(a_lo);
+                        const uint64_t dbh0 = smem_desc_sw128(b_hi), dbl0 = smem_desc_sw128(b_lo);
+                        const uint32_t d = tmem + dcol;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {                  // 4 K steps of 8 tf32 (32 bytes)
+                            const uint64_t o = (uint64_t)(j * 2);
+                            if (j == 0) umma<MODE_TF32X3>(d, dal0, dbh0, idesc, kb == 0 ? 0u : 1u);
+                            else umma_acc<MODE_TF32X3>(d, dal0 + o, dbh0 + o, idesc);
+                            umma_acc<MODE_TF32X3>(d, dah0 + o, dbl0 + o, idesc);
+                            umma_acc<MODE_TF32X3>(d, dah0 + o, dbh0 + o, idesc);
+                        }
+                        umma_commit(&empty_bar[s]);
+                        if (last) umma_commit(&acc_bar);
+                    }
+                    __syncwarp();
+                }
+            }
+            continue;
+        }
+        // ================================ producers / epilogues (warps 0-15) ================================
+        const int grp = tid >> 8, pt = tid & 255;
+        const int q = warp & 3, cg = warp >> 2, row = q * 32 + lane;          // epilogue: TMEM lane quarter, column group
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        // ---- stage the tile: node features and the CSR slice (tile-local indices)
+        const int slot0 = __ldg(p.rowptr + n0);
+        const int total = __ldg(p.rowptr + n0 + rows) - slot0;
+        for (int it = tid; it < MK_ROWS * 16; it += MK_PROD) {
+            const int r = it >> 4, c4 = it & 15;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < rows) v = ldg4(p.x0 + (size_t)(n0 + r) * MK_F + 4 * c4);
+            *reinterpret_cast<float4*>(X + r * MK_XLD + 4 * c4) = v;
+        }
+        for (int r = tid; r <= MK_ROWS; r += MK_PROD) rp[r] = r <= rows ? __ldg(p.rowptr + n0 + r) - slot0 : total;
+        for (int e = tid; e < total; e += MK_PROD) {
+            csrc[e] = (uint8_t)(__ldg(p.col_src + slot0 + e) - n0);
+            ccode[e] = __ldg(p.col_code + slot0 + e);
+        }
+        mk_bar_producers();
+
+        for (int l = 0; l < p.L; ++l) {
+            const uint8_t* const img = p.images + (size_t)l * MK_IMG_LAYER;
+            const float* const tab = p.tab + (size_t)l * GNN_NUM_BOND_CODES * MK_C;
+            // ---------------- phases A and B: 24 k-blocks, group g produces the k-blocks of ring stage g
+            for (int i = grp; i < 24; i += 2) {
+                if (i == 4 + grp) {
+                    // phase A accumulators -> Psrc tile (+ bias); every producer takes part, then phase B may gather
+                    mbar_wait(&acc_bar, accph & 1u);
+                    tc_fence_after();
+                    {
+                        const int t = cg >> 1, f0 = (cg & 1) * 32;
+                        const float* b = p.bpre + (size_t)l * p.bpre_ls + (size_t)t * p.bpre_ts + f0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float v[16];
+                            tmem_ld16(lane_addr + (uint32_t)(cg * 32 + h * 16), v);
+                            float* dst = PS + row * MK_PLD + cg * 32 + h * 16;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 bb = ldg4(b + h * 16 + j);
+                                *reinterpret_cast<float4*>(dst + j) =
+                                    make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mk_bar_producers();
+                }
+                const uint32_t kcur = kc + (uint32_t)i, s = kcur & 1u, use = kcur >> 1;
+                if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1u);
+                uint8_t* const stage = smem + s * MK_STAGE;
+                if (i < 4) {
+                    const int t = i >> 1, kb = i & 1;
+                    if (pt == 0) {
+                        mbar_expect_tx(&full_bar[s], MK_IMG_PROJ);
+                        bulk_g2s(stage + MK_A_BYTES, img + (size_t)(t * 2 + kb) * MK_IMG_PROJ, MK_IMG_PROJ, &full_bar[s]);
+                    }
+                    for (int it = pt; it < MK_ROWS * 8; it += 256) {
+                        const int r = it >> 3, c = it & 7;
+                        put_chunk_tf32<MODE_TF32X3>(stage, MK_APLANE, sw128_offset(r, c),
+                                                    *reinterpret_cast<const float4*>(X + r * MK_XLD + kb * 32 + 4 * c));
+                    }
+                } else {
+                    const int j = i - 4, t = j / 10, kb = j % 10;
+                    if (pt == 0) {
+                        mbar_expect_tx(&full_bar[s], MK_IMG_POST);
+                        bulk_g2s(stage + MK_A_BYTES, img + MK_IMG_POST_OFF + (size_t)(t * 10 + kb) * MK_IMG_POST, MK_IMG_POST,
+                                 &full_bar[s]);
+                    }
+                    if (kb < 2) {
+                        for (int it = pt; it < MK_ROWS * 8; it += 256) {
+                            const int r = it >> 3, c = it & 7;
+                            put_chunk_tf32<MODE_TF32X3>(stage, MK_APLANE, sw128_offset(r, c),
+                                                        *reinterpret_cast<const float4*>(X + r * MK_XLD + kb * 32 + 4 * c));
+                        }
+                    } else {
+                        // aggregates of 8 features (4 per thread) of tower t for one row: mean / min / max / std
+                        const int r = pt >> 1, h = pt & 1, col = t * MK_F + 8 * (kb - 2) + 4 * h;
+                        const int beg = rp[r], cnt = rp[r + 1] - beg;
+                        float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), sd = mean, mn = mean, mx = mean;
+                        if (cnt > 0) {
+                            PnaAcc<false> acc;
+                            acc.first(pna_add4(*reinterpret_cast<const float4*>(PS + (int)csrc[beg] * MK_PLD + col),
+                                               ldg4(tab + (int)ccode[beg] * MK_C + col)));
+                            for (int e = 1; e < cnt; ++e)
+                                acc.next(pna_add4(*reinterpret_cast<const float4*>(PS + (int)csrc[beg + e] * MK_PLD + col),
+                                                  ldg4(tab + (int)ccode[beg + e] * MK_C + col)));
+                            acc.finish(cnt, mean, sd);
+                            mn = acc.mn;
+                            mx = acc.mx;
+                        }
+                        put_chunk_tf32<MODE_TF32X3>(stage, MK_APLANE, sw128_offset(r, 0 + h), mean);
+                        put_chunk_tf32<MODE_TF32X3>(stage, MK_APLANE, sw128_offset(r, 2 + h), mn);
+                        put_chunk_tf32<MODE_TF32X3>(stage, MK_APLANE, sw128_offset(r, 4 + h), mx);
+                        put_chunk_tf32<MODE_TF32X3>(stage, MK_APLANE, sw128_offset(r, 6 + h), sd);
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(&full_bar[s]);
+            }
+            accph += 1;              // phase A hand-over consumed above
+            // ---------------- phase B accumulators -> O (combined, + bias) -> A operand of phase C in the ring
+            mbar_wait(&acc_bar, accph & 1u);
+            tc_fence_after();
+            accph += 1;
+            {
+                const int t = cg >> 1, half = cg & 1;
+                const uint32_t kcur = kc + 24u + (uint32_t)t, s = kcur & 1u, use = kcur >> 1;
+                if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1u);
+                uint8_t* const stage = smem + s * MK_STAGE;
+                if (q == 0 && half == 0 && lane == 0) {
+                    mbar_expect_tx(&full_bar[s], MK_IMG_LIN);
+                    bulk_g2s(stage + MK_A_BYTES, img + MK_IMG_LIN_OFF + (size_t)t * MK_IMG_LIN, MK_IMG_LIN, &full_bar[s]);
+                }
+                const int deg = rp[row + 1] - rp[row];
+                const float avg = __ldg(p.avg_deg_log + l);
+                float amp, att;
+                pna_scalers(deg, avg, amp, att);
+                const uint32_t base = lane_addr + 128u + (uint32_t)t * 96u + (uint32_t)half * 16u;
+                float v[16], d1[16], d2[16];
+                tmem_ld16(base, v);
+                tmem_ld16(base + 32u, d1);
+                tmem_ld16(base + 64u, d2);
+                const float* b = p.bpost + (size_t)l * p.bpost_ls + (size_t)t * p.bpost_ts + half * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 bb = ldg4(b + j);
+                    const float4 o = make_float4(v[j] + amp * d1[j] + att * d2[j] + bb.x,
+                                                 v[j + 1] + amp * d1[j + 1] + att * d2[j + 1] + bb.y,
+                                                 v[j + 2] + amp * d1[j + 2] + att * d2[j + 2] + bb.z,
+                                                 v[j + 3] + amp * d1[j + 3] + att * d2[j + 3] + bb.w);
+                    put_chunk_tf32<MODE_TF32X3>(stage, MK_APLANE, sw128_offset(row, half * 4 + (j >> 2)), o);
+                }
+                tc_fence_before();
+                fence_async_smem();
+                mbar_arrive(&full_bar[s]);
+            }
+            // ---------------- phase C accumulator -> x = relu(y + b') (+ x)
+            mbar_wait(&acc_bar, accph & 1u);
+            tc_fence_after();
+            accph += 1;
+            {
+                float v[16];
+                tmem_ld16(lane_addr + 320u + (uint32_t)cg * 16u, v);
+                const float* b = p.blin + (size_t)l * MK_F + cg * 16;
+                float* xr = X + row * MK_XLD + cg * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 bb = ldg4(b + j);
+                    float4 y = make_float4(fmaxf(v[j] + bb.x, 0.f), fmaxf(v[j + 1] + bb.y, 0.f), fmaxf(v[j + 2] + bb.z, 0.f),
+                                           fmaxf(v[j + 3] + bb.w, 0.f));
+                    if (p.skip) {
+                        const float4 xo = *reinterpret_cast<const float4*>(xr + j);
+                        y = make_float4(y.x + xo.x, y.y + xo.y, y.z + xo.z, y.w + xo.w);
+                    }
+                    *reinterpret_cast<float4*>(xr + j) = y;
+                }
+            }
+            tc_fence_before();
+            mk_bar_producers();
+            kc += MK_KB_LAYER;
+        }
+        // ---- write the tile's node features back
+        for (int it = tid; it < rows * 16; it += MK_PROD) {
+            const int r = it >> 4, c4 = it & 15;
+            *reinterpret_cast<float4*>(p.x_out + (size_t)(n0 + r) * MK_F + 4 * c4) =
+                *reinterpret_cast<const float4*>(X + r * MK_XLD + 4 * c4);
+        }
+        mk_bar_producers();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+// Greedy packing of consecutive graphs into tiles of <= 128 nodes and <= MK_SLOTS CSR slots.  One CTA per range of
+// 2048 graphs: node / slot prefixes of the range in shared memory, next[g] (where a tile starting at graph g ends) by
+// binary search in parallel, then one thread follows the chain; tiles are appended to an unordered list.
+constexpr int TB_GRAPHS = 2048;
+__global__ void __launch_bounds__(1024)
+build_tiles_kernel(const int* __restrict__ graph_ptr, const int* __restrict__ rowptr, int num_graphs,
+                   const int* __restrict__ valid_graphs, int2* __restrict__ tiles, int max_tiles, int* num_tiles, int* err) {
+    __shared__ int gp[TB_GRAPHS + 1], sp[TB_GRAPHS + 1], nxt[TB_GRAPHS];
+    int G = num_graphs;
+    if (valid_graphs != nullptr) G = min(G, __ldg(valid_graphs));
+    const int g0 = blockIdx.x * TB_GRAPHS;
+    const int cnt = min(TB_GRAPHS, G - g0);
+    if (cnt <= 0) return;
+    for (int i = threadIdx.x; i <= cnt; i += blockDim.x) {
+        const int n = __ldg(graph_ptr + g0 + i);
+        gp[i] = n;
+        sp[i] = __ldg(rowptr + n);
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < cnt; g += blockDim.x) {
+        // largest e in (g, cnt] with gp[e] - gp[g] <= 128 and sp[e] - sp[g] <= MK_SLOTS (both prefixes are monotone)
+        int lo = g, hi = cnt;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (gp[mid] - gp[g] <= MK_ROWS && sp[mid] - sp[g] <= MK_SLOTS) lo = mid;
+            else hi = mid - 1;
+        }
+        nxt[g] = lo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int g = 0;
+        while (g < cnt) {
+            int e = nxt[g];
+            if (e == g) {                    // a single graph exceeds a tile: reported, skipped
+                if (err) atomicOr(err, GNN_INPUT_ERR_EDGE_INDEX);
+                e = g + 1;
+            } else if (gp[e] > gp[g]) {
+                const int slot = atomicAdd(num_tiles, 1);
+                if (slot < max_tiles) tiles[slot] = make_int2(gp[g], gp[e]);
+            }
+            g = e;
+        }
+    }
+}
+}  // namespace tc
+
+extern "C" int64_t gnn_tc_infer_image_bytes(int num_layers) { return (int64_t)num_layers * tc::MK_IMG_LAYER; }
+
+extern "C" int gnn_tc_infer_pack(const float* wpre, int64_t wpre_tower_stride, const float* Vx, const float* wpost,
+                                 int64_t wpost_tower_stride, int64_t layer_stride, const float* wlin_folded,
+                                 int num_layers, int F, int F_out, int towers, void* images, int64_t image_bytes,
+                                 void* stream) {
+    if (F != MK_F || F_out != MK_FO || towers != MK_T) return GNN_ERR_UNSUPPORTED;
+    if (num_layers < 1 || image_bytes < gnn_tc_infer_image_bytes(num_layers)) return GNN_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(images) & 127) != 0) return GNN_ERR_BAD_ARG;
+    cudaStream_t st = gnn_stream(stream);
+    for (int l = 0; l < num_layers; ++l) {
+        uint8_t* img = reinterpret_cast<uint8_t*>(images) + (size_t)l * MK_IMG_LAYER;
+        VProjWeight pw{wpre + l * layer_stride, wpre_tower_stride, F, towers, 1, 1};
+        pack_b_kernel<MODE_TF32X3, VProjWeight><<<dim3(2 * 2, 2, 1), PROD_GROUP_THREADS, 0, st>>>(pw, 64, (int64_t)F, 2, 2, img);
+        VPostWeight ow{wpost + l * layer_stride, wpost_tower_stride, F, F_out, MK_FO,
+                       Vx + (size_t)l * towers * 3 * F_out * F, 64};
+        pack_b_kernel<MODE_TF32X3, VPostWeight><<<dim3(10 * 3, 1, 2), PROD_GROUP_THREADS, 0, st>>>(
+            ow, 96, (int64_t)(64 + 4 * F), 1, 10, img + MK_IMG_POST_OFF);
+        VRowMajor lw{wlin_folded + (size_t)l * F * F, F, F, F, 0, 1};
+        pack_b_kernel<MODE_TF32X3, VRowMajor><<<dim3(2 * 2, 1, 1), PROD_GROUP_THREADS, 0, st>>>(lw, 64, (int64_t)F, 1, 2,
+                                                                                                img + MK_IMG_LIN_OFF);
+    }
+    return gnn_launch_status();
+}
+
+extern "C" int gnn_tc_infer_tiles(const int32_t* graph_ptr, const int32_t* rowptr, int64_t num_graphs,
+                                  const int32_t* valid_graphs, int32_t* tiles, int64_t max_tiles, int32_t* num_tiles,
+                                  int32_t* err_flag, void* stream) {
+    if (num_graphs < 1 || max_tiles < 1) return GNN_ERR_BAD_ARG;
+    cudaStream_t st = gnn_stream(stream);
+    cudaError_t e = cudaMemsetAsync(num_tiles, 0, sizeof(int), st);
+    if (e != cudaSuccess) return (int)e;
+    const int blocks = (int)gnn_ceil_div(num_graphs, TB_GRAPHS);
+    build_tiles_kernel<<<blocks, 1024, 0, st>>>(graph_ptr, rowptr, (int)num_graphs, valid_graphs,
+                                                reinterpret_cast<int2*>(tiles), (int)max_tiles, num_tiles, err_flag);
+    return gnn_launch_status();
+}
+
+extern "C" int gnn_tc_pna_stack_infer(const float* x0, const int32_t* rowptr, const int32_t* col_src,
+                                      const uint8_t* col_code, const int32_t* tiles, const int32_t* num_tiles,
+                                      const void* images, const float* tab, const float* bpre, int64_t bpre_tower_stride,
+                                      int64_t bpre_layer_stride, const float* bpost, int64_t bpost_tower_stride,
+                                      int64_t bpost_layer_stride, const float* blin, const float* avg_deg_log,
+                                      int num_layers, int F, int F_out, int towers, int skip, float* x_out,
+                                      void* stream) {
+    if (F != MK_F || F_out != MK_FO || towers != MK_T) return GNN_ERR_UNSUPPORTED;
+    if (num_layers < 1) return GNN_ERR_BAD_ARG;
+    REQUIRE_VEC(x0, F);
+    REQUIRE_VEC(x_out, F);
+    REQUIRE_VEC(tab, (int64_t)MK_C);
+    REQUIRE_VEC(bpre, bpre_tower_stride);
+    REQUIRE_VEC(bpre, bpre_layer_stride);
+    REQUIRE_VEC(bpost, bpost_tower_stride);
+    REQUIRE_VEC(bpost, bpost_layer_stride);
+    REQUIRE_VEC(blin, F);
+    MkParams p{x0, x_out, rowptr, col_src, col_code, reinterpret_cast<const int2*>(tiles), num_tiles,
+               reinterpret_cast<const uint8_t*>(images), tab, bpre, bpre_tower_stride, bpre_layer_stride, bpost,
+               bpost_tower_stride, bpost_layer_stride, blin, avg_deg_log, num_layers, skip};
+    cudaError_t e = cudaFuncSetAttribute(pna_infer_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MK_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    pna_infer_tiles_kernel<<<gnn_sm_count(), MK_THREADS, MK_SMEM, gnn_stream(stream)>>>(p);
+    return gnn_launch_status();
+}

@@ -35,11 +35,12 @@ class CompactBatch:
     is_compact = True
 
     def __init__(self, num_graphs: int, pad_nodes: int, pad_slots: int, self_loops: bool, own_surplus: bool = False,
-                 **tensors):
+                 tileable: bool = False, **tensors):
         self.num_graphs = int(num_graphs)           # graph capacity (outputs have cap + 1 rows; rows [:B] are real)
         self.pad_nodes, self.pad_slots = int(pad_nodes), int(pad_slots)
         self.self_loops = bool(self_loops)
         self.own_surplus = bool(own_surplus)        # surplus CSR slots are self-edges of the padding nodes
+        self.tileable = bool(tileable)              # every graph fits an inference tile (<= 128 nodes, <= 1024 slots)
         for k in self.FIELDS:
             setattr(self, k, tensors.get(k))
         self.err = tensors.get("err")
@@ -71,7 +72,8 @@ class CompactBatch:
     def _apply(self, fn):
         kw = {k: (fn(getattr(self, k)) if getattr(self, k) is not None else None) for k in self.FIELDS}
         kw["err"] = fn(self.err) if self.err is not None else None
-        return CompactBatch(self.num_graphs, self.pad_nodes, self.pad_slots, self.self_loops, self.own_surplus, **kw)
+        return CompactBatch(self.num_graphs, self.pad_nodes, self.pad_slots, self.self_loops, self.own_surplus,
+                            self.tileable, **kw)
 
     def to(self, *args, **kwargs):
         return self._apply(lambda t: t.to(*args, **kwargs))
@@ -247,6 +249,11 @@ class CompactGraphStore:
                               node_off=host["node_off"].long(), slot_off=host["slot_off"].long(), para=host.get("para"))
         return self
 
+    @property
+    def tileable(self) -> bool:
+        """Every graph fits one inference tile of gnn_tc_pna_stack_infer (<= 128 nodes, <= 1024 CSR slots)."""
+        return bool(self.num_graphs > 0 and int(self.node_count.max()) <= 128 and int(self.slot_count.max()) <= 1024)
+
     # ---- planning (host) -----------------------------------------------------------------------
     def sizes(self, ids: torch.Tensor) -> Tuple[int, int]:
         """(nodes, CSR slots) of the batch `ids` (host int64 tensor) - no device access."""
@@ -312,7 +319,7 @@ class CompactGraphStore:
         i32 = dict(dtype=torch.int32, device=dev)
         u8 = dict(dtype=torch.uint8, device=dev)
         para = torch.zeros((num_graphs + 1) * self.num_para, dtype=torch.float32, device=dev) if self.num_para else None
-        return CompactBatch(num_graphs, pad_nodes, pad_slots, self.self_loops, own_surplus,
+        return CompactBatch(num_graphs, pad_nodes, pad_slots, self.self_loops, own_surplus, self.tileable,
                             x=torch.zeros(max(pad_nodes, 1), 9, **u8), rowptr=torch.zeros(pad_nodes + 1, **i32),
                             col_src=torch.zeros(max(pad_slots, 1), **i32), col_code=torch.zeros(max(pad_slots, 1), **u8),
                             node_graph=torch.zeros(max(pad_nodes, 1), **i32), graph_ptr=torch.zeros(num_graphs + 2, **i32),
@@ -408,7 +415,7 @@ class CompactGraphStore:
             para = torch.ones((cap + 1) * self.num_para, dtype=torch.float32)
             para[:nb * self.num_para] = h["para"][ids].reshape(-1)
         valid = torch.tensor([n, nb, s, 0], dtype=torch.int32)
-        out = CompactBatch(cap, pn, ps, self.self_loops, own_surplus, x=x, rowptr=rowptr, col_src=col_src, col_code=col_code,
+        out = CompactBatch(cap, pn, ps, self.self_loops, own_surplus, self.tileable, x=x, rowptr=rowptr, col_src=col_src, col_code=col_code,
                            node_graph=node_graph, graph_ptr=graph_ptr, para=para, valid=valid,
                            err=torch.zeros(1, dtype=torch.int32))
         return out.pin_memory() if pin else out

@@ -40,6 +40,12 @@ FOLD_DST = os.environ.get("GNN_B200_FOLD", "1") != "0"
 # instead of 0.5 GB of DRAM traffic); "all": training forwards too (the kernel then also stores the aggregates:
 # 183 us, slower than the two-kernel path); "off": never.
 FUSE_AGG = os.environ.get("GNN_B200_FUSE_AGG", "infer")
+# Store-resident inference of the default architecture: the whole PNAConv stack of a tile of <= 128 nodes (whole
+# graphs) in one persistent CTA (gnn_tc_pna_stack_infer: node features and source projections stay in shared memory,
+# one launch for all layers).  Bit-identical to the per-layer kernels, but measured slower on B200 (1.59 vs 1.46 ms per
+# 4096 graphs: its two-stage operand ring leaves the tensor pipe waiting), so it is opt-in:
+# GNN_B200_TILE_INFER=1.
+TILE_INFER = os.environ.get("GNN_B200_TILE_INFER", "0") == "1"
 
 
 @dataclasses.dataclass
@@ -626,8 +632,14 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         _c("gnn_pna_fold_fwd", conv0.post_nns[0][0].weight, tsp, conv0.pre_nns[0][0].weight, tower_stride_pre,
            layer_stride, L, F, Fo, T, Vx_all)
 
+    use_tiles = (TILE_INFER and compact and not save and not training and fold and mm == 0 and L > 0 and H == 64
+                 and pp.post_layers == 1 and bool(getattr(graph, "tileable", False))
+                 and all(b.module.running_mean is not None for b in model.batch_norms))
+    if use_tiles:
+        x = _conv_stack_tiles(model, x, graph, tab, Vx_all, layer_stride, tower_stride_pre)
+
     layers = []
-    for l in range(L):
+    for l in range(L if use_tiles else 0, L):
         conv, bn = model.convs[l], model.batch_norms[l].module
         rec = _Saved()
         rec.x_in = x
@@ -768,6 +780,40 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         sv.training, sv.mm, sv.fold = training, mm, fold
         sv.compact, sv.valid_nodes, sv.valid_graphs = compact, valid_nodes, valid_graphs
     return out, sv
+
+
+def _conv_stack_tiles(model: PNAPCSAFT, x, g, tab, Vx_all, layer_stride, tower_stride_pre):
+    """All PNAConv + BatchNorm(eval) + ReLU + skip layers of a compact batch in ONE launch (gnn_tc_pna_stack_infer)."""
+    pp = model.pna_params
+    dev = x.device
+    H = model.hidden_dim
+    F, Fo, T, L = H, H // TOWERS, TOWERS, pp.propagation_depth
+    n = x.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    conv0 = model.convs[0]
+    wf_all = torch.empty(L, H, H, **f32)
+    bf_all = torch.empty(L, H, **f32)
+    for l in range(L):
+        conv, bn = model.convs[l], model.batch_norms[l].module
+        _c("gnn_bn_fold_linear", conv.lin.weight, H, conv.lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+           float(bn.eps), H, H, wf_all[l], bf_all[l])
+    nbytes = _lib.query("gnn_tc_infer_image_bytes", L)
+    images = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    pre0, post0 = conv0.pre_nns[0][0], conv0.post_nns[0][0]
+    ts_post = model._offset_of(conv0.post_nns[1][0].weight) - model._offset_of(post0.weight)
+    bs_pre = model._offset_of(conv0.pre_nns[1][0].bias) - model._offset_of(pre0.bias)
+    bs_post = model._offset_of(conv0.post_nns[1][0].bias) - model._offset_of(post0.bias)
+    _c("gnn_tc_infer_pack", pre0.weight, tower_stride_pre, Vx_all, post0.weight, ts_post, layer_stride, wf_all, L, F, Fo, T,
+       images, images.numel())
+    cap = int(g.num_graphs)
+    tiles = torch.empty(2 * max(cap, 1), dtype=torch.int32, device=dev)
+    ntiles = torch.empty(1, dtype=torch.int32, device=dev)
+    _c("gnn_tc_infer_tiles", g.graph_ptr, g.rowptr, cap, g.valid[1:2], tiles, max(cap, 1), ntiles, g.err)
+    avg = torch.cat([c.aggr_module.avg_deg_log.reshape(1) for c in model.convs]).to(torch.float32)
+    x_out = torch.zeros(n, H, **f32)        # rows outside every tile (padding nodes) stay zero
+    _c("gnn_tc_pna_stack_infer", x, g.rowptr, g.col_src, g.col_code, tiles, ntiles, images, tab, pre0.bias, bs_pre,
+       layer_stride, post0.bias, bs_post, layer_stride, bf_all, avg, L, F, Fo, T, 1 if pp.skip_connections else 0, x_out)
+    return x_out
 
 
 def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.Tensor):

@@ -399,6 +399,39 @@ int gnn_tc_linear_skip_fwd(const float* X, int64_t ldx, const float* W, int64_t 
                            int64_t M, int N, int K, int act, const float* skip, int64_t ldskip, float* Y,
                            int64_t ldy, int precision, void* pack_ws, int64_t pack_ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- inference: the whole PNAConv stack per tile
+ * Store-resident inference of the default architecture (F = 64, F_out = 32, 2 towers, folded destination projection,
+ * post_layers == 1; other shapes: GNN_ERR_UNSUPPORTED).  Replaces, for ALL layers at once, the chain
+ * gnn_tc_pna_projsrc_fwd -> gnn_tc_pna_postf_agg_fwd -> gnn_bn_fold_linear + gnn_tc_linear_skip_fwd, i.e.
+ * PNAConv + BatchNorm (running statistics) + ReLU + skip of reference models.py:126-131: one persistent CTA keeps a
+ * tile of <= 128 nodes made of whole graphs (no edge leaves a graph) in shared memory - node features, source
+ * projections, CSR slice - and runs every layer on it with tcgen05 MMAs (TF32x3); only packed weights are re-read.
+ *   gnn_tc_infer_pack   : packed weight images of all layers (wpre / wpost point at tower 0 of layer 0, layer l sits
+ *                         l*layer_stride floats further; Vx [L,T,3,F_out,F] from gnn_pna_fold_fwd; wlin_folded
+ *                         [L,H,H] from gnn_bn_fold_linear)
+ *   gnn_tc_infer_tiles  : greedy packing of consecutive graphs (graph_ptr [G+1], only the first *valid_graphs when
+ *                         given) into tiles = int2 (first node, end node) with <= 128 nodes and <= 1024 CSR slots;
+ *                         tiles needs room for one tile per graph; a graph that fits no tile sets err_flag
+ *   gnn_tc_pna_stack_infer : x_out [N, H] = the conv stack applied to x0 [N, H]; tab [L,60,T*F] bond tables
+ *                         (gnn_bond_table_fwd), bpre / bpost = bias of pre_nns[0][0] / post_nns[0][0] of layer 0
+ *                         (+ tower / layer strides), blin [L,H] folded bias, avg_deg_log [L]; rows of nodes outside
+ *                         every tile are left untouched */
+int64_t gnn_tc_infer_image_bytes(int num_layers);
+int gnn_tc_infer_pack(const float* wpre, int64_t wpre_tower_stride, const float* Vx, const float* wpost,
+                      int64_t wpost_tower_stride, int64_t layer_stride, const float* wlin_folded,
+                      int num_layers, int F, int F_out, int towers, void* images, int64_t image_bytes,
+                      void* stream);
+int gnn_tc_infer_tiles(const int32_t* graph_ptr, const int32_t* rowptr, int64_t num_graphs,
+                       const int32_t* valid_graphs, int32_t* tiles, int64_t max_tiles, int32_t* num_tiles,
+                       int32_t* err_flag, void* stream);
+int gnn_tc_pna_stack_infer(const float* x0, const int32_t* rowptr, const int32_t* col_src,
+                           const uint8_t* col_code, const int32_t* tiles, const int32_t* num_tiles,
+                           const void* images, const float* tab, const float* bpre, int64_t bpre_tower_stride,
+                           int64_t bpre_layer_stride, const float* bpost, int64_t bpost_tower_stride,
+                           int64_t bpost_layer_stride, const float* blin, const float* avg_deg_log,
+                           int num_layers, int F, int F_out, int towers, int skip, float* x_out,
+                           void* stream);
+
 /* ---------------------------------------------------------------- pooling, loss, optimiser
  * global_add_pool (models.py:133): out[g,:] = sum_{i in graph g} x[i,:]; graph_ptr int32 [B+1] */
 int gnn_segment_pool_fwd(const float* x, const int32_t* graph_ptr, int64_t num_graphs, int C,

@@ -615,6 +615,73 @@ def gnn_tc_pna_projsrc_wgrad(dPsrc, x, n, f, towers, dwpre, wts, dbpre, bts, pre
             _flat(dbpre, f, t * bts).add_(dPsrc[:n, t * f:(t + 1) * f].sum(0))
 
 
+# ------------------------------------------------------------------ inference: whole conv stack per tile
+_INFER_IMAGES = {}      # the CPU restatement keeps the weight references instead of packed tensor-core images
+
+
+def gnn_tc_infer_image_bytes(num_layers):
+    return 256
+
+
+def gnn_tc_infer_pack(wpre, wpre_ts, Vx, wpost, wpost_ts, layer_stride, wlin_folded, num_layers, f, f_out, towers, images,
+                      image_bytes, stream=None):
+    _INFER_IMAGES[images.data_ptr()] = (wpre, wpre_ts, Vx, wpost, wpost_ts, layer_stride, wlin_folded)
+
+
+def gnn_tc_infer_tiles(graph_ptr, rowptr, num_graphs, valid_graphs, tiles, max_tiles, num_tiles, err_flag=None,
+                       stream=None, range_graphs=2048):
+    """Greedy packing of consecutive graphs into tiles of <= 128 nodes and <= 1024 CSR slots, restarted every
+    `range_graphs` graphs (one CTA per range in the CUDA kernel, which appends its tiles in no particular order)."""
+    g_total = int(num_graphs) if valid_graphs is None else min(int(num_graphs), int(valid_graphs.reshape(-1)[0]))
+    gp = graph_ptr.tolist()
+    rp = rowptr.tolist()
+    out = []
+    for g0 in range(0, g_total, range_graphs):
+        g, end = g0, min(g_total, g0 + range_graphs)
+        while g < end:
+            e = g
+            while e < end and gp[e + 1] - gp[g] <= 128 and rp[gp[e + 1]] - rp[gp[g]] <= 1024:
+                e += 1
+            if e == g:
+                if err_flag is not None:
+                    err_flag |= 1
+                e = g + 1
+            elif gp[e] > gp[g]:
+                out.append((gp[g], gp[e]))
+            g = e
+    num_tiles[0] = len(out)
+    t = tiles.view(-1, 2)
+    for i, (a, b) in enumerate(out[:max_tiles]):
+        t[i, 0], t[i, 1] = a, b
+
+
+def gnn_tc_pna_stack_infer(x0, rowptr, col_src, col_code, tiles, num_tiles, images, tab, bpre, bpre_ts, bpre_ls, bpost,
+                           bpost_ts, bpost_ls, blin, avg_deg_log, num_layers, f, f_out, towers, skip, x_out, stream=None):
+    wpre, wpre_ts, Vx, wpost, wpost_ts, ls, wlin = _INFER_IMAGES[images.data_ptr()]
+    n, c = x0.shape[0], towers * f
+    x = x0.clone()
+    scal = torch.zeros(n, 2, dtype=x.dtype)
+    for l in range(num_layers):
+        psrc = torch.zeros(n, c, dtype=x.dtype)
+        for t in range(towers):
+            w = _mat(wpre, f, 3 * f, 3 * f, l * ls + t * wpre_ts)
+            psrc[:, t * f:(t + 1) * f] = x @ w[:, f:2 * f].t() + _flat(bpre, f, l * bpre_ls + t * bpre_ts)
+        A = torch.zeros(n, towers * 4 * f, dtype=x.dtype)
+        gnn_pna_aggregate_src_fwd(psrc, tab[l], rowptr, col_src, col_code, n, towers, f, A)
+        gnn_pna_scalers(rowptr, avg_deg_log[l:l + 1], n, scal)
+        v = Vx[l].reshape(towers, 3, f_out, f)
+        O = torch.zeros(n, towers * f_out, dtype=x.dtype)
+        for t in range(towers):
+            wp = _mat(wpost, f_out, 13 * f, 13 * f, l * ls + t * wpost_ts)
+            w = torch.cat([v[t, 0], v[t, 1], v[t, 2], wp[:, f:]], dim=1)
+            O[:, t * f_out:(t + 1) * f_out] = (_postf_cat(x, A, scal, n, f, towers, t) @ w.t() +
+                                               _flat(bpost, f_out, l * bpost_ls + t * bpost_ts))
+        y = (O @ wlin[l].t() + blin[l]).clamp(min=0)
+        x = y + x if skip else y
+    for a, b in tiles.view(-1, 2)[: int(num_tiles[0])].tolist():
+        x_out[a:b] = x[a:b]
+
+
 # ------------------------------------------------------------------ BatchNorm / pool / loss / optimiser
 def gnn_bn_workspace_bytes(rows, c):
     return 256

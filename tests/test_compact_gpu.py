@@ -177,3 +177,48 @@ def test_host_fed_compact_step_and_epoch():
     mean_loss = e1.fit_epoch(store, 128, generator=torch.Generator().manual_seed(0))
     assert mean_loss == mean_loss and mean_loss > 0
     assert int(e1.step_count.item()) == 1 + 5
+
+
+def test_tile_inference_kernel_matches_per_layer_kernels():
+    """gnn_tc_pna_stack_infer (all PNAConv layers of a <= 128-node tile in one persistent CTA) against the per-layer
+    kernels: the same TF32x3 products accumulated in the same order, so the predictions agree bit for bit; the tile
+    list covers every real node exactly once."""
+    from gnnepcsaft_b200 import _lib
+    from gnnepcsaft_b200.train import models as M
+    c = cfg()
+    packed = make_packed_graphs(700, seed=13, num_para=c.num_para)
+    _, o64, m = make_pair(c, packed.in_degree_histogram())
+    m.to(DEV)
+    eng = TrainEngine.from_config(m, c, distributed=False)
+    eng.use_cuda_graphs = False
+    store = CompactGraphStore(packed, device=DEV)
+    assert store.tileable
+    ids = torch.randperm(700, generator=torch.Generator().manual_seed(2))[:600]
+    old = M.TILE_INFER
+    try:
+        M.TILE_INFER = False
+        y_ref = eng.predict_from_store(store, ids).clone()
+        M.TILE_INFER = True
+        y = eng.predict_from_store(store, ids).clone()
+    finally:
+        M.TILE_INFER = old
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    o64.eval()
+    with torch.no_grad():
+        y64 = o64(batch_from_packed(packed, ids))
+    assert float((y.double().cpu() - y64).abs().max() / y64.abs().max()) <= 1e-5
+    # the tile builder: tiles partition the real nodes, each within the limits
+    cb = store.batch(ids)
+    tiles = torch.zeros(2 * 600, dtype=torch.int32, device=DEV)
+    nt = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _lib.call("gnn_tc_infer_tiles", cb.graph_ptr, cb.rowptr, cb.num_graphs, cb.valid[1:2], tiles, 600, nt, cb.err,
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    t = tiles.view(-1, 2)[: int(nt)].cpu()
+    t = t[t[:, 0].argsort()]
+    n_real = int(cb.valid[0])
+    assert int(t[0, 0]) == 0 and int(t[-1, 1]) == n_real and torch.equal(t[1:, 0], t[:-1, 1])
+    assert int((t[:, 1] - t[:, 0]).max()) <= 128 and int(cb.err.item()) == 0
+    gp = set(cb.graph_ptr.cpu().tolist())
+    assert all(int(v) in gp for v in t.reshape(-1))          # tile boundaries are graph boundaries
