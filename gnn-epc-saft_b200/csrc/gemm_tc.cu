@@ -2304,10 +2304,21 @@ __global__ void __launch_bounds__(MK_THREADS, 1) pna_infer_tiles_kernel(const Mk
                         const int beg = rp[r], cnt = rp[r + 1] - beg;
                         float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), sd = mean, mn = mean, mx = mean;
                         if (cnt > 0) {
+                            // the loads of the first PF in-edges go out together (slots beyond the segment re-read
+                            // its first message, which leaves every statistic unchanged); molecules rarely have more
+                            constexpr int PF = 5;
+                            float4 pr[PF], tb[PF];
+#pragma unroll
+                            for (int e = 0; e < PF; ++e) {
+                                const int slot = beg + (e < cnt ? e : 0);
+                                pr[e] = *reinterpret_cast<const float4*>(PS + (int)csrc[slot] * MK_PLD + col);
+                                tb[e] = ldg4(tab + (int)ccode[slot] * MK_C + col);
+                            }
                             PnaAcc<false> acc;
-                            acc.first(pna_add4(*reinterpret_cast<const float4*>(PS + (int)csrc[beg] * MK_PLD + col),
-                                               ldg4(tab + (int)ccode[beg] * MK_C + col)));
-                            for (int e = 1; e < cnt; ++e)
+                            acc.first(pna_add4(pr[0], tb[0]));
+#pragma unroll
+                            for (int e = 1; e < PF; ++e) acc.next(pna_add4(pr[e], tb[e]));
+                            for (int e = PF; e < cnt; ++e)
                                 acc.next(pna_add4(*reinterpret_cast<const float4*>(PS + (int)csrc[beg + e] * MK_PLD + col),
                                                   ldg4(tab + (int)ccode[beg + e] * MK_C + col)));
                             acc.finish(cnt, mean, sd);
