@@ -1596,9 +1596,21 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
         // weights (B) are packed once per call when a workspace is given and the M loop re-uses them
         const int num_kb = (int)gnn_ceil_div(K, kb_elems);
         const int64_t pack_bytes = (int64_t)groups * g.n_tiles * num_kb * parts * BN * ROW_BYTES;
-        const bool packed = pack_ws != nullptr && splits == 1 && g.m_tiles >= 2 && pack_bytes <= pack_ws_bytes &&
-                            (reinterpret_cast<uintptr_t>(pack_ws) & 127) == 0;
-        if (packed) {
+        // pack_ws_bytes < 0: the image of exactly these weights was packed into pack_ws by an earlier call (inference
+        // with constant weights): no pack kernel
+        const bool prepacked = pack_ws_bytes < 0;
+        if (prepacked) pack_ws_bytes = -pack_ws_bytes;
+        const bool fits = pack_ws != nullptr && splits == 1 && pack_bytes <= pack_ws_bytes &&
+                          (reinterpret_cast<uintptr_t>(pack_ws) & 127) == 0;
+        const bool packed = fits;
+        if (prepacked && !fits) return GNN_ERR_WORKSPACE;
+        if (packed && prepacked) {
+            auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+            kern<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g,
+                                                                        reinterpret_cast<const uint8_t*>(pack_ws), ag);
+        } else if (packed) {
             dim3 pgrid((unsigned)(num_kb * ((BN + PACK_ROWS - 1) / PACK_ROWS)), (unsigned)g.n_tiles, (unsigned)groups);
             pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
                                                                           reinterpret_cast<uint8_t*>(pack_ws));

@@ -124,6 +124,7 @@ class TrainEngine:
         _c("gnn_adamw_amsgrad_step", self.net._arena, self.grad, self.exp_avg, self.exp_avg_sq, self.max_exp_avg_sq,
            self.numel, self.step_count, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.t0, scale)
         _c("gnn_step_increment", self.step_count)
+        self.net._weights_epoch += 1        # invalidates the inference plan (weights changed through raw pointers)
         return loss * scale if self.world > 1 else loss
 
     def _train_bucket(self, ent):
@@ -131,6 +132,7 @@ class TrainEngine:
         parallel: the captured graph ends with the backward pass and the collective + optimizer kernels (3 launches)
         are issued eagerly - NCCL registers the buffers of captured collectives across ranks at capture time, which
         needs lock-step captures, but the ranks meet new shape buckets at different steps."""
+        self.net._weights_epoch += 1        # a replayed graph runs no Python: invalidate the inference plan here
         if self.world == 1:
             return self._run_bucket(ent, self._step)
         return self._step_update(self._run_bucket(ent, self._step_compute))
@@ -147,6 +149,14 @@ class TrainEngine:
         finally:
             net.train(was_training)
         return out
+
+    def _fresh_plan(self, batch):
+        """Captured eval graphs contain no weight-preparation kernels: bring the model's inference plan up to date with
+        one eager forward whenever the weights changed since it was filled."""
+        net = self.net
+        kind = "tiles" if (models.TILE_INFER and getattr(batch, "tileable", False)) else "layers"
+        if net._matmul_mode() >= 0 and net._infer_plan(self.grad.device, kind).filling:
+            self._predict(batch)
 
     def _predict(self, batch) -> torch.Tensor:
         net = self.net
@@ -228,6 +238,7 @@ class TrainEngine:
                 pn, ps = bucket(n, s)
                 ent = self._bucket("eval", store, int(ids.numel()), pn, ps)
                 store.batch(ids, out=ent["batch"], ids_device=ids_device)
+                self._fresh_plan(ent["batch"])
                 out = self._run_bucket(ent, self._predict)
         finally:
             net.train(was_training)
@@ -269,6 +280,7 @@ class TrainEngine:
                     for a, b in ranges:
                         ids_dev = ids_all[a - lo:b - lo]
                         store.batch(ids_dev, out=ent["batch"], ids_device=ids_dev)
+                        self._fresh_plan(ent["batch"])
                         y = self._run_bucket(ent, self._predict)
                         if out is not False:
                             out[a - lo:b - lo].copy_(y[:b - a])

@@ -69,6 +69,12 @@ class EnsemblePredictor:
         return len(self.nets)
 
     # ---- one batch ------------------------------------------------------------------------------
+    def _fresh_plans(self, batch):
+        """The captured ensemble graph holds no weight-preparation kernels (see TrainEngine._fresh_plan)."""
+        kind = "tiles" if (M.TILE_INFER and getattr(batch, "tileable", False)) else "layers"
+        if any(n._matmul_mode() >= 0 and n._infer_plan(self.device, kind).filling for n in self.nets):
+            self._predict_all(batch)
+
     def _predict_all(self, batch) -> torch.Tensor:
         """[rows, K, P]: rows = molecules (+ the padding graph of a compact batch)."""
         compact = getattr(batch, "is_compact", False)
@@ -118,6 +124,7 @@ class EnsemblePredictor:
             n, s = store.sizes(ids)
             ent = eng._bucket("ensemble", store, int(ids.numel()), *bucket(n, s))
             store.batch(ids, out=ent["batch"])
+            self._fresh_plans(ent["batch"])
             out = eng._run_bucket(ent, self._predict_all)
         return out[:int(ids.numel())].to(dtype)
 
@@ -145,5 +152,6 @@ class EnsemblePredictor:
             for a, b in ranges:
                 ids_dev = ids_all[a - lo:b - lo]
                 store.batch(ids_dev, out=ent["batch"], ids_device=ids_dev)
+                self._fresh_plans(ent["batch"])
                 out[a - lo:b - lo].copy_(eng._run_bucket(ent, self._predict_all)[:b - a])
         return out.mean(dim=1).to(dtype), out.to(dtype)

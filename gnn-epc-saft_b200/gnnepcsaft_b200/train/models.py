@@ -175,12 +175,12 @@ def _al(t, *dims):
     return (t.data_ptr() & 15) == 0 and all((d & 3) == 0 for d in dims)
 
 
-def _lin_fwd(mm, X, ldx, W, ldw, bias, M, N, K, act, Y, ldy):
+def _lin_fwd(mm, X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, plan=None, key=None):
     if mm < 0 or not _al(X, ldx, K):
         _c("gnn_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy)
     else:
-        ws = _pack_ws(Y.device)
-        _c("gnn_tc_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, mm, ws, ws.numel())
+        ws, nb = _site_ws(plan, key, N, K, Y.device)
+        _c("gnn_tc_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, mm, ws, nb)
 
 
 def _lin_dgrad(mm, dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx):
@@ -198,12 +198,12 @@ def _lin_wgrad(mm, dY, lddy, X, ldx, M, N, K, dW, lddw, db):
         _c("gnn_tc_linear_wgrad", dY, lddy, X, ldx, M, N, K, dW, lddw, db, mm)
 
 
-def _post_fwd(mm, *args):
+def _post_fwd(mm, *args, ws=None):
     if mm < 0:
         _c("gnn_pna_post_fwd", *args)
     else:
-        ws = _pack_ws(args[-1].device)
-        _c("gnn_tc_pna_post_fwd", *args, mm, ws, ws.numel())
+        buf, nb = ws if ws is not None else (_pack_ws(args[-1].device), _pack_ws(args[-1].device).numel())
+        _c("gnn_tc_pna_post_fwd", *args, mm, buf, nb)
 
 
 def _post_dgrad(mm, *args):
@@ -261,6 +261,53 @@ PACK_WS_BYTES = 32 << 20      # covers the wide model (H = 256: 7.9 MB for the p
 def _pack_ws(device):
     """Scratch for the packed weight operand of the tensor-core GEMMs (stream-ordered reuse)."""
     return _WS.get("pack", PACK_WS_BYTES, device)
+
+
+class _InferPlan:
+    """Weight-derived tensors of the inference fast path - bond tables, folded post / lin weights, the packed
+    tensor-core image of every GEMM call site - kept across forwards for as long as the weights do not change, so that
+    an eval forward (and a captured eval graph) launches only the kernels that depend on the batch.  Buffers are
+    allocated once and refilled IN PLACE when the weights change: captured graphs keep their addresses."""
+
+    def __init__(self, device):
+        self.device = device
+        self.token = None           # weights version the contents were computed for
+        self.pending = None
+        self.filling = True         # this forward (re)computes the contents
+        self.tensors = {}
+        self.sites = {}
+
+    def tensor(self, key, shape, dtype=torch.float32):
+        t = self.tensors.get(key)
+        if t is None:
+            if not self.filling:
+                raise RuntimeError(f"inference plan: {key} was not produced by the pass that filled the plan")
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.tensors[key] = t
+        return t
+
+    def site(self, key, nbytes):
+        """(pack workspace, signed size) of a GEMM call site: negative size = image already packed (header)."""
+        buf = self.sites.get(key)
+        if buf is None or buf.numel() < nbytes:
+            if not self.filling:
+                raise RuntimeError(f"inference plan: the packed image of {key} was not produced by the pass that "
+                                   "filled the plan")
+            buf = torch.empty((int(nbytes) + 4095) // 4096 * 4096, dtype=torch.uint8, device=self.device)
+            self.sites[key] = buf
+        return buf, (buf.numel() if self.filling else -buf.numel())
+
+
+def _pack_bound(n_rows: int, k: int) -> int:
+    """Upper bound of the packed image (tf32 hi + lo planes) of a weight operand with n_rows rows and K = k."""
+    return 8 * (n_rows + 64) * ((k + 31) // 32 * 32 + 32)
+
+
+def _site_ws(plan, key, n_rows, k, device):
+    if plan is None:
+        ws = _pack_ws(device)
+        return ws, ws.numel()
+    return plan.site(key, _pack_bound(n_rows, k))
 
 
 _INPUT_ERRORS = ((1, IndexError, "edge_index out of range [0, num_nodes)"),
@@ -390,6 +437,8 @@ class PNAPCSAFT(nn.Module):
         self._arena: Optional[torch.Tensor] = None
         self._arena_offsets: List[int] = []
         self._row_off = None
+        self._plan = None           # inference plans by kernel path
+        self._weights_epoch = 0     # bumped by everything that changes weights / BatchNorm buffers through raw pointers
         # dense stages: "tf32x3" = tcgen05 with fp32 operands split into tf32 hi+lo (fp32-level accuracy),
         # "bf16" = tcgen05 bf16 operands / fp32 accumulate (torch "medium" matmul precision, which the
         # reference itself sets at train.py:319), "simt" = plain fp32 FMA kernels
@@ -453,6 +502,22 @@ class PNAPCSAFT(nn.Module):
 
     def _offset_of(self, p: torch.Tensor) -> int:
         return (p.data_ptr() - self._arena.data_ptr()) // 4
+
+    def _infer_plan(self, device, kind: str = "layers") -> _InferPlan:
+        """The inference plan for the current weights (see _InferPlan); `filling` tells the forward whether its
+        weight-derived tensors have to be (re)computed."""
+        arena = self.arena()
+        token = (arena.data_ptr(), arena._version, self._weights_epoch, sum(p._version for p in self._param_list()),
+                 sum(b._version for b in self.buffers()), self.matmul_precision, self.training, TILE_INFER, FUSE_AGG,
+                 FOLD_DST)
+        if self._plan is None:
+            self._plan = {}
+        plan = self._plan.get(kind)             # one plan per kernel path ("layers" / "tiles"): different contents
+        if plan is None or plan.device != device:
+            plan = self._plan[kind] = _InferPlan(device)
+        plan.filling = plan.token != token
+        plan.pending = token
+        return plan
 
     def _consts(self, device):
         if self._row_off is None or self._row_off.device != device:
@@ -537,7 +602,7 @@ def _bn_forward(y, bn: nn.BatchNorm1d, training: bool, skip, relu: bool, valid=N
     return out, stats, use_batch
 
 
-def _lin_bn_eval(mm, X, lin: nn.Linear, bn: nn.BatchNorm1d, skip, relu: bool):
+def _lin_bn_eval(mm, X, lin: nn.Linear, bn: nn.BatchNorm1d, skip, relu: bool, plan=None, key=None):
     """Inference fast path: Linear -> BatchNorm(eval) -> ReLU (-> + skip) as ONE tensor-core GEMM with the running
     statistics folded into the weights (gnn_bn_fold_linear + gnn_tc_linear_skip_fwd).  Returns None when the shape
     needs the general path."""
@@ -545,14 +610,17 @@ def _lin_bn_eval(mm, X, lin: nn.Linear, bn: nn.BatchNorm1d, skip, relu: bool):
     if mm < 0 or bn.running_mean is None or (k & 3) or (nout & 3) or not _al(X, k) or rows == 0:
         return None
     dev = X.device
-    wf = torch.empty(nout, k, dtype=torch.float32, device=dev)
-    bf = torch.empty(nout, dtype=torch.float32, device=dev)
-    _c("gnn_bn_fold_linear", lin.weight, k, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-       float(bn.eps), nout, k, wf, bf)
+    if plan is not None:
+        wf, bf = plan.tensor((key, "wf"), (nout, k)), plan.tensor((key, "bf"), (nout,))
+    else:
+        wf = torch.empty(nout, k, dtype=torch.float32, device=dev)
+        bf = torch.empty(nout, dtype=torch.float32, device=dev)
+    if plan is None or plan.filling:
+        _c("gnn_bn_fold_linear", lin.weight, k, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+           float(bn.eps), nout, k, wf, bf)
     out = torch.empty(rows, nout, dtype=torch.float32, device=dev)
-    ws = _pack_ws(dev)
-    _c("gnn_tc_linear_skip_fwd", X, k, wf, k, bf, rows, nout, k, 1 if relu else 0, skip, nout, out, nout, mm, ws,
-       ws.numel())
+    ws, nb = _site_ws(plan, key, nout, k, dev)
+    _c("gnn_tc_linear_skip_fwd", X, k, wf, k, bf, rows, nout, k, 1 if relu else 0, skip, nout, out, nout, mm, ws, nb)
     return out
 
 
@@ -601,6 +669,15 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
     fold = model._fold_dst(mm)
     row_off = model._consts(dev)
     sv = _Saved() if save else None
+    # inference with a tensor-core matmul mode: weight-derived tensors and packed weight images persist in the model's
+    # inference plan and are only recomputed when the weights changed (fill)
+    use_tiles = (TILE_INFER and compact and not save and not training and fold and mm == 0 and L > 0 and H == 64
+                 and pp.post_layers == 1 and bool(getattr(graph, "tileable", False))
+                 and all(b.module.running_mean is not None for b in model.batch_norms))
+    plan = model._infer_plan(dev, "tiles" if use_tiles else "layers") if (not save and not training and mm >= 0) else None
+    fill = plan is None or plan.filling
+    if training:
+        model._weights_epoch += 1       # the BatchNorm running statistics are about to change (raw-pointer kernels)
 
     # AtomEncoder: the 9 tables are contiguous in the arena
     atom_tab = model.node_embed.atom_embedding_list[0].weight
@@ -620,23 +697,25 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         layer_stride = (model._offset_of(model.convs[1].edge_encoder.weight) -
                         model._offset_of(conv0.edge_encoder.weight)) if L > 1 else 0
         tower_stride_pre = model._offset_of(conv0.pre_nns[1][0].weight) - model._offset_of(conv0.pre_nns[0][0].weight)
-        enc = torch.empty(L, NUM_BOND_CODES, F, **f32)
-        tab = torch.empty(L, NUM_BOND_CODES, C, **f32)
-        _c("gnn_bond_table_fwd", bond_tab, conv0.edge_encoder.weight, conv0.edge_encoder.bias,
-           conv0.pre_nns[0][0].weight, tower_stride_pre, layer_stride, L, H, T, enc, tab)
+        if plan is not None:
+            enc, tab = plan.tensor("enc", (L, NUM_BOND_CODES, F)), plan.tensor("tab", (L, NUM_BOND_CODES, C))
+        else:
+            enc = torch.empty(L, NUM_BOND_CODES, F, **f32)
+            tab = torch.empty(L, NUM_BOND_CODES, C, **f32)
+        if fill:
+            _c("gnn_bond_table_fwd", bond_tab, conv0.edge_encoder.weight, conv0.edge_encoder.bias,
+               conv0.pre_nns[0][0].weight, tower_stride_pre, layer_stride, L, H, T, enc, tab)
 
     Vx_all = None
     if fold and L > 0:      # folded x columns of post_nns[t][0] for all layers (one launch)
         tsp = model._offset_of(conv0.post_nns[1][0].weight) - model._offset_of(conv0.post_nns[0][0].weight)
-        Vx_all = torch.empty(L, T, 3, Fo, F, **f32)
-        _c("gnn_pna_fold_fwd", conv0.post_nns[0][0].weight, tsp, conv0.pre_nns[0][0].weight, tower_stride_pre,
-           layer_stride, L, F, Fo, T, Vx_all)
+        Vx_all = plan.tensor("Vx", (L, T, 3, Fo, F)) if plan is not None else torch.empty(L, T, 3, Fo, F, **f32)
+        if fill:
+            _c("gnn_pna_fold_fwd", conv0.post_nns[0][0].weight, tsp, conv0.pre_nns[0][0].weight, tower_stride_pre,
+               layer_stride, L, F, Fo, T, Vx_all)
 
-    use_tiles = (TILE_INFER and compact and not save and not training and fold and mm == 0 and L > 0 and H == 64
-                 and pp.post_layers == 1 and bool(getattr(graph, "tileable", False))
-                 and all(b.module.running_mean is not None for b in model.batch_norms))
     if use_tiles:
-        x = _conv_stack_tiles(model, x, graph, tab, Vx_all, layer_stride, tower_stride_pre)
+        x = _conv_stack_tiles(model, x, graph, tab, Vx_all, layer_stride, tower_stride_pre, plan)
 
     layers = []
     for l in range(L if use_tiles else 0, L):
@@ -656,11 +735,11 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         rec.Vx = None
         if fold:
             rec.Vx = Vx_all[l]
-            ws = _pack_ws(dev)
-            _c("gnn_tc_pna_projsrc_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, ws.numel())
+            ws, nb = _site_ws(plan, ("projsrc", l), C, F, dev)
+            _c("gnn_tc_pna_projsrc_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, nb)
         elif mm_proj >= 0:
-            ws = _pack_ws(dev)
-            _c("gnn_tc_pna_proj_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, ws.numel())
+            ws, nb = _site_ws(plan, ("proj", l), 2 * C, F, dev)
+            _c("gnn_tc_pna_proj_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, nb)
         else:
             for t in range(T):
                 w = conv.pre_nns[t][0].weight
@@ -700,19 +779,20 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         rec.scal = scal
         # post_nns (virtual 13F concat) -> lin
         O = torch.empty(n, H, **f32)
+        post_rows = T * 3 * ((Fo + 63) // 64) * 64         # rows of the packed post image (towers x scaler groups x tiles)
         if fuse_agg:
-            ws = _pack_ws(dev)
+            ws, nb = _site_ws(plan, ("postf_agg", l), post_rows, 5 * F + 32, dev)
             _c("gnn_tc_pna_postf_agg_fwd", x, P, tab[l], g.rowptr, g.col_src, g.col_code, scal, rec.Vx,
                conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T,
-               1 if pp.post_layers > 1 else 0, O, A, mm, ws, ws.numel())
+               1 if pp.post_layers > 1 else 0, O, A, mm, ws, nb)
         elif fold:
-            ws = _pack_ws(dev)
+            ws, nb = _site_ws(plan, ("postf", l), post_rows, 5 * F, dev)
             _c("gnn_tc_pna_postf_fwd", x, A, scal, rec.Vx, conv.post_nns[0][0].weight, tower_stride_post,
-               conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O, mm, ws,
-               ws.numel())
+               conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O, mm, ws, nb)
         else:
             _post_fwd(mm, x, A, scal, conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias,
-               bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O)
+               bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O,
+               ws=_site_ws(plan, ("post", l), post_rows, 5 * F, dev) if mm >= 0 else None)
         os_ = [O]
         for k in range(1, pp.post_layers):
             O2 = torch.empty(n, H, **f32)
@@ -720,18 +800,18 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
             for t in range(T):
                 lin = conv.post_nns[t][2 * k]
                 _lin_fwd(mm, O[:, t * Fo:], H, lin.weight, Fo, lin.bias, n, Fo, Fo, 0 if last else 1,
-                   O2[:, t * Fo:], H)
+                   O2[:, t * Fo:], H, plan, ("postk", l, k, t))
             os_.append(O2)
             O = O2
         rec.os = os_
         fused = None
         if not training and not save:       # inference: lin + BatchNorm(running stats) + ReLU + skip in one GEMM
-            fused = _lin_bn_eval(mm, O, conv.lin, bn, rec.x_in if pp.skip_connections else None, True)
+            fused = _lin_bn_eval(mm, O, conv.lin, bn, rec.x_in if pp.skip_connections else None, True, plan, ("lin", l))
         if fused is not None:
             x = fused
         else:
             y = torch.empty(n, H, **f32)
-            _lin_fwd(mm, O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H)
+            _lin_fwd(mm, O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H, plan, ("lin_plain", l))
             rec.y = y
             x, rec.stats, rec.bn_batch = _bn_forward(y, bn, training, rec.x_in if pp.skip_connections else None, True,
                                                      valid_nodes)
@@ -744,12 +824,15 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
 
     # MLP head
     head = []
+    head_keys = []
     hcur = pooled
 
     def head_block(lin: nn.Linear, bn: Optional[nn.BatchNorm1d]):
         nonlocal hcur
+        hkey = ("head", len(head_keys))
+        head_keys.append(hkey)
         if bn is not None and not training and not save:
-            fused = _lin_bn_eval(mm, hcur, lin, bn, None, True)
+            fused = _lin_bn_eval(mm, hcur, lin, bn, None, True, plan, hkey)
             if fused is not None:
                 hcur = fused
                 return
@@ -757,7 +840,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         rec.inp, rec.lin, rec.bn = hcur, lin, bn
         z = torch.empty(hcur.shape[0], lin.out_features, **f32)
         _lin_fwd(mm, hcur, lin.in_features, lin.weight, lin.in_features, lin.bias, hcur.shape[0],
-           lin.out_features, lin.in_features, 0, z, lin.out_features)
+           lin.out_features, lin.in_features, 0, z, lin.out_features, plan, hkey)
         rec.z = z
         if bn is not None:
             hcur, rec.stats, rec.bn_batch = _bn_forward(z, bn, training, None, True, valid_graphs)
@@ -772,6 +855,8 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
     head_block(tail[4], tail[5])
     head_block(tail[8], None)
     out = hcur
+    if plan is not None and plan.filling and not (dev.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+        plan.token = plan.pending       # contents now match the weights (a capture only records the fill kernels)
 
     if save:
         sv.g, sv.layers, sv.head, sv.enc, sv.tab = g, layers, head, enc, tab
@@ -782,7 +867,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
     return out, sv
 
 
-def _conv_stack_tiles(model: PNAPCSAFT, x, g, tab, Vx_all, layer_stride, tower_stride_pre):
+def _conv_stack_tiles(model: PNAPCSAFT, x, g, tab, Vx_all, layer_stride, tower_stride_pre, plan=None):
     """All PNAConv + BatchNorm(eval) + ReLU + skip layers of a compact batch in ONE launch (gnn_tc_pna_stack_infer)."""
     pp = model.pna_params
     dev = x.device
@@ -791,25 +876,31 @@ def _conv_stack_tiles(model: PNAPCSAFT, x, g, tab, Vx_all, layer_stride, tower_s
     n = x.shape[0]
     f32 = dict(dtype=torch.float32, device=dev)
     conv0 = model.convs[0]
-    wf_all = torch.empty(L, H, H, **f32)
-    bf_all = torch.empty(L, H, **f32)
-    for l in range(L):
-        conv, bn = model.convs[l], model.batch_norms[l].module
-        _c("gnn_bn_fold_linear", conv.lin.weight, H, conv.lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-           float(bn.eps), H, H, wf_all[l], bf_all[l])
     nbytes = _lib.query("gnn_tc_infer_image_bytes", L)
-    images = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if plan is not None:
+        wf_all, bf_all = plan.tensor("tile_wf", (L, H, H)), plan.tensor("tile_bf", (L, H))
+        images = plan.tensor("tile_images", (nbytes,), torch.uint8)
+        avg = plan.tensor("tile_avg", (L,))
+    else:
+        wf_all, bf_all = torch.empty(L, H, H, **f32), torch.empty(L, H, **f32)
+        images = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        avg = torch.empty(L, **f32)
     pre0, post0 = conv0.pre_nns[0][0], conv0.post_nns[0][0]
     ts_post = model._offset_of(conv0.post_nns[1][0].weight) - model._offset_of(post0.weight)
     bs_pre = model._offset_of(conv0.pre_nns[1][0].bias) - model._offset_of(pre0.bias)
     bs_post = model._offset_of(conv0.post_nns[1][0].bias) - model._offset_of(post0.bias)
-    _c("gnn_tc_infer_pack", pre0.weight, tower_stride_pre, Vx_all, post0.weight, ts_post, layer_stride, wf_all, L, F, Fo, T,
-       images, images.numel())
+    if plan is None or plan.filling:
+        for l in range(L):
+            conv, bn = model.convs[l], model.batch_norms[l].module
+            _c("gnn_bn_fold_linear", conv.lin.weight, H, conv.lin.bias, bn.weight, bn.bias, bn.running_mean,
+               bn.running_var, float(bn.eps), H, H, wf_all[l], bf_all[l])
+        _c("gnn_tc_infer_pack", pre0.weight, tower_stride_pre, Vx_all, post0.weight, ts_post, layer_stride, wf_all, L, F,
+           Fo, T, images, images.numel())
+        torch.cat([c.aggr_module.avg_deg_log.reshape(1).to(torch.float32) for c in model.convs], out=avg)
     cap = int(g.num_graphs)
     tiles = torch.empty(2 * max(cap, 1), dtype=torch.int32, device=dev)
     ntiles = torch.empty(1, dtype=torch.int32, device=dev)
     _c("gnn_tc_infer_tiles", g.graph_ptr, g.rowptr, cap, g.valid[1:2], tiles, max(cap, 1), ntiles, g.err)
-    avg = torch.cat([c.aggr_module.avg_deg_log.reshape(1) for c in model.convs]).to(torch.float32)
     x_out = torch.zeros(n, H, **f32)        # rows outside every tile (padding nodes) stay zero
     _c("gnn_tc_pna_stack_infer", x, g.rowptr, g.col_src, g.col_code, tiles, ntiles, images, tab, pre0.bias, bs_pre,
        layer_stride, post0.bias, bs_post, layer_stride, bf_all, avg, L, F, Fo, T, 1 if pp.skip_connections else 0, x_out)

@@ -286,7 +286,10 @@ int gnn_pna_post_wgrad(const float* dO, const float* x, const float* A, const fl
  * pack_ws (optional, 128-byte aligned, may be NULL): scratch in which the weight operand is first packed
  * as the exact shared-memory tile image (swizzled, hi/lo planes) so the GEMM fetches it with TMA bulk
  * copies instead of re-converting it for every 128-row tile; 4 MiB covers every shape of the default model, the
- * wide one (hidden 256) needs 8 MiB for its post GEMM (the host passes 32 MiB).  Too small -> unpacked (slower) path. */
+ * wide one (hidden 256) needs 8 MiB for its post GEMM (the host passes 32 MiB).  Too small -> unpacked (slower) path.
+ * pack_ws_bytes < 0 (inference with constant weights): pack_ws (|pack_ws_bytes| bytes) already holds the image that an
+ * earlier call of the same entry point with the same weights and shapes packed there - the pack kernel is skipped;
+ * GNN_ERR_WORKSPACE if the image cannot have fitted. */
 int gnn_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
                       int64_t M, int N, int K, int act, float* Y, int64_t ldy, int precision,
                       void* pack_ws, int64_t pack_ws_bytes, void* stream);

@@ -222,3 +222,33 @@ def test_tile_inference_kernel_matches_per_layer_kernels():
     assert int((t[:, 1] - t[:, 0]).max()) <= 128 and int(cb.err.item()) == 0
     gp = set(cb.graph_ptr.cpu().tolist())
     assert all(int(v) in gp for v in t.reshape(-1))          # tile boundaries are graph boundaries
+
+
+def test_inference_plan_and_captured_eval_graph_follow_training():
+    """Captured eval graphs hold no weight-preparation kernels (the inference plan is refreshed eagerly): predictions
+    after training steps must be those of the trained weights, for replayed graphs too."""
+    from gnnepcsaft_b200.train.utils import create_model
+    c = cfg(propagation_depth=3)
+    packed = make_packed_graphs(900, seed=17, num_para=c.num_para)
+    deg = packed.in_degree_histogram()
+    _, _, m = make_pair(c, deg, dtype64=False)
+    m.to(DEV)
+    eng = TrainEngine.from_config(m, c, distributed=False)
+    store = CompactGraphStore(packed, device=DEV)
+    ids = torch.arange(512)
+
+    def fresh_prediction():
+        ref = create_model(c, deg)
+        ref.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+        ref.to(DEV).eval()
+        with torch.no_grad():
+            return ref(batch_from_packed(packed, ids).to(DEV))
+
+    for rnd in range(3):
+        for _ in range(3):                      # eager, capture + replay, replay
+            y = eng.predict_from_store(store, ids).clone()
+        ref = fresh_prediction()
+        assert float((y - ref).abs().max() / ref.abs().max()) < 1e-5, rnd
+        for _ in range(2):
+            eng.step_from_store(store, torch.arange(100, 612))
+    assert eng.graph_replays >= 6

@@ -126,3 +126,43 @@ def test_engine_steps_match_reference_training_loop(cpu_backend):
         torch.testing.assert_close(out, o32(batch_from_packed(packed)), rtol=1e-3, atol=1e-4)
     sd = engine.optimizer_state_dict()
     assert len(sd["state"]) == len(list(m.parameters())) and sd["param_groups"][0]["amsgrad"]
+
+
+def test_inference_plan_follows_weight_changes(cpu_backend):
+    """The eval fast path caches weight-derived tensors (bond tables, folded weights, packed images) in the model's
+    inference plan: every way the weights can change must invalidate it."""
+    from gnnepcsaft_b200.train.engine import TrainEngine
+    from gnnepcsaft_b200.train.utils import create_model
+    c = cfg(propagation_depth=2)
+    packed = make_packed_graphs(10, seed=4)
+    deg = packed.in_degree_histogram()
+    batch = batch_from_packed(packed)
+    _, _, m = make_pair(c, deg, dtype64=False)
+    engine = TrainEngine.from_config(m, c, distributed=False)
+
+    def fresh_prediction():
+        ref = create_model(c, deg)
+        ref.load_state_dict(m.state_dict())
+        ref.eval()
+        with torch.no_grad():
+            return ref(batch)
+
+    y0 = engine.predict(batch)
+    assert m._plan and all(pl.token is not None for pl in m._plan.values())
+    torch.testing.assert_close(engine.predict(batch), y0, rtol=0, atol=0)          # served from the plan
+    engine.step(batch)                                                              # raw-pointer update (AdamW, BN)
+    y1 = engine.predict(batch)
+    assert not torch.equal(y1, y0)
+    torch.testing.assert_close(y1, fresh_prediction(), rtol=1e-6, atol=1e-7)
+    with torch.no_grad():                                                           # in-place edit by the user
+        m.convs[0].lin.weight.mul_(1.5)
+    torch.testing.assert_close(engine.predict(batch), fresh_prediction(), rtol=1e-6, atol=1e-7)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}                          # load_state_dict
+    sd["mlp.0.weight"] = sd["mlp.0.weight"] * 0.5
+    m.load_state_dict(sd)
+    torch.testing.assert_close(engine.predict(batch), fresh_prediction(), rtol=1e-6, atol=1e-7)
+    m.train()                                                                       # autograd training forward: BN stats move
+    M.mape(m(batch), batch.para.view(-1, c.num_para)).backward()
+    m.eval()
+    with torch.no_grad():
+        torch.testing.assert_close(m(batch), fresh_prediction(), rtol=1e-6, atol=1e-7)
