@@ -87,19 +87,18 @@ class TrainEngine:
     def _step_compute(self, batch) -> torch.Tensor:
         """Forward, loss and backward into the flat gradient arena (everything of a step that is rank-local)."""
         net = self.net
-        net.train()
         net.arena()
         models.check_input_errors(block=False)
         compact = getattr(batch, "is_compact", False)
         valid = None
         if compact:     # store-resident compact batch (padded: graph `num_graphs` is the padding graph)
-            out, sv = _forward_impl(net, None, None, None, None, batch.b, save=True, graph=batch)
+            out, sv = _forward_impl(net, None, None, None, None, batch.b, save=True, graph=batch, training=True)
             valid = batch.valid[1:2]
         else:
             batchvec = getattr(batch, "batch", None)
             num_graphs = batch.num_graphs if batchvec is not None else 1
             out, sv = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs),
-                                    save=True)
+                                    save=True, training=True)
         target = batch.para
         if target is None:
             raise ValueError("TrainEngine.step: the batch has no `para` targets")
@@ -140,15 +139,8 @@ class TrainEngine:
     @torch.no_grad()
     def predict(self, batch) -> torch.Tensor:
         """Eval-mode forward (running BatchNorm statistics), no autograd, no collective."""
-        net = self.net
-        was_training = net.training
-        net.eval()
-        try:
-          with models._device_guard(self.grad.device):
-            out = self._predict(batch)
-        finally:
-            net.train(was_training)
-        return out
+        with models._device_guard(self.grad.device):      # the mode is passed down: no module-tree flips
+            return self._predict(batch)
 
     def _fresh_plan(self, batch):
         """Captured eval graphs contain no weight-preparation kernels: bring the model's inference plan up to date with
@@ -161,11 +153,12 @@ class TrainEngine:
     def _predict(self, batch) -> torch.Tensor:
         net = self.net
         if getattr(batch, "is_compact", False):
-            out, _ = _forward_impl(net, None, None, None, None, batch.b, save=False, graph=batch)
+            out, _ = _forward_impl(net, None, None, None, None, batch.b, save=False, graph=batch, training=False)
             return out          # [num_graphs + 1, P]: the last row is the padding graph
         batchvec = getattr(batch, "batch", None)
         num_graphs = batch.num_graphs if batchvec is not None else 1
-        out, _ = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs), save=False)
+        out, _ = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, batchvec, int(num_graphs), save=False,
+                               training=False)
         return out
 
     # ---- store-resident path: compact device collate + one captured CUDA graph per shape bucket --------------
@@ -204,7 +197,6 @@ class TrainEngine:
         as a device scalar that the NEXT step of the same bucket overwrites (read or clone it before)."""
         from ..data.compact import bucket
         with models._device_guard(self.grad.device):
-            self.net.train()
             self.net.arena()
             n, s = store.sizes(ids)
             pn, ps = bucket(n, s)
@@ -217,7 +209,6 @@ class TrainEngine:
         """The same for a compact batch assembled on the host (`store.host_batch(ids)`, pinned): one H2D copy per
         field into the bucket's static buffers, then the captured step."""
         with models._device_guard(self.grad.device):
-            self.net.train()
             self.net.arena()
             ent = self._bucket("train", store, host_batch.num_graphs, host_batch.pad_nodes, host_batch.pad_slots)
             ent["batch"].copy_from(host_batch)
@@ -229,19 +220,14 @@ class TrainEngine:
         static output, overwritten by the next call on the same bucket)."""
         from ..data.compact import bucket
         net = self.net
-        was_training = net.training
-        net.eval()
-        try:
-            with models._device_guard(self.grad.device):
-                net.arena()
-                n, s = store.sizes(ids)
-                pn, ps = bucket(n, s)
-                ent = self._bucket("eval", store, int(ids.numel()), pn, ps)
-                store.batch(ids, out=ent["batch"], ids_device=ids_device)
-                self._fresh_plan(ent["batch"])
-                out = self._run_bucket(ent, self._predict)
-        finally:
-            net.train(was_training)
+        with models._device_guard(self.grad.device):
+            net.arena()
+            n, s = store.sizes(ids)
+            pn, ps = bucket(n, s)
+            ent = self._bucket("eval", store, int(ids.numel()), pn, ps)
+            store.batch(ids, out=ent["batch"], ids_device=ids_device)
+            self._fresh_plan(ent["batch"])
+            out = self._run_bucket(ent, self._predict)
         return out[:int(ids.numel())]
 
     @torch.no_grad()
@@ -256,9 +242,7 @@ class TrainEngine:
         hi = store.num_graphs if hi is None else hi
         net = self.net
         dev = self.grad.device
-        was_training = net.training
-        net.eval()
-        try:
+        if True:
             with models._device_guard(dev):
                 net.arena()
                 # even micro-batches: k = ceil(nodes / budget) ranges of about nodes / k each, so that the last one is
@@ -284,8 +268,6 @@ class TrainEngine:
                         y = self._run_bucket(ent, self._predict)
                         if out is not False:
                             out[a - lo:b - lo].copy_(y[:b - a])
-        finally:
-            net.train(was_training)
         nodes = [int(store.node_count[a:b].sum()) for a, b in ranges]
         return (None if out is False else out), len(ranges), nodes
 

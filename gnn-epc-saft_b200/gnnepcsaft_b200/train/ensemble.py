@@ -89,9 +89,10 @@ class EnsemblePredictor:
         for net in self.nets:
             net.arena()
             if compact:
-                out, _ = _forward_impl(net, None, None, None, None, batch.b, save=False, graph=batch)
+                out, _ = _forward_impl(net, None, None, None, None, batch.b, save=False, graph=batch, training=False)
             else:
-                out, _ = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, bv, nb, save=False, graph=g)
+                out, _ = _forward_impl(net, batch.x, batch.edge_index, batch.edge_attr, bv, nb, save=False, graph=g,
+                                       training=False)
             outs.append(out)
         if not compact:
             g.defer_check()

@@ -436,8 +436,10 @@ class PNAPCSAFT(nn.Module):
             nn.Linear(hidden_dim // 4, mlp_params.num_para)))
         self._arena: Optional[torch.Tensor] = None
         self._arena_offsets: List[int] = []
+        self._arena_ends = ()
         self._row_off = None
         self._plan = None           # inference plans by kernel path
+        self._plan_tensors = None
         self._weights_epoch = 0     # bumped by everything that changes weights / BatchNorm buffers through raw pointers
         # dense stages: "tf32x3" = tcgen05 with fp32 operands split into tf32 hi+lo (fp32-level accuracy),
         # "bf16" = tcgen05 bf16 operands / fp32 accumulate (torch "medium" matmul precision, which the
@@ -463,9 +465,10 @@ class PNAPCSAFT(nn.Module):
     def _arena_valid(self) -> bool:
         if self._arena is None:
             return False
-        ps = self._param_list()
+        # the first and the last parameter still view the arena (nn.Module keeps the Parameter objects; walking the
+        # module tree for them on every call cost 0.1 ms of host time per forward)
         base = self._arena.data_ptr()
-        for p, off in ((ps[0], self._arena_offsets[0]), (ps[-1], self._arena_offsets[-1])):
+        for p, off in self._arena_ends:
             if p.data_ptr() != base + 4 * off or p.device != self._arena.device:
                 return False
         return True
@@ -492,6 +495,7 @@ class PNAPCSAFT(nn.Module):
                 view.copy_(p.data)
                 p.data = view
         self._arena, self._arena_offsets = arena, offsets
+        self._arena_ends = ((ps[0], offsets[0]), (ps[-1], offsets[-1]))
         self._row_off = None
         return arena
 
@@ -503,13 +507,16 @@ class PNAPCSAFT(nn.Module):
     def _offset_of(self, p: torch.Tensor) -> int:
         return (p.data_ptr() - self._arena.data_ptr()) // 4
 
-    def _infer_plan(self, device, kind: str = "layers") -> _InferPlan:
+    def _infer_plan(self, device, kind: str = "layers", training: Optional[bool] = None) -> _InferPlan:
         """The inference plan for the current weights (see _InferPlan); `filling` tells the forward whether its
         weight-derived tensors have to be (re)computed."""
         arena = self.arena()
-        token = (arena.data_ptr(), arena._version, self._weights_epoch, sum(p._version for p in self._param_list()),
-                 sum(b._version for b in self.buffers()), self.matmul_precision, self.training, TILE_INFER, FUSE_AGG,
-                 FOLD_DST)
+        if self._plan_tensors is None or self._plan_tensors[0] is not arena:
+            # (walking the module tree costs ~0.2 ms per call: the tensors whose versions make up the token are listed
+            # once per arena; nn.Module keeps Parameter / buffer objects across in-place updates and load_state_dict)
+            self._plan_tensors = (arena, self._param_list() + list(self.buffers()))
+        token = (arena.data_ptr(), arena._version, self._weights_epoch, sum(t._version for t in self._plan_tensors[1]),
+                 self.matmul_precision, TILE_INFER, FUSE_AGG, FOLD_DST)
         if self._plan is None:
             self._plan = {}
         plan = self._plan.get(kind)             # one plan per kernel path ("layers" / "tiles"): different contents
@@ -624,7 +631,8 @@ def _lin_bn_eval(mm, X, lin: nn.Linear, bn: nn.BatchNorm1d, skip, relu: bool, pl
     return out
 
 
-def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_graphs, save: bool, graph=None):
+def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_graphs, save: bool, graph=None,
+                  training: Optional[bool] = None):
     """The forward kernel chain.  `graph`: a prebuilt `GraphStructure`, or a compact store batch
     (`data.compact.CompactBatch`: uint8 atom features + int32 CSR straight from `gnn_compact_collate`, possibly padded
     to a shape bucket - then x_idx / edge_index / edge_attr / batch are ignored and the output has one extra row, the
@@ -646,7 +654,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         valid_nodes, valid_graphs = graph.valid[0:1], graph.valid[1:2]
     else:
         _check_inputs(x_idx, edge_index, edge_attr, batch)
-    if model.training and (pp.dropout > 0.0 or mp.dropout > 0.0):
+    if (model.training if training is None else training) and (pp.dropout > 0.0 or mp.dropout > 0.0):
         raise NotImplementedError("gnnepcsaft_b200: dropout > 0 in training mode is not implemented "
                                   "(the reference configs use dropout_rate = 0.0)")
     dev = x_idx.device
@@ -662,7 +670,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         if batch is not None:
             batch = batch.contiguous()
     n = int(graph.n) if compact else int(x_idx.shape[0])
-    training = model.training
+    training = model.training if training is None else bool(training)      # engines pass the mode: no module-tree flips
     f32 = dict(dtype=torch.float32, device=dev)
 
     g = graph if graph is not None else GraphStructure(edge_index, edge_attr, batch, n, num_graphs, pp.self_loops)
