@@ -431,10 +431,11 @@ def main():
             sys.stderr.write(f"{n:32s} {t / 2:9.3f} ms/step {c // 2:4d} calls/step {100 * t / total:5.1f}%\n")
 
     # ---------------- end to end from pinned host buffers (`e2e`)
-    # Compact batches assembled on the host in pinned memory; DevicePrefetcher copies each step's batch on a side
-    # stream while the previous step computes; the step copies it into the bucket's static buffers (device to
-    # device) and replays the captured graph; every step's loss is read back to the host (one step late, so the read
-    # does not drain the queue).  All copies and reads of the K timed steps happen inside the timed region.
+    # Compact batches assembled on the host in pinned memory; TrainEngine.steps_from_host copies each step's batch on a
+    # copy stream into preallocated staging buffers while the previous step computes; the step copies it into the
+    # bucket's static buffers (device to device) and replays the captured graph; every step's loss is read back to the
+    # host (one step late, so the read does not drain the queue).  All copies and reads of the K timed steps happen
+    # inside the timed region.
     host_compact = [store.host_batch(ids) for ids, _ in planned[:min(args.steps, 8)]]
     h2d_bytes = host_compact[0].nbytes()
     loss_slots = torch.empty(max(args.steps, 3), dtype=torch.float32, pin_memory=True)   # pinned once, outside the loop
@@ -445,8 +446,7 @@ def main():
 
     def e2e_run(count):
         out, pending = [], None
-        for k, db in enumerate(DevicePrefetcher(host_feed(count), dev, depth=2)):
-            loss_dev = engine.step_from_host(store, db)
+        for k, loss_dev in enumerate(engine.steps_from_host(store, host_feed(count), depth=2)):
             host_loss = loss_slots[k:k + 1]
             host_loss.copy_(loss_dev, non_blocking=True)                # D2H of this step's loss
             ev = torch.cuda.Event()
@@ -604,7 +604,8 @@ def main():
                                                              "every step is a different random batch"},
                 "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-                        "what": "pinned host compact batches -> H2D on a side stream -> captured step -> D2H loss"},
+                        "what": "pinned host compact batches -> H2D on a copy stream into staging buffers -> captured step "
+                                "-> D2H loss"},
                 "gpu_launches": int(launches_per_step * args.steps),
                 "graph_launches": graph_launches, "kernels_per_step": launches_per_step,
                 "roofline": roofline, "roofline_by_kernel": roofline_by_kernel, "cpu_baseline": cpu_baseline,

@@ -64,6 +64,8 @@ class TrainEngine:
         self._pool = None
         self._warm = False
         self.graph_replays = 0
+        self._copy_stream = None
+        self._staging = {}
 
     @classmethod
     def from_config(cls, model, config, **kw):
@@ -213,6 +215,58 @@ class TrainEngine:
             ent = self._bucket("train", store, host_batch.num_graphs, host_batch.pad_nodes, host_batch.pad_slots)
             ent["batch"].copy_from(host_batch)
             return self._train_bucket(ent)
+
+    @torch.no_grad()
+    def steps_from_host(self, store, host_batches, depth: int = 2):
+        """Generator: one optimisation step per pinned host compact batch (`store.host_batch(ids)`), yielding each
+        step's loss.  The H2D copies of the next `depth` batches run on a copy stream into PREALLOCATED staging buffers
+        (per shape bucket, reused round-robin behind events) while the current step computes; the step then copies its
+        batch device-to-device into the bucket's static buffers and replays the captured graph.  No per-step
+        allocation: with tensors allocated per batch on the copy stream (DevicePrefetcher) the caching allocator's
+        deferred frees degraded into cudaMalloc calls after a few dozen steps (4.8 -> 5.1-7.6 ms per step)."""
+        from collections import deque
+        dev = self.grad.device
+        with models._device_guard(dev):
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            copy_stream = self._copy_stream
+            source = iter(host_batches)
+            queue = deque()
+
+            def enqueue() -> bool:
+                hb = next(source, None)
+                if hb is None:
+                    return False
+                key = (hb.num_graphs, hb.pad_nodes, hb.pad_slots)
+                ring = self._staging.get((id(store), key))
+                if ring is None:
+                    ring = {"bufs": [store.allocate(*key) for _ in range(depth + 1)], "free": [None] * (depth + 1), "next": 0}
+                    self._staging[(id(store), key)] = ring
+                j = ring["next"]
+                ring["next"] = (j + 1) % len(ring["bufs"])
+                with torch.cuda.stream(copy_stream):
+                    if ring["free"][j] is not None:
+                        copy_stream.wait_event(ring["free"][j])     # its previous contents were consumed
+                    ring["bufs"][j].copy_from(hb)
+                    ready = torch.cuda.Event()
+                    ready.record(copy_stream)
+                queue.append((ring, j, key, ready))
+                return True
+
+            while len(queue) < depth and enqueue():
+                pass
+            while queue:
+                ring, j, key, ready = queue.popleft()
+                cur = torch.cuda.current_stream(dev)
+                cur.wait_event(ready)
+                self.net.arena()
+                ent = self._bucket("train", store, *key)
+                ent["batch"].copy_from(ring["bufs"][j])
+                free = torch.cuda.Event()
+                free.record(cur)
+                ring["free"][j] = free
+                enqueue()
+                yield self._train_bucket(ent)
 
     @torch.no_grad()
     def predict_from_store(self, store, ids: torch.Tensor, ids_device: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -252,3 +252,25 @@ def test_inference_plan_and_captured_eval_graph_follow_training():
         for _ in range(2):
             eng.step_from_store(store, torch.arange(100, 612))
     assert eng.graph_replays >= 6
+
+
+def test_steps_from_host_matches_store_steps():
+    """The pinned-host feed (staging ring on a copy stream) trains exactly like the store-resident path."""
+    c = cfg(propagation_depth=2, learning_rate=1e-5)
+    packed = make_packed_graphs(900, seed=19, num_para=c.num_para)
+    deg = packed.in_degree_histogram()
+    _, _, m1 = make_pair(c, deg, dtype64=False)
+    _, _, m2 = make_pair(c, deg, dtype64=False)
+    m1.to(DEV), m2.to(DEV)
+    e1 = TrainEngine.from_config(m1, c, distributed=False)
+    e2 = TrainEngine.from_config(m2, c, distributed=False)
+    store = CompactGraphStore(packed, device=DEV)
+    gen = torch.Generator().manual_seed(3)
+    ids_list = [torch.randperm(900, generator=gen)[:256] for _ in range(9)]
+    host = [store.host_batch(i) for i in ids_list]
+    l1 = [float(v) for v in e1.steps_from_host(store, host, depth=2)]
+    l2 = [float(e2.step_from_store(store, i)) for i in ids_list]
+    assert len(l1) == 9
+    for a, b in zip(l1, l2):
+        assert abs(a - b) <= 2e-4 * abs(b), (l1, l2)
+    assert int(e1.step_count.item()) == 9
