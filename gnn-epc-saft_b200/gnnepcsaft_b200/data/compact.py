@@ -125,8 +125,19 @@ def bucket(num_nodes: int, num_slots: int, own_surplus: bool = False, quantum_no
     return pn, ps
 
 
+_STORE_UIDS = iter(range(1, 1 << 62))
+
+
 class CompactGraphStore:
     """Device-resident dataset in compact dtypes + one destination CSR over all graphs."""
+
+    @property
+    def uid(self) -> int:
+        """Process-unique id of this store (keys of the engines' per-store shape buckets; `id()` can be reused)."""
+        u = self.__dict__.get("_uid")
+        if u is None:
+            u = self.__dict__["_uid"] = next(_STORE_UIDS)
+        return u
 
     def __init__(self, packed: PackedGraphs, device="cuda", self_loops: bool = True, keep_host_mirror: bool = True):
         dev = torch.device(device)

@@ -64,6 +64,7 @@ class TrainEngine:
         self._pool = None
         self._warm = False
         self.graph_replays = 0
+        self._arena_ptr = arena.data_ptr()
         self._copy_stream = None
         self._staging = {}
 
@@ -165,7 +166,7 @@ class TrainEngine:
 
     # ---- store-resident path: compact device collate + one captured CUDA graph per shape bucket --------------
     def _bucket(self, mode: str, store, nb: int, pn: int, ps: int):
-        key = (mode, id(store), nb, pn, ps)
+        key = (mode, store.uid, nb, pn, ps)
         ent = self._buckets.get(key)
         if ent is None:
             ent = {"batch": store.allocate(nb, pn, ps), "graph": None, "out": None}
@@ -177,6 +178,13 @@ class TrainEngine:
         kernel attributes exist), then captured once and replayed."""
         if not self.use_cuda_graphs:
             return fn(ent["batch"])
+        arena_ptr = self.net.arena().data_ptr()
+        if arena_ptr != self._arena_ptr:
+            # the parameter arena was rebuilt (model.to(...), .float(), ...): every captured graph still addresses
+            # the old one - drop them all (the static batch buffers stay valid)
+            for other in self._buckets.values():
+                other["graph"], other["out"] = None, None
+            self._arena_ptr = arena_ptr
         if ent["graph"] is None:
             if not self._warm:
                 self._warm = True
@@ -238,10 +246,10 @@ class TrainEngine:
                 if hb is None:
                     return False
                 key = (hb.num_graphs, hb.pad_nodes, hb.pad_slots)
-                ring = self._staging.get((id(store), key))
+                ring = self._staging.get((store.uid, key))
                 if ring is None:
                     ring = {"bufs": [store.allocate(*key) for _ in range(depth + 1)], "free": [None] * (depth + 1), "next": 0}
-                    self._staging[(id(store), key)] = ring
+                    self._staging[(store.uid, key)] = ring
                 j = ring["next"]
                 ring["next"] = (j + 1) % len(ring["bufs"])
                 with torch.cuda.stream(copy_stream):

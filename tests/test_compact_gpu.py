@@ -274,3 +274,36 @@ def test_steps_from_host_matches_store_steps():
     for a, b in zip(l1, l2):
         assert abs(a - b) <= 2e-4 * abs(b), (l1, l2)
     assert int(e1.step_count.item()) == 9
+
+
+def test_captured_graphs_are_dropped_when_the_arena_is_rebuilt():
+    """model.to(...) / flatten_parameters() move the parameters: graphs captured before address the old arena."""
+    from gnnepcsaft_b200.train.utils import create_model
+    c = cfg(propagation_depth=2)
+    packed = make_packed_graphs(700, seed=23, num_para=c.num_para)
+    deg = packed.in_degree_histogram()
+    _, _, m = make_pair(c, deg, dtype64=False)
+    m.to(DEV)
+    eng = TrainEngine.from_config(m, c, distributed=False)
+    store = CompactGraphStore(packed, device=DEV)
+    ids = torch.arange(512)
+    for _ in range(3):
+        eng.step_from_store(store, ids)
+        y_before = eng.predict_from_store(store, ids).clone()
+    old = m.arena().data_ptr()
+    m.flatten_parameters()                      # new arena, same values
+    assert m.arena().data_ptr() != old
+    y_after = eng.predict_from_store(store, ids).clone()
+    assert torch.equal(y_after, y_before)
+    with torch.no_grad():
+        m._arena.mul_(1.0)                      # touch: the old arena must not be what the graphs read
+    for _ in range(2):
+        eng.step_from_store(store, ids)
+    ref = create_model(c, deg)
+    ref.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    ref.to(DEV).eval()
+    with torch.no_grad():
+        want = ref(batch_from_packed(packed, ids).to(DEV))
+    got = eng.predict_from_store(store, ids)
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-5
+    assert not torch.equal(got, y_before)       # the steps after the rebuild did train the new arena

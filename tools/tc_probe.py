@@ -7,6 +7,8 @@ from gnnepcsaft_b200 import _lib
 
 dev = "cuda"
 lib = _lib.load()
+import ctypes
+lib.gnn_tc_set_profile_buffer.argtypes = [ctypes.c_void_p]
 prof = torch.zeros(16, dtype=torch.int64, device=dev)
 ws = torch.zeros(4 << 20, dtype=torch.uint8, device=dev)
 st = lambda: _lib.stream_ptr()
@@ -34,7 +36,7 @@ def report(name, fn, reps=5):
           f"start {p[12]/ct:7.0f} mma issued {p[13]/ct:8.0f} acc ready {p[14]/ct:8.0f}")
 
 
-n = 102263
+n = int(os.environ.get("TC_ROWS", "102263"))
 x = torch.randn(n, 64, device=dev)
 W = torch.randn(64, 64, device=dev) * 0.1
 b = torch.randn(64, device=dev)
