@@ -467,12 +467,27 @@ mape_kernel(const float* __restrict__ pred, const float* __restrict__ target, in
     const float inv = 1.0f / (float)(numel > 0 ? numel : 1);
     if (dpred)
         for (int64_t i = numel + threadIdx.x; i < total; i += blockDim.x) dpred[i] = 0.f;
-    for (int64_t i = threadIdx.x; i < numel; i += blockDim.x) {
-        float p = pred[i], t = target[i];
-        float den = fmaxf(fabsf(t), 1.17e-06f);
-        float d = p - t;
-        acc += (double)(fabsf(d) / den);
-        if (dpred) dpred[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / den * inv * grad_scale;
+    // four elements per trip: the eight loads are independent and in flight together (one CTA walks the whole
+    // [B, P] matrix, so the loop is latency-bound otherwise); the terms are summed in the order of the plain loop
+    for (int64_t i0 = threadIdx.x; i0 < numel; i0 += 4 * (int64_t)blockDim.x) {
+        float p[4], t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            const bool ok = i < numel;
+            p[u] = ok ? pred[i] : 0.f;
+            t[u] = ok ? target[i] : 1.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + (int64_t)u * blockDim.x;
+            if (i < numel) {
+                const float den = fmaxf(fabsf(t[u]), 1.17e-06f);
+                const float d = p[u] - t[u];
+                acc += (double)(fabsf(d) / den);
+                if (dpred) dpred[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) / den * inv * grad_scale;
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(GNN_FULL_MASK, acc, o);
@@ -493,23 +508,31 @@ extern "C" int gnn_mape_fwd_bwd(const float* pred, const float* target, int64_t 
 }
 
 // ------------------------------------------------------------------ AdamW(amsgrad) + cosine warm restarts
-__global__ void adamw_amsgrad_kernel(float* __restrict__ param, const float* __restrict__ grad,
-                                     float* __restrict__ m, float* __restrict__ v, float* __restrict__ vmax,
-                                     int64_t numel, const int64_t* __restrict__ step_count, float lr0, float beta1,
-                                     float beta2, float eps, float wd, int64_t t0, float grad_scale) {
-    // step t (0-based count of completed steps); torch's `step` state is t+1
-    const int64_t t = *step_count;
-    const double kPi = 3.14159265358979323846;
-    double lr = lr0;
-    if (t0 > 0) lr = 0.5 * (double)lr0 * (1.0 + cos(kPi * (double)(t % t0) / (double)t0));
-    const double step = (double)(t + 1);
-    const double bc1 = 1.0 - pow((double)beta1, step);
-    const double bc2 = 1.0 - pow((double)beta2, step);
-    const float step_size = (float)(lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
-    const float decay = (float)(1.0 - lr * (double)wd);
+__global__ void __launch_bounds__(256)
+adamw_amsgrad_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m,
+                     float* __restrict__ v, float* __restrict__ vmax, int64_t numel,
+                     const int64_t* __restrict__ step_count, float lr0, float beta1, float beta2, float eps, float wd,
+                     int64_t t0, float grad_scale) {
+    // The schedule / bias-correction scalars need double-precision cos / pow: one thread per CTA computes them (every
+    // thread doing so made this 2 MB kernel take 19 us).  step t = 0-based count of completed steps; torch's `step`
+    // state is t + 1.
+    __shared__ float sc[3];
+    if (threadIdx.x == 0) {
+        const int64_t t = *step_count;
+        const double kPi = 3.14159265358979323846;
+        double lr = lr0;
+        if (t0 > 0) lr = 0.5 * (double)lr0 * (1.0 + cos(kPi * (double)(t % t0) / (double)t0));
+        const double step = (double)(t + 1);
+        const double bc1 = 1.0 - pow((double)beta1, step);
+        const double bc2 = 1.0 - pow((double)beta2, step);
+        sc[0] = (float)(lr / bc1);
+        sc[1] = (float)sqrt(bc2);
+        sc[2] = (float)(1.0 - lr * (double)wd);
+    }
+    __syncthreads();
+    const float step_size = sc[0], bc2_sqrt = sc[1], decay = sc[2];
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; i < numel; i += stride) {
         float g = grad[i] * grad_scale;
         float p = param[i] * decay;
