@@ -443,10 +443,31 @@ __global__ void segment_pool_bwd_kernel(const float* __restrict__ dout, const in
         dx[i] = accumulate ? dx[i] + v : v;
     }
 }
+// float4 variant (C % 4 == 0, 16-byte aligned rows): thread = (node, column quad), 32-bit index arithmetic
+__global__ void segment_pool_bwd4_kernel(const float* __restrict__ dout, const int* __restrict__ node_graph, int n,
+                                         int C4, int accumulate, float* __restrict__ dx) {
+    const int total = n * C4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int r = i / C4, c = i - r * C4;
+        const int g = node_graph ? __ldg(node_graph + r) : 0;
+        float4 v = ldg4(dout + ((size_t)g * C4 + c) * 4);
+        float4* dst = reinterpret_cast<float4*>(dx) + i;
+        if (accumulate) {
+            const float4 o = *dst;
+            v = make_float4(v.x + o.x, v.y + o.y, v.z + o.z, v.w + o.w);
+        }
+        *dst = v;
+    }
+}
 extern "C" int gnn_segment_pool_bwd(const float* dout, const int32_t* node_graph, int64_t n, int C, int accumulate,
                                     float* dx, void* stream) {
     if (n < 0 || C < 1) return GNN_ERR_BAD_ARG;
     if (n == 0) return 0;
+    if ((C & 3) == 0 && n * (int64_t)(C >> 2) < (1ll << 31) && ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0) {
+        segment_pool_bwd4_kernel<<<ew_grid(n * (C >> 2), 256), 256, 0, gnn_stream(stream)>>>(dout, node_graph, (int)n, C >> 2,
+                                                                                           accumulate, dx);
+        return gnn_launch_status();
+    }
     segment_pool_bwd_kernel<<<ew_grid(n * C, 256), 256, 0, gnn_stream(stream)>>>(dout, node_graph, n * C, C, accumulate,
                                                                                   dx);
     return gnn_launch_status();
