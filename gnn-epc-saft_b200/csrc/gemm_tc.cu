@@ -16,6 +16,7 @@
 //           torch.set_float32_matmul_precision("medium"), train.py:319, allows).
 #include "common.cuh"
 
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_bf16.h>
 
 #include <type_traits>
@@ -72,6 +73,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// TMA tensor-map load of a 2-D box (SWIZZLE_128B), completion (bytes) signalled on an mbarrier; rows / columns
+// outside the tensor arrive as zeros
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int col, int row, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(col), "r"(row)
+        : "memory");
 }
 // 256-bit global store (STG.E.256): one full 32-byte sector per lane per instruction
 __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
@@ -1124,12 +1134,19 @@ pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t*
     produce_tile<MODE>(bl, tile, b_plane, rows, (int64_t)nt * BN + r_begin, (int64_t)kb * KB_ELEMS, K, threadIdx.x);
 }
 
-template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP, class AG = NoAgg>
+// A_TMA: the activation operand is ONE plain row-major fp32 matrix - its 128 x 32 tiles are fetched by the TMA unit
+// through a tensor map (cp.async.bulk.tensor.2d, SWIZZLE_128B, zero fill outside the matrix) straight into the `hi`
+// plane: kind::tf32 MMAs read only the top 19 bits of each word, so the raw fp32 tile IS the tf32 hi part (by
+// truncation); the producers then only compute lo = x - trunc(x) from shared memory.  No global loads, address
+// arithmetic or bounds checks in the producer warps.
+template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP, class AG = NoAgg, bool A_TMA = false>
 __global__ void __launch_bounds__(cta_threads(MN_MAJOR, !std::is_same<AG, NoAgg>::value), 1)
 gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b,
-               const AG ag) {
+               const AG ag, const __grid_constant__ CUtensorMap amap) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar[2], tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar[2], tmem_empty_bar[2], atma_bar[4];
+    static_assert(!A_TMA || (PACKED && !MN_MAJOR && !SCALED && MODE == MODE_TF32X3 && std::is_same<AG, NoAgg>::value),
+                  "tensor-map activation tiles: plain K-major TF32X3 launches with packed weights");
     __shared__ uint32_t tmem_base_s;
 
     constexpr int KB_ELEMS = tf32_like(MODE) ? 32 : 64;
@@ -1158,6 +1175,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
         for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], PROD_GROUP_THREADS);
             mbar_init(&empty_bar[s], 1);
+            if (A_TMA) mbar_init(&atma_bar[s], 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full_bar[b], 1);
@@ -1431,7 +1449,7 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                 if constexpr (AGG) {
                     if (agg_kb) agg_compute(ag, grp, m0, g.M, (int)((kbase - ag.xpad) >> 5), p, at.v);
                     else load_a_seg<MODE, SCALED>(aop, grp, m0, kbase, k_end, p, at);
-                } else if constexpr (!MN_MAJOR) {
+                } else if constexpr (!MN_MAJOR && !A_TMA) {
                     load_a_seg<MODE, SCALED>(aop, grp, m0, kbase, k_end, p, at);
                 }
                 if (GNN_PROF(g) && p == 0 && agg_kb) atomicAdd(GNN_PROF(g) + 15, (unsigned long long)(clock64() - pt0));   // gather + reduce
@@ -1455,7 +1473,25 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         mbar_expect_tx(&full_bar[s], bytes);
                         bulk_g2s(stage + PARTS * a_plane, packed_b + tile_idx * bytes, bytes, &full_bar[s]);
                     }
-                    if constexpr (AGG) {
+                    if constexpr (A_TMA) {
+                        if (p == 0) {
+                            mbar_expect_tx(&atma_bar[s], a_plane);
+                            tma_load_2d(stage, &amap, (int)kbase, (int)m0, &atma_bar[s]);
+                            mbar_arrive(&atma_bar[s]);
+                        }
+                        mbar_wait(&atma_bar[s], use & 1);                       // the raw fp32 tile (= hi plane) has landed
+                        const int c = p & 7, r0 = p >> 3;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t off = sw128_offset(r0 + 16 * i, c);
+                            const float4 x = *reinterpret_cast<const float4*>(stage + off);
+                            const float4 lo = make_float4(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u),
+                                                          x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u),
+                                                          x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u),
+                                                          x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+                            *reinterpret_cast<float4*>(stage + a_plane + off) = lo;
+                        }
+                    } else if constexpr (AGG) {
                         if (agg_kb) agg_store(ag, grp, m0, g.M, (int)((kbase - ag.xpad) >> 5), p, stage, a_plane, at.v);
                         else store_a_seg<MODE, SCALED>(stage, a_plane, p, at);
                     } else {
@@ -1541,8 +1577,41 @@ static const size_t kSmemLimit = 232448;     // 227 KB opt-in maximum per CTA
 static unsigned long long* g_prof = nullptr; // debug build only: per-role cycle counters of the next launches
 #endif
 
+// Tensor map of a plain row-major fp32 activation matrix [rows, cols] (row stride ld floats) for 32-column x 128-row
+// boxes in SWIZZLE_128B.  cuTensorMapEncodeTiled comes from the driver through cudaGetDriverEntryPoint (the library
+// links libcudart only).  Returns false when the operand does not qualify or the encoder is unavailable.
+static bool make_a_tensor_map(const SegOperand& aop, int groups, int64_t K, CUtensorMap* map) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<EncodeFn>(fn);
+        (void)cudaGetLastError();
+    }
+    if (encode == nullptr || aop.nseg != 1 || groups != 1) return false;
+    const Seg& sg = aop.seg[0];
+    if (sg.scale >= 0 || sg.start != 0 || sg.width < K || aop.rows < 1 || aop.rows >= (1ll << 31) || K >= (1ll << 31))
+        return false;
+    if ((reinterpret_cast<uintptr_t>(sg.base) & 15) != 0 || (sg.ld % 4) != 0 || sg.ld * 4 >= (1ll << 40)) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)aop.rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)sg.ld * sizeof(float)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sg.base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // BL: K-major weight functor (packed through pack_ws when possible) or, for MN_MAJOR, a SegOperand
-template <int MODE, bool MN_MAJOR = false, bool SCALED = false, class BL, class EP, class AG = NoAgg>
+// TRY_TMA: the A operand may be one plain matrix - fetch its tiles through a tensor map when it qualifies
+template <int MODE, bool MN_MAJOR = false, bool SCALED = false, bool TRY_TMA = false, class BL, class EP, class AG = NoAgg>
 static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN, int64_t K, int64_t k_chunk, int splits,
                   int groups, cudaStream_t st, void* pack_ws = nullptr, int64_t pack_ws_bytes = 0,
                   ColSum colsum = ColSum{nullptr, 0, 0, 0, 1}, AG ag = AG{}) {
@@ -1591,7 +1660,7 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
         auto kern = gemm_tc_kernel<MODE, false, true, SCALED, BL, EP>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr, NoAgg{});
+        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr, NoAgg{}, CUtensorMap{});
     } else {
         // weights (B) are packed once per call when a workspace is given and the M loop re-uses them
         const int num_kb = (int)gnn_ceil_div(K, kb_elems);
@@ -1604,17 +1673,22 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
                           (reinterpret_cast<uintptr_t>(pack_ws) & 127) == 0;
         const bool packed = fits;
         if (prepacked && !fits) return GNN_ERR_WORKSPACE;
+        CUtensorMap amap{};
+        bool a_tma = false;
+        if constexpr (TRY_TMA && MODE == MODE_TF32X3 && !SCALED && !AGG) a_tma = packed && make_a_tensor_map(aop, groups, K, &amap);
+        using KernT = void (*)(const SegOperand, const BL, const EP, const Geom, const uint8_t*, const AG, const CUtensorMap);
+        KernT kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG>;
+        if constexpr (TRY_TMA && MODE == MODE_TF32X3 && !SCALED && !AGG)
+            if (a_tma) kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG, true>;
         if (packed && prepacked) {
-            auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             kern<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g,
-                                                                        reinterpret_cast<const uint8_t*>(pack_ws), ag);
+                                                                        reinterpret_cast<const uint8_t*>(pack_ws), ag, amap);
         } else if (packed) {
             dim3 pgrid((unsigned)(num_kb * ((BN + PACK_ROWS - 1) / PACK_ROWS)), (unsigned)g.n_tiles, (unsigned)groups);
             pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
                                                                           reinterpret_cast<uint8_t*>(pack_ws));
-            auto kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG>;
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             // programmatic dependent of the pack kernel above (see pack_b_kernel)
@@ -1628,13 +1702,13 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, kern, aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws), ag);
+            e = cudaLaunchKernelEx(&cfg, kern, aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws), ag, amap);
             if (e != cudaSuccess) return (int)e;
         } else {
-            auto kern = gemm_tc_kernel<MODE, false, false, SCALED, BL, EP, AG>;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            auto kern_u = gemm_tc_kernel<MODE, false, false, SCALED, BL, EP, AG>;
+            cudaError_t e = cudaFuncSetAttribute(kern_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            kern<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g, nullptr, ag);
+            kern_u<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g, nullptr, ag, amap);
         }
     }
     return gnn_launch_status();
@@ -1697,7 +1771,7 @@ extern "C" int gnn_tc_linear_fwd(const float* X, int64_t ldx, const float* W, in
     VRowMajor bl{W, ldw, N, K, 0, is_vec(W, ldw)};
     EStore ep{Y, ldy, 0, bias, 0, act, 0, is_vec(Y, ldy) && (bias == nullptr || is_vec(bias, 0))};
     const int BN = pick_bn(N);
-    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, M, N, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
+    DISPATCH_MODE(precision, return (launch<MODE, false, false, true>(aop, bl, ep, M, N, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
                                                   pack_ws_bytes)));
 }
 
@@ -1716,7 +1790,7 @@ extern "C" int gnn_tc_linear_skip_fwd(const float* X, int64_t ldx, const float* 
     VRowMajor bl{W, ldw, N, K, 0, is_vec(W, ldw)};
     EStoreSkip ep{Y, ldy, bias, skip, ldskip, act};
     const int BN = pick_bn(N);
-    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, M, N, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
+    DISPATCH_MODE(precision, return (launch<MODE, false, false, true>(aop, bl, ep, M, N, BN, K, K, 1, 1, gnn_stream(stream), pack_ws,
                                                   pack_ws_bytes)));
 }
 
@@ -1730,7 +1804,7 @@ extern "C" int gnn_tc_linear_dgrad(const float* dY, int64_t lddy, const float* W
     VTransposed bl{W, ldw, K, N, 0};                       // row kk, k = n -> W[n, kk]
     EStore ep{dX, lddx, 0, nullptr, 0, 0, accumulate, is_vec(dX, lddx)};
     const int BN = pick_bn(K);
-    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, M, K, BN, N, N, 1, 1, gnn_stream(stream), pack_ws,
+    DISPATCH_MODE(precision, return (launch<MODE, false, false, true>(aop, bl, ep, M, K, BN, N, N, 1, 1, gnn_stream(stream), pack_ws,
                                                   pack_ws_bytes)));
 }
 
@@ -1894,7 +1968,7 @@ extern "C" int gnn_tc_pna_proj_fwd(const float* x, const float* wpre, int64_t wp
     EProjStore ep{P, bpre, bpre_tower_stride, F, towers, 2 * (int64_t)C};
     int BN = pick_bn(2 * C);
     if (BN > 128) BN = 128;
-    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, 2 * C, BN, (int64_t)F, (int64_t)F, 1, 1,
+    DISPATCH_MODE(precision, return (launch<MODE, false, false, true>(aop, bl, ep, n, 2 * C, BN, (int64_t)F, (int64_t)F, 1, 1,
                                                   gnn_stream(stream), pack_ws, pack_ws_bytes)));
 }
 // source half only, bias included: Psrc[N, C] = x Wsrc_t^T + b_t   (folded destination projection)
@@ -1912,7 +1986,7 @@ extern "C" int gnn_tc_pna_projsrc_fwd(const float* x, const float* wpre, int64_t
     EProjStore ep{Psrc, bpre, bpre_tower_stride, F, towers, (int64_t)C};
     int BN = pick_bn(C);
     if (BN > 128) BN = 128;
-    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, C, BN, (int64_t)F, (int64_t)F, 1, 1,
+    DISPATCH_MODE(precision, return (launch<MODE, false, false, true>(aop, bl, ep, n, C, BN, (int64_t)F, (int64_t)F, 1, 1,
                                                   gnn_stream(stream), pack_ws, pack_ws_bytes)));
 }
 

@@ -181,8 +181,9 @@ def test_host_fed_compact_step_and_epoch():
 
 def test_tile_inference_kernel_matches_per_layer_kernels():
     """gnn_tc_pna_stack_infer (all PNAConv layers of a <= 128-node tile in one persistent CTA) against the per-layer
-    kernels: the same TF32x3 products accumulated in the same order, so the predictions agree bit for bit; the tile
-    list covers every real node exactly once."""
+    kernels: the same TF32x3 products in the same order - the only difference is the hi / lo split of the activation
+    operand (round-to-nearest here, truncation in the per-layer GEMMs that fetch their tiles by tensor-map TMA), i.e.
+    a few 1e-7; the tile list covers every real node exactly once."""
     from gnnepcsaft_b200 import _lib
     from gnnepcsaft_b200.train import models as M
     c = cfg()
@@ -203,7 +204,9 @@ def test_tile_inference_kernel_matches_per_layer_kernels():
     finally:
         M.TILE_INFER = old
     torch.cuda.synchronize()
-    assert torch.equal(y, y_ref)
+    diff = float((y - y_ref).abs().max() / y_ref.abs().max())
+    print(f"tile kernel vs per-layer kernels: max-normalised difference {diff:.2e}")
+    assert diff <= 2e-6
     o64.eval()
     with torch.no_grad():
         y64 = o64(batch_from_packed(packed, ids))
