@@ -1142,7 +1142,8 @@ pack_b_kernel(const BL bl0, int BN, int64_t K, int n_tiles, int num_kb, uint8_t*
 template <int MODE, bool PACKED, bool MN_MAJOR, bool SCALED, class BL, class EP, class AG = NoAgg, bool A_TMA = false>
 __global__ void __launch_bounds__(cta_threads(MN_MAJOR, !std::is_same<AG, NoAgg>::value), 1)
 gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, const uint8_t* __restrict__ packed_b,
-               const AG ag, const __grid_constant__ CUtensorMap amap) {
+               const AG ag, const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap amap1,
+               const int tma_split, const int tma_gstride0, const int tma_gstride1) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar[2], tmem_empty_bar[2], atma_bar[4];
     static_assert(!A_TMA || (PACKED && !MN_MAJOR && !SCALED && MODE == MODE_TF32X3 && std::is_same<AG, NoAgg>::value),
@@ -1475,8 +1476,14 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     }
                     if constexpr (A_TMA) {
                         if (p == 0) {
+                            // operand = [segment 0 | segment 1] (two plain matrices, e.g. [x | A_t]): columns below
+                            // tma_split come from the first tensor map, the rest from the second; a group (tower)
+                            // shifts the columns of a segment by its group stride
                             mbar_expect_tx(&atma_bar[s], a_plane);
-                            tma_load_2d(stage, &amap, (int)kbase, (int)m0, &atma_bar[s]);
+                            if ((int)kbase < tma_split)
+                                tma_load_2d(stage, &amap, (int)kbase + grp * tma_gstride0, (int)m0, &atma_bar[s]);
+                            else
+                                tma_load_2d(stage, &amap1, (int)kbase - tma_split + grp * tma_gstride1, (int)m0, &atma_bar[s]);
                             mbar_arrive(&atma_bar[s]);
                         }
                         mbar_wait(&atma_bar[s], use & 1);                       // the raw fp32 tile (= hi plane) has landed
@@ -1577,10 +1584,15 @@ static const size_t kSmemLimit = 232448;     // 227 KB opt-in maximum per CTA
 static unsigned long long* g_prof = nullptr; // debug build only: per-role cycle counters of the next launches
 #endif
 
-// Tensor map of a plain row-major fp32 activation matrix [rows, cols] (row stride ld floats) for 32-column x 128-row
-// boxes in SWIZZLE_128B.  cuTensorMapEncodeTiled comes from the driver through cudaGetDriverEntryPoint (the library
-// links libcudart only).  Returns false when the operand does not qualify or the encoder is unavailable.
-static bool make_a_tensor_map(const SegOperand& aop, int groups, int64_t K, CUtensorMap* map) {
+// Tensor maps of the activation operand for 32-column x 128-row boxes in SWIZZLE_128B: one plain row-major fp32 matrix,
+// or the concatenation of two (e.g. [x | A_t] of the post GEMM; a group = tower shifts the columns of a segment).
+// cuTensorMapEncodeTiled comes from the driver through cudaGetDriverEntryPoint (the library links libcudart only).
+// Returns false when the operand does not qualify or the encoder is unavailable.
+struct ATma {
+    CUtensorMap map0, map1;
+    int split, gstride0, gstride1;
+};
+static bool make_a_tensor_maps(const SegOperand& aop, int groups, int64_t K, ATma* out) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1595,18 +1607,37 @@ static bool make_a_tensor_map(const SegOperand& aop, int groups, int64_t K, CUte
             encode = reinterpret_cast<EncodeFn>(fn);
         (void)cudaGetLastError();
     }
-    if (encode == nullptr || aop.nseg != 1 || groups != 1) return false;
-    const Seg& sg = aop.seg[0];
-    if (sg.scale >= 0 || sg.start != 0 || sg.width < K || aop.rows < 1 || aop.rows >= (1ll << 31) || K >= (1ll << 31))
+    if (encode == nullptr || aop.nseg < 1 || aop.nseg > 2 || aop.rows < 1 || aop.rows >= (1ll << 31) || K >= (1ll << 31))
         return false;
-    if ((reinterpret_cast<uintptr_t>(sg.base) & 15) != 0 || (sg.ld % 4) != 0 || sg.ld * 4 >= (1ll << 40)) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)aop.rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)sg.ld * sizeof(float)};
-    const cuuint32_t box[2] = {32u, (cuuint32_t)BM};
-    const cuuint32_t estr[2] = {1u, 1u};
-    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sg.base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    // every segment: an unscaled plain matrix whose columns start at a k-block boundary; a group shifts its columns
+    int64_t covered = 0;
+    for (int i = 0; i < aop.nseg; ++i) {
+        const Seg& sg = aop.seg[i];
+        if (sg.scale >= 0 || sg.start != covered || (sg.start % 32) != 0) return false;
+        if (i + 1 < aop.nseg && (sg.width % 32) != 0) return false;
+        if ((reinterpret_cast<uintptr_t>(sg.base) & 15) != 0 || (sg.ld % 4) != 0 || sg.ld * 4 >= (1ll << 40)) return false;
+        if (groups > 1 && sg.group_stride != 0 && (sg.group_stride % 4) != 0) return false;
+        if (sg.group_stride >= (1ll << 30)) return false;
+        covered += sg.width;
+    }
+    if (covered < K) return false;
+    for (int i = 0; i < aop.nseg; ++i) {
+        const Seg& sg = aop.seg[i];
+        // columns of the underlying matrix that any group may address through this segment
+        const int64_t cols = sg.width + (int64_t)(groups - 1) * sg.group_stride;
+        const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)aop.rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)sg.ld * sizeof(float)};
+        const cuuint32_t box[2] = {32u, (cuuint32_t)BM};
+        const cuuint32_t estr[2] = {1u, 1u};
+        if (encode(i == 0 ? &out->map0 : &out->map1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sg.base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    out->split = aop.nseg > 1 ? aop.seg[1].start : (int)(1 << 30);
+    out->gstride0 = (int)aop.seg[0].group_stride;
+    out->gstride1 = aop.nseg > 1 ? (int)aop.seg[1].group_stride : 0;
+    return true;
 }
 
 // BL: K-major weight functor (packed through pack_ws when possible) or, for MN_MAJOR, a SegOperand
@@ -1660,7 +1691,8 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
         auto kern = gemm_tc_kernel<MODE, false, true, SCALED, BL, EP>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr, NoAgg{}, CUtensorMap{});
+        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr, NoAgg{}, CUtensorMap{}, CUtensorMap{}, 0,
+                                                              0, 0);
     } else {
         // weights (B) are packed once per call when a workspace is given and the M loop re-uses them
         const int num_kb = (int)gnn_ceil_div(K, kb_elems);
@@ -1673,10 +1705,11 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
                           (reinterpret_cast<uintptr_t>(pack_ws) & 127) == 0;
         const bool packed = fits;
         if (prepacked && !fits) return GNN_ERR_WORKSPACE;
-        CUtensorMap amap{};
+        ATma tm{};
         bool a_tma = false;
-        if constexpr (TRY_TMA && MODE == MODE_TF32X3 && !SCALED && !AGG) a_tma = packed && make_a_tensor_map(aop, groups, K, &amap);
-        using KernT = void (*)(const SegOperand, const BL, const EP, const Geom, const uint8_t*, const AG, const CUtensorMap);
+        if constexpr (TRY_TMA && MODE == MODE_TF32X3 && !SCALED && !AGG) a_tma = packed && make_a_tensor_maps(aop, groups, K, &tm);
+        using KernT = void (*)(const SegOperand, const BL, const EP, const Geom, const uint8_t*, const AG, const CUtensorMap,
+                               const CUtensorMap, const int, const int, const int);
         KernT kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG>;
         if constexpr (TRY_TMA && MODE == MODE_TF32X3 && !SCALED && !AGG)
             if (a_tma) kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG, true>;
@@ -1684,7 +1717,8 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             kern<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g,
-                                                                        reinterpret_cast<const uint8_t*>(pack_ws), ag, amap);
+                                                                        reinterpret_cast<const uint8_t*>(pack_ws), ag, tm.map0,
+                                                                        tm.map1, tm.split, tm.gstride0, tm.gstride1);
         } else if (packed) {
             dim3 pgrid((unsigned)(num_kb * ((BN + PACK_ROWS - 1) / PACK_ROWS)), (unsigned)g.n_tiles, (unsigned)groups);
             pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
@@ -1702,13 +1736,14 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            e = cudaLaunchKernelEx(&cfg, kern, aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws), ag, amap);
+            e = cudaLaunchKernelEx(&cfg, kern, aop, bl, ep, g, reinterpret_cast<const uint8_t*>(pack_ws), ag, tm.map0, tm.map1,
+                                   tm.split, tm.gstride0, tm.gstride1);
             if (e != cudaSuccess) return (int)e;
         } else {
             auto kern_u = gemm_tc_kernel<MODE, false, false, SCALED, BL, EP, AG>;
             cudaError_t e = cudaFuncSetAttribute(kern_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
-            kern_u<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g, nullptr, ag, amap);
+            kern_u<<<(unsigned)grid, cta_threads(false, AGG), smem, st>>>(aop, bl, ep, g, nullptr, ag, tm.map0, tm.map1, 0, 0, 0);
         }
     }
     return gnn_launch_status();
@@ -1862,7 +1897,7 @@ static int post_fwd_impl(const float* x, const float* A, const float* scal, cons
     VPostWeight bl{wpost, wpost_tower_stride, F, F_out, FoP, vx, 0};
     EPostCombine ep{O, scal, bpost, bpost_tower_stride, F_out, FoP, towers, 0, act,
                     (F_out % 4 == 0) && is_vec(O, 0) && is_vec(bpost, bpost_tower_stride)};
-    DISPATCH_MODE(precision, return (launch<MODE>(aop, bl, ep, n, tiles * 3 * FoP, 3 * FoP, 5 * (int64_t)F,
+    DISPATCH_MODE(precision, return (launch<MODE, false, false, true>(aop, bl, ep, n, tiles * 3 * FoP, 3 * FoP, 5 * (int64_t)F,
                                                   5 * (int64_t)F, 1, towers, gnn_stream(stream), pack_ws, pack_ws_bytes)));
 }
 
