@@ -940,12 +940,13 @@ __device__ __forceinline__ MnPlan mn_plan(const SegOperand& op, int grp, int R, 
 }
 // wait_stage() is called once all loads are in flight and before the first shared-memory store (the ring stage may
 // still be read by the MMAs of the previous use until then).
-template <int MODE, bool SCALED, int NA, int NB, class WaitFn>
+template <int MODE, bool SCALED, int NA, int NB_, class WaitFn, bool DO_B = true>
 __device__ __forceinline__ void produce_mn_pair_tf32(const MnPlan& pa, const MnPlan& pb, uint8_t* a_tile, uint32_t a_plane,
                                                      uint8_t* b_tile, uint32_t b_plane, int64_t kbase, int64_t lim,
                                                      float4* colacc, WaitFn&& wait_stage) {
+    constexpr int NB = DO_B ? NB_ : 0;             // DO_B = false: the B operand arrives by TMA
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 va[NA], vb[NB];
+    float4 va[NA], vb[NB > 0 ? NB : 1];
     float f[NA];
     const float* qa = pa.q != nullptr ? pa.q + kbase * pa.row_ld : nullptr;
     const float* qb = pb.q != nullptr ? pb.q + kbase * pb.row_ld : nullptr;
@@ -1146,8 +1147,12 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                const int tma_split, const int tma_gstride0, const int tma_gstride1) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tmem_full_bar[2], tmem_empty_bar[2], atma_bar[4];
-    static_assert(!A_TMA || (PACKED && !MN_MAJOR && !SCALED && MODE == MODE_TF32X3 && std::is_same<AG, NoAgg>::value),
-                  "tensor-map activation tiles: plain K-major TF32X3 launches with packed weights");
+    // MN-major (weight-gradient) launches: A_TMA means the B operand (a plain matrix: the aggregates A_t or x) arrives
+    // through the tensor map, as 32-column x KBR-row boxes in SWIZZLE_128B_ATOM_32B - the MN-major tf32 layout; the A
+    // operand (degree-scaled gradients) is still produced by the warps.
+    static_assert(!A_TMA || (MODE == MODE_TF32X3 && std::is_same<AG, NoAgg>::value &&
+                             ((PACKED && !MN_MAJOR && !SCALED) || (MN_MAJOR && !PACKED))),
+                  "tensor-map operand tiles: TF32X3 launches, plain K-major activations or plain MN-major B operands");
     __shared__ uint32_t tmem_base_s;
 
     constexpr int KB_ELEMS = tf32_like(MODE) ? 32 : 64;
@@ -1344,10 +1349,17 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                         const uint32_t b_kgs = ((uint32_t)BN * (tf32_like(MODE) ? 4 : 2) / 128) * ATOM;
                         dah0 = smem_desc_sw128_mn(a_hi, ATOM, a_kgs, LT);
                         dal0 = smem_desc_sw128_mn(a_lo, ATOM, a_kgs, LT);
-                        dbh0 = smem_desc_sw128_mn(b_hi, ATOM, b_kgs, LT);
-                        dbl0 = smem_desc_sw128_mn(b_lo, ATOM, b_kgs, LT);
+                        if constexpr (A_TMA) {
+                            // TMA boxes: [MN group][K row][128 B] - MN groups KBR rows apart, K groups of 4 rows adjacent
+                            dbh0 = smem_desc_sw128_mn(b_hi, (uint32_t)KBR * 128u, ATOM, LT);
+                            dbl0 = smem_desc_sw128_mn(b_lo, (uint32_t)KBR * 128u, ATOM, LT);
+                            bstep = (2 * ATOM) >> 4;
+                        } else {
+                            dbh0 = smem_desc_sw128_mn(b_hi, ATOM, b_kgs, LT);
+                            dbl0 = smem_desc_sw128_mn(b_lo, ATOM, b_kgs, LT);
+                            bstep = (2 * b_kgs) >> 4;
+                        }
                         astep = (2 * a_kgs) >> 4;
-                        bstep = (2 * b_kgs) >> 4;
                     } else {
                         dah0 = smem_desc_sw128(a_hi);
                         dal0 = smem_desc_sw128(a_lo);
@@ -1509,7 +1521,31 @@ gemm_tc_kernel(const SegOperand aop, const BL bl0, const EP ep0, const Geom g, c
                     const int64_t lim = k_end < aop.rows ? k_end : aop.rows;
                     uint8_t* bt = stage + PARTS * a_plane;
                     float4* ca = do_colsum ? colacc : nullptr;
-                    if (BN == 256) produce_mn_pair_tf32<MODE, SCALED, 4, 8>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
+                    if constexpr (A_TMA) {
+                        // B by TMA: one 32-column x KBR-row box per MN group, issued as soon as the stage is free
+                        // (while this group converts and stores its A rows); then lo = x - trunc(x) over the tile
+                        auto wait_and_issue = [&]() {
+                            wait_stage();
+                            if (p == 0) {
+                                mbar_expect_tx(&atma_bar[s], b_plane);
+                                for (int mg = 0; mg < BN / 32; ++mg)
+                                    tma_load_2d(bt + (uint32_t)mg * (uint32_t)KBR * 128u, &amap,
+                                                n0 + mg * 32 + grp * tma_gstride0, (int)kbase, &atma_bar[s]);
+                                mbar_arrive(&atma_bar[s]);
+                            }
+                        };
+                        if (BN >= 128) produce_mn_pair_tf32<MODE, SCALED, 4, 1, decltype(wait_and_issue)&, false>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_and_issue);
+                        else produce_mn_pair_tf32<MODE, SCALED, 8, 1, decltype(wait_and_issue)&, false>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_and_issue);
+                        mbar_wait(&atma_bar[s], use & 1);
+                        for (uint32_t off = (uint32_t)p * 16u; off < b_plane; off += PROD_GROUP_THREADS * 16u) {
+                            const float4 x = *reinterpret_cast<const float4*>(bt + off);
+                            *reinterpret_cast<float4*>(bt + b_plane + off) =
+                                make_float4(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u),
+                                            x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u),
+                                            x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u),
+                                            x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+                        }
+                    } else if (BN == 256) produce_mn_pair_tf32<MODE, SCALED, 4, 8>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
                     else if (BN == 128) produce_mn_pair_tf32<MODE, SCALED, 4, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
                     else if (BN == 64) produce_mn_pair_tf32<MODE, SCALED, 8, 4>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
                     else produce_mn_pair_tf32<MODE, SCALED, 8, 2>(pa, pb, stage, a_plane, bt, b_plane, kbase, lim, ca, wait_stage);
@@ -1592,7 +1628,8 @@ struct ATma {
     CUtensorMap map0, map1;
     int split, gstride0, gstride1;
 };
-static bool make_a_tensor_maps(const SegOperand& aop, int groups, int64_t K, ATma* out) {
+static bool make_a_tensor_maps(const SegOperand& aop, int groups, int64_t K, ATma* out, int box_rows = BM,
+                               bool atom32 = false) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1627,10 +1664,11 @@ static bool make_a_tensor_maps(const SegOperand& aop, int groups, int64_t K, ATm
         const int64_t cols = sg.width + (int64_t)(groups - 1) * sg.group_stride;
         const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)aop.rows};
         const cuuint64_t strides[1] = {(cuuint64_t)sg.ld * sizeof(float)};
-        const cuuint32_t box[2] = {32u, (cuuint32_t)BM};
+        const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
         const cuuint32_t estr[2] = {1u, 1u};
         if (encode(i == 0 ? &out->map0 : &out->map1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sg.base), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return false;
     }
@@ -1688,11 +1726,20 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
     if constexpr (MN_MAJOR) {
         if ((BN & (BN - 1)) != 0 || BN < (MODE == MODE_TF32X3 ? 32 : 64)) return GNN_ERR_UNSUPPORTED;   // whole 128-byte groups
         if constexpr (AGG) return GNN_ERR_UNSUPPORTED;
-        auto kern = gemm_tc_kernel<MODE, false, true, SCALED, BL, EP>;
+        using KernT = void (*)(const SegOperand, const BL, const EP, const Geom, const uint8_t*, const NoAgg, const CUtensorMap,
+                               const CUtensorMap, const int, const int, const int);
+        KernT kern = gemm_tc_kernel<MODE, false, true, SCALED, BL, EP>;
+        ATma tm{};
+        if constexpr (TRY_TMA && MODE == MODE_TF32X3 && std::is_same<BL, SegOperand>::value) {
+            // B operand (a plain matrix, the MN dimension tiled by BN columns) through a tensor map
+            if (stages >= 3 && N % 32 == 0 && BN % 32 == 0 && make_a_tensor_maps(bl, groups, N, &tm, kb_rows, true) &&
+                bl.nseg == 1)
+                kern = gemm_tc_kernel<MODE, false, true, SCALED, BL, EP, NoAgg, true>;
+        }
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr, NoAgg{}, CUtensorMap{}, CUtensorMap{}, 0,
-                                                              0, 0);
+        kern<<<(unsigned)grid, cta_threads(true), smem, st>>>(aop, bl, ep, g, nullptr, NoAgg{}, tm.map0, tm.map1, 0, tm.gstride0,
+                                                              0);
     } else {
         // weights (B) are packed once per call when a workspace is given and the M loop re-uses them
         const int num_kb = (int)gnn_ceil_div(K, kb_elems);
@@ -1861,7 +1908,7 @@ extern "C" int gnn_tc_linear_wgrad(const float* dY, int64_t lddy, const float* X
         const int BN = pick_bn_mn(K, MODE);
         const int64_t tiles = gnn_ceil_div(N, BM) * gnn_ceil_div(K, BN);
         splitk(M, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
-        return (launch<MODE, true>(aop, bop, ep, N, K, BN, M, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
+        return (launch<MODE, true, false, true>(aop, bop, ep, N, K, BN, M, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
                                    ColSum{db, 0, 0, db ? N : 0, N}));
     });
 }
@@ -2094,7 +2141,7 @@ extern "C" int gnn_tc_pna_proj_wgrad(const float* dP, const float* x, int64_t n,
         const int BN = pick_bn_mn(F, MODE);
         const int64_t tiles = gnn_ceil_div(2 * C, BM) * gnn_ceil_div(F, BN);
         splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
-        return (launch<MODE, true>(aop, bop, ep, 2 * C, F, BN, n, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
+        return (launch<MODE, true, false, true>(aop, bop, ep, 2 * C, F, BN, n, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
                                    ColSum{dbpre, 0, bpre_tower_stride, dbpre ? C : 0, F}));
     });
 }
@@ -2117,7 +2164,7 @@ extern "C" int gnn_tc_pna_projsrc_wgrad(const float* dPsrc, const float* x, int6
         const int BN = pick_bn_mn(F, MODE);
         const int64_t tiles = gnn_ceil_div(C, BM) * gnn_ceil_div(F, BN);
         splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
-        return (launch<MODE, true>(aop, bop, ep, C, F, BN, n, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
+        return (launch<MODE, true, false, true>(aop, bop, ep, C, F, BN, n, k_chunk, splits, 1, gnn_stream(stream), nullptr, 0,
                                    ColSum{dbpre, 0, bpre_tower_stride, dbpre ? C : 0, F}));
     });
 }
@@ -2147,7 +2194,7 @@ static int post_wgrad_impl(const float* dO, const float* x, const float* A, cons
             const int BN = pick_bn_mn(4 * F, MODE);
             const int64_t tiles = gnn_ceil_div(4 * F, BN) * gnn_ceil_div(3 * FoP, BM) * towers;
             splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
-            rc = (launch<MODE, true, true>(aop, bop, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st, nullptr, 0,
+            rc = (launch<MODE, true, true, true>(aop, bop, ep, 3 * FoP, 4 * F, BN, n, k_chunk, splits, towers, st, nullptr, 0,
                                      ColSum{dbpost, bpost_tower_stride, 0, dbpost ? F_out : 0, F_out}));
         });
         if (rc) return rc;
@@ -2163,7 +2210,7 @@ static int post_wgrad_impl(const float* dO, const float* x, const float* A, cons
             const int BN = pick_bn_mn(F, MODE);
             const int64_t tiles = gnn_ceil_div(F, BN) * gnn_ceil_div(3 * F_out, BM) * towers;
             splitk(n, tiles, tf32_like(MODE) ? 32 : 64, k_chunk, splits);
-            rc = (launch<MODE, true, true>(aop, bop, ep, 3 * F_out, F, BN, n, k_chunk, splits, towers, st));
+            rc = (launch<MODE, true, true, true>(aop, bop, ep, 3 * F_out, F, BN, n, k_chunk, splits, towers, st));
         });
         return rc;
     }
