@@ -147,6 +147,24 @@ def test_atom_embed_fwd_bwd():
     close(gpu[-1], cpu[-1], 1e-5, "atom table gradient")
 
 
+@pytest.mark.parametrize("H", [32, 64, 128, 256, 48])
+@pytest.mark.parametrize("graphs", [3, 700])
+def test_atom_embed_bwd_private_copies(H, graphs):
+    """H = 64 accumulates the table gradient in private shared-memory copies fed by a cp.async ring, the other widths
+    take the atomic kernel: int64 and uint8 features, few and many nodes (every CTA, every ring slot and partial
+    trips in use), accumulation onto a non-zero gradient."""
+    packed = make_packed_graphs(graphs, seed=5)
+    x = packed.x
+    n, rows = x.shape[0], 174
+    off = torch.tensor([0, 119, 124, 136, 148, 158, 164, 170, 172], dtype=torch.int32)
+    dout = torch.randn(n, H)
+    dt = torch.randn(rows, H)
+    cpu, gpu = run_both("gnn_atom_embed_bwd", x, n, dout, off, rows, H, dt)
+    close(gpu[-1], cpu[-1], 2e-5, "atom table gradient (int64 features)")
+    cpu8, gpu8 = run_both("gnn_atom_embed_u8_bwd", x.to(torch.uint8), n, dout, off, rows, H, dt)
+    close(gpu8[-1], cpu[-1], 2e-5, "atom table gradient (uint8 features)")
+
+
 @pytest.mark.parametrize("H,L", [(64, 3), (16, 1)])
 def test_bond_table_fwd_bwd(H, L):
     F, T = H, 2
