@@ -715,112 +715,6 @@ def test_aggregate_src_fwd_bwd(n, e, T, F, quant):
 
 
 @pytest.mark.parametrize("precision", [0, 2])
-@pytest.mark.parametrize("n,F", [(1000, 64), (70, 16), (3, 8), (300, 128)])
-def test_tc_fused_projection_stage(precision, n, F):
-    """proj_fwd / dx_dgrad / proj_wgrad: the four projection Linears (and the x part of the post stage) in one GEMM each."""
-    tol = TC_TOL[precision]
-    T, Fo, C = 2, F // 2, 2 * F
-    g = torch.Generator().manual_seed(n + F)
-    x = torch.randn(n, F, generator=g)
-    pre_ts = F * 3 * F + F + 4            # [weight F x 3F | bias F | pad] per tower
-    pre = torch.randn(T * pre_ts, generator=g) * 0.1
-    post_ts = Fo * 13 * F + Fo + 4
-    post = torch.randn(T * post_ts, generator=g) * 0.1
-    ws = lambda dev: torch.zeros(4 << 20, dtype=torch.uint8, device=dev)
-    res = []
-    for dev in ("cpu", DEV):
-        b = pre.to(dev)
-        args = [x.to(dev), b, pre_ts, b[F * 3 * F:], pre_ts, n, F, T, torch.zeros(n, 2 * C, device=dev), precision, ws(dev), 4 << 20]
-        R.gnn_tc_pna_proj_fwd(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_proj_fwd", *args, _lib.stream_ptr())
-        res.append(args[8])
-    close(res[1], res[0], tol, "proj fwd")
-    dP, dO = torch.randn(n, 2 * C, generator=g), torch.randn(n, T * Fo, generator=g)
-    for acc in (0, 1):
-        res = []
-        for dev in ("cpu", DEV):
-            dx = torch.ones(n, F, device=dev) * 0.5
-            args = [dP.to(dev), dO.to(dev), pre.to(dev), pre_ts, post.to(dev), post_ts, n, F, Fo, T, acc, dx, precision,
-                    ws(dev), 4 << 20]
-            R.gnn_tc_pna_dx_dgrad(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_dx_dgrad", *args, _lib.stream_ptr())
-            res.append(dx)
-        close(res[1], res[0], tol, "fused dx dgrad")
-    res = []
-    for dev in ("cpu", DEV):
-        gb = torch.zeros(T * pre_ts, device=dev)
-        args = [dP.to(dev), x.to(dev), n, F, T, gb, pre_ts, gb[F * 3 * F:], pre_ts, precision]
-        R.gnn_tc_pna_proj_wgrad(*args) if dev == "cpu" else _lib.call("gnn_tc_pna_proj_wgrad", *args, _lib.stream_ptr())
-        res.append(gb)
-    close(res[1], res[0], 2 * tol, "proj wgrad")
-
-
-# ------------------------------------------------------------------ folded destination projection
-@pytest.mark.parametrize("F,L", [(64, 3), (16, 1), (8, 2), (128, 2), (40, 1)])
-def test_fold_fwd_bwd(F, L):
-    T, Fo = 2, F // 2
-    g = torch.Generator().manual_seed(F)
-    pre_ts = F * 3 * F + F + 4
-    post_ts = Fo * 13 * F + Fo + 4
-    ls = T * (pre_ts + post_ts) + 8                 # layer l: [pre towers | post towers | pad]
-    buf = torch.randn(L * ls, generator=g) * 0.1
-    post = buf[T * pre_ts:]
-    cpu, gpu = run_both("gnn_pna_fold_fwd", post, post_ts, buf, pre_ts, ls, L, F, Fo, T, torch.zeros(L, T, 3, Fo, F))
-    close(gpu[-1], cpu[-1], 1e-5, "Vx")
-    dVx = torch.randn(L, T, 3, Fo, F, generator=g)
-    res = []
-    for dev in ("cpu", DEV):
-        gb, wb = torch.randn(L * ls, generator=torch.Generator().manual_seed(1)).to(dev), buf.to(dev)   # += semantics
-        args = [dVx.to(dev), wb[T * pre_ts:], post_ts, wb, pre_ts, ls, L, F, Fo, T, gb[T * pre_ts:], gb]
-        R.gnn_pna_fold_bwd(*args) if dev == "cpu" else _lib.call("gnn_pna_fold_bwd", *args, _lib.stream_ptr())
-        res.append(gb)
-    close(res[1], res[0], 1e-5, "dwpost / dwpre")
-
-
-@pytest.mark.parametrize("n,e,T,F,quant", [(64, 150, 2, 64, False), (33, 40, 2, 16, True), (20, 300, 2, 256, False),
-                                           (200, 500, 2, 40, False), (64, 150, 2, 64, True)])
-def test_aggregate_src_fwd_bwd(n, e, T, F, quant):
-    ref, ep, P, tab = _agg_inputs(n, e, T, F, seed=n + F, loops=True, quantise=quant)
-    C = T * F
-    Ps = P[:, C:].contiguous()
-    A = torch.zeros(n, T * 4 * F)
-    cpu, gpu = run_both("gnn_pna_aggregate_src_fwd", Ps, tab, ref["rowptr"], ref["col_src"], ref["col_code"], n, T, F, A)
-    A_cpu, A_gpu = cpu[-1], gpu[-1].cpu()
-    a4c, a4g = A_cpu.view(n, T, 4, F), A_gpu.view(n, T, 4, F)
-    close(a4g[:, :, :3], a4c[:, :, :3], 1e-5, "mean/min/max of q")
-    sd_c, sd_g = a4c[:, :, 3], a4g[:, :, 3]
-    near = (sd_c.double() ** 2 - 1e-5).abs() < 2e-6
-    bad = ((sd_g - sd_c).abs() > 1e-5 * max(float(sd_c.abs().max()), 1.0)) & ~near & ~((sd_c == 0) & (sd_g ** 2 < 1.2e-5))
-    assert not bad.any()
-    # the unfolded kernel on [Pdst | Psrc] must give the same aggregates shifted by Pdst (std unchanged)
-    A_full = torch.zeros(n, T * 4 * F, device=DEV)
-    _lib.call("gnn_pna_aggregate_fwd", P.to(DEV), tab.to(DEV), ref["rowptr"].to(DEV), ref["col_src"].to(DEV),
-              ref["col_code"].to(DEV), n, T, F, A_full, _lib.stream_ptr())
-    af = A_full.cpu().view(n, T, 4, F)
-    pd = P[:, :C].view(n, T, 1, F)
-    close(af[:, :, :3], a4g[:, :, :3] + pd, 1e-5, "unfolded == folded + Pdst")
-    assert torch.equal(af[:, :, 3], a4g[:, :, 3])
-
-    gA = torch.randn(n, T * 4 * F)
-    nb = _lib.query("gnn_pna_aggregate_bwd_workspace_bytes", T, F)
-    zws = torch.zeros(nb, dtype=torch.uint8)
-    dPs, dq, dtab = torch.zeros(n, C), torch.zeros(max(ep, 1), C), torch.zeros(60, C)
-    cpu, gpu = run_both("gnn_pna_aggregate_src_bwd", gA, Ps, tab, A_gpu, ref["rowptr"], ref["col_src"],
-                        ref["col_code"], n, T, F, dPs, dq, dtab, zws, nb)
-    close(gpu[-4][:ep], cpu[-4][:ep], 2e-5, "dq")
-    close(gpu[-3], cpu[-3], 1e-4, "dtab")
-    assert int(gpu[-2].count_nonzero()) == 0
-    dq_gpu = gpu[-4].cpu()
-    cpu, gpu = run_both("gnn_slot_sum_by_source", dq_gpu, ref["srcptr"], ref["src_slot"], n, C, torch.zeros(n, C), C)
-    close(gpu[-2], cpu[-2], 1e-5, "dPsrc")
-    two_pass = gpu[-2].cpu()
-    dPs3, dtab3 = torch.full((n, C), 7.0), torch.zeros(60, C)
-    cpu, gpu = run_both("gnn_pna_aggregate_src_bwd", gA, Ps, tab, A_gpu, ref["rowptr"], ref["col_src"],
-                        ref["col_code"], n, T, F, dPs3, None, dtab3, zws, nb)
-    close(gpu[-5], cpu[-5], 2e-5, "dPsrc (atomic variant)")
-    close(gpu[-5], two_pass, 2e-5, "dPsrc atomic vs two-pass")
-    close(gpu[-3], cpu[-3], 1e-4, "dtab (atomic variant)")
-
-
-@pytest.mark.parametrize("precision", [0, 2])
 @pytest.mark.parametrize("n,F", [(1000, 64), (70, 16), (3, 8), (300, 128), (257, 256), (90, 40)])
 def test_tc_folded_stage(precision, n, F):
     """projsrc_fwd / postf_fwd / postf_wgrad / dxf_dgrad / projsrc_wgrad against their CPU restatements."""
