@@ -1685,7 +1685,10 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
                   int groups, cudaStream_t st, void* pack_ws = nullptr, int64_t pack_ws_bytes = 0,
                   ColSum colsum = ColSum{nullptr, 0, 0, 0, 1}, AG ag = AG{}) {
     constexpr bool AGG = !std::is_same<AG, NoAgg>::value;
-    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    // M == 0 with a pack workspace: only the weight image is packed (a later call passes the same workspace with a
+    // negative size); the host uses it to take the pack kernels off the critical path of a captured training step
+    const bool pack_only = M == 0 && !MN_MAJOR && pack_ws != nullptr && pack_ws_bytes > 0;
+    if ((M <= 0 && !pack_only) || N <= 0 || K <= 0) return 0;
     if (BN % 16 != 0 || BN < 16 || BN > 256) return GNN_ERR_UNSUPPORTED;
     constexpr int parts = tf32_like(MODE) ? 2 : 1;
     constexpr int kb_elems = tf32_like(MODE) ? 32 : 64;
@@ -1751,13 +1754,13 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
         const bool fits = pack_ws != nullptr && splits == 1 && pack_bytes <= pack_ws_bytes &&
                           (reinterpret_cast<uintptr_t>(pack_ws) & 127) == 0;
         const bool packed = fits;
-        if (prepacked && !fits) return GNN_ERR_WORKSPACE;
+        if ((prepacked || pack_only) && !fits) return GNN_ERR_WORKSPACE;
         ATma tm{};
         bool a_tma = false;
         // (with only two ring stages - the wide model's tiles - the exposed TMA latency costs more than the producers
         // save: measured 12.4 vs 11.8 ms per wide training step)
         if constexpr (TRY_TMA && MODE == MODE_TF32X3 && !SCALED && !AGG)
-            a_tma = packed && stages >= 3 && make_a_tensor_maps(aop, groups, K, &tm);
+            a_tma = packed && !pack_only && stages >= 3 && make_a_tensor_maps(aop, groups, K, &tm);
         using KernT = void (*)(const SegOperand, const BL, const EP, const Geom, const uint8_t*, const AG, const CUtensorMap,
                                const CUtensorMap, const int, const int, const int);
         KernT kern = gemm_tc_kernel<MODE, true, false, SCALED, BL, EP, AG>;
@@ -1773,6 +1776,7 @@ static int launch(const SegOperand& aop, BL bl, EP ep, int64_t M, int N, int BN,
             dim3 pgrid((unsigned)(num_kb * ((BN + PACK_ROWS - 1) / PACK_ROWS)), (unsigned)g.n_tiles, (unsigned)groups);
             pack_b_kernel<MODE, BL><<<pgrid, PROD_GROUP_THREADS, 0, st>>>(bl, BN, K, g.n_tiles, num_kb,
                                                                           reinterpret_cast<uint8_t*>(pack_ws));
+            if (pack_only) return gnn_launch_status();
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return (int)e;
             // programmatic dependent of the pack kernel above (see pack_b_kernel)

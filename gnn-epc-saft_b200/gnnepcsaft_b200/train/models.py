@@ -175,20 +175,20 @@ def _al(t, *dims):
     return (t.data_ptr() & 15) == 0 and all((d & 3) == 0 for d in dims)
 
 
-def _lin_fwd(mm, X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, plan=None, key=None):
+def _lin_fwd(mm, X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, plan=None, key=None, pa=None):
     if mm < 0 or not _al(X, ldx, K):
         _c("gnn_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy)
     else:
-        ws, nb = _site_ws(plan, key, N, K, Y.device)
-        _c("gnn_tc_linear_fwd", X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, mm, ws, nb)
+        _gemm_site(plan, pa if key is not None else None, key, N, K, Y.device, "gnn_tc_linear_fwd", 5,
+                   X, ldx, W, ldw, bias, M, N, K, act, Y, ldy, mm)
 
 
-def _lin_dgrad(mm, dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx):
+def _lin_dgrad(mm, dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, pa=None, key=None):
     if mm < 0 or not _al(dY, lddy, N):
         _c("gnn_linear_dgrad", dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx)
     else:
-        ws = _pack_ws(dX.device)
-        _c("gnn_tc_linear_dgrad", dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, mm, ws, ws.numel())
+        _gemm_site(None, pa if key is not None else None, key, K, N, dX.device, "gnn_tc_linear_dgrad", 4,
+                   dY, lddy, W, ldw, M, N, K, accumulate, dX, lddx, mm)
 
 
 def _lin_wgrad(mm, dY, lddy, X, ldx, M, N, K, dW, lddw, db):
@@ -206,12 +206,15 @@ def _post_fwd(mm, *args, ws=None):
         _c("gnn_tc_pna_post_fwd", *args, mm, buf, nb)
 
 
-def _post_dgrad(mm, *args):
+def _post_dgrad(mm, *args, pa=None, key=None):
     if mm < 0:
         _c("gnn_pna_post_dgrad", *args)
     else:
-        ws = _pack_ws(args[-1].device)
-        _c("gnn_tc_pna_post_dgrad", *args, mm, ws, ws.numel())
+        # (dO, scal, wpost, tower stride, n, F, F_out, towers, dx, gA): image = towers x [4F rows, K = 3 F_out]; with
+        # dx given the entry point runs further GEMMs through the same workspace -> shared scratch
+        n_rows, k = args[7] * 4 * args[5], 3 * args[6]
+        _gemm_site(None, pa if (key is not None and args[8] is None) else None, key, n_rows, k, args[-1].device,
+                   "gnn_tc_pna_post_dgrad", 4, *args, mm)
 
 
 def _post_wgrad(mm, *args):
@@ -296,6 +299,74 @@ class _InferPlan:
             buf = torch.empty((int(nbytes) + 4095) // 4096 * 4096, dtype=torch.uint8, device=self.device)
             self.sites[key] = buf
         return buf, (buf.numel() if self.filling else -buf.numel())
+
+
+class _PackAhead:
+    """Training steps under CUDA-graph capture: the pack kernel of every tensor-core GEMM call site (weights -> the
+    swizzled hi/lo tile image) runs on a second stream that depends on the weights only, into a buffer of its own, and
+    the GEMM is launched with the `already packed` convention of the ABI (row count 0 = pack only, negative workspace
+    size = packed).  In the captured graph the ~45 pack kernels of a step form a branch beside the data path instead of
+    sitting between consecutive GEMMs.
+    The per-site buffers are allocated by EAGER steps (the engine runs one before it captures) and live as long as the
+    model: a block handed out by the caching allocator inside a capture may have belonged to a tensor whose last
+    main-stream user the pack branch is not ordered after.  Eager steps keep the in-line pack (two more host calls per
+    GEMM would cost more than the few microseconds of GPU time); a site without a buffer packs in line too."""
+
+    PACK_AHEAD = os.environ.get("GNN_B200_PACK_AHEAD", "1") != "0"
+    _streams = {}
+
+    def __init__(self, model, dev, capturing):
+        self.dev = dev
+        self.capturing = capturing
+        if not hasattr(model, "_train_sites"):
+            model._train_sites = {}
+        self.sites = model._train_sites
+        if capturing:
+            key = dev.index if dev.index is not None else torch.cuda.current_device()
+            if key not in _PackAhead._streams:
+                _PackAhead._streams[key] = torch.cuda.Stream(device=dev)
+            self.side = _PackAhead._streams[key]
+            fork = torch.cuda.Event()
+            fork.record()                       # the weights (and the folded Vx) are final from here on
+            self.side.wait_event(fork)
+
+    @staticmethod
+    def begin(model, dev, training, save, mm):
+        if _PackAhead.PACK_AHEAD and training and save and mm >= 0 and dev.type == "cuda":
+            return _PackAhead(model, dev, torch.cuda.is_current_stream_capturing())
+        return None
+
+    def call(self, key, nbytes, name, n_idx, args):
+        buf = self.sites.get(key)
+        if not self.capturing:
+            if buf is None or buf.numel() < nbytes:
+                self.sites[key] = torch.empty((int(nbytes) + 4095) // 4096 * 4096, dtype=torch.uint8, device=self.dev)
+            buf = None
+        if buf is None or buf.numel() < nbytes:
+            ws = _pack_ws(self.dev)
+            _c(name, *args, ws, ws.numel())
+            return
+        a0 = list(args)
+        a0[n_idx] = 0
+        with torch.cuda.stream(self.side):
+            _c(name, *a0, buf, buf.numel())
+            ev = torch.cuda.Event()
+            ev.record()
+        torch.cuda.current_stream().wait_event(ev)
+        _c(name, *args, buf, -buf.numel())
+
+
+def _gemm_site(plan, pa, key, n_rows, k, dev, name, n_idx, *args):
+    """Tensor-core GEMM with a packed weight operand; `args` = the ABI arguments before (pack_ws, pack_ws_bytes) and
+    args[n_idx] the row count.  plan: inference (image persists while the weights do); pa: training step."""
+    if plan is not None:
+        ws, nb = plan.site(key, _pack_bound(n_rows, k))
+        _c(name, *args, ws, nb)
+    elif pa is not None:
+        pa.call(key, _pack_bound(n_rows, k), name, n_idx, args)
+    else:
+        ws = _pack_ws(dev)
+        _c(name, *args, ws, ws.numel())
 
 
 def _pack_bound(n_rows: int, k: int) -> int:
@@ -722,6 +793,8 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
             _c("gnn_pna_fold_fwd", conv0.post_nns[0][0].weight, tsp, conv0.pre_nns[0][0].weight, tower_stride_pre,
                layer_stride, L, F, Fo, T, Vx_all)
 
+    pa = _PackAhead.begin(model, dev, training, save, mm)     # after the fold: the dgrad images read Vx
+
     if use_tiles:
         x = _conv_stack_tiles(model, x, graph, tab, Vx_all, layer_stride, tower_stride_pre, plan)
 
@@ -743,11 +816,11 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         rec.Vx = None
         if fold:
             rec.Vx = Vx_all[l]
-            ws, nb = _site_ws(plan, ("projsrc", l), C, F, dev)
-            _c("gnn_tc_pna_projsrc_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, nb)
+            _gemm_site(plan, pa, ("projsrc", l), C, F, dev, "gnn_tc_pna_projsrc_fwd", 5,
+                       x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj)
         elif mm_proj >= 0:
-            ws, nb = _site_ws(plan, ("proj", l), 2 * C, F, dev)
-            _c("gnn_tc_pna_proj_fwd", x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj, ws, nb)
+            _gemm_site(plan, pa, ("proj", l), 2 * C, F, dev, "gnn_tc_pna_proj_fwd", 5,
+                       x, pre0.weight, ts_pre, pre0.bias, bs_pre, n, F, T, P, mm_proj)
         else:
             for t in range(T):
                 w = conv.pre_nns[t][0].weight
@@ -789,14 +862,14 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         O = torch.empty(n, H, **f32)
         post_rows = T * 3 * ((Fo + 63) // 64) * 64         # rows of the packed post image (towers x scaler groups x tiles)
         if fuse_agg:
-            ws, nb = _site_ws(plan, ("postf_agg", l), post_rows, 5 * F + 32, dev)
-            _c("gnn_tc_pna_postf_agg_fwd", x, P, tab[l], g.rowptr, g.col_src, g.col_code, scal, rec.Vx,
-               conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T,
-               1 if pp.post_layers > 1 else 0, O, A, mm, ws, nb)
+            _gemm_site(plan, pa, ("postf_agg", l), post_rows, 5 * F + 32, dev, "gnn_tc_pna_postf_agg_fwd", 12,
+                       x, P, tab[l], g.rowptr, g.col_src, g.col_code, scal, rec.Vx,
+                       conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias, bias_stride_post, n, F,
+                       Fo, T, 1 if pp.post_layers > 1 else 0, O, A, mm)
         elif fold:
-            ws, nb = _site_ws(plan, ("postf", l), post_rows, 5 * F, dev)
-            _c("gnn_tc_pna_postf_fwd", x, A, scal, rec.Vx, conv.post_nns[0][0].weight, tower_stride_post,
-               conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O, mm, ws, nb)
+            _gemm_site(plan, pa, ("postf", l), post_rows, 5 * F, dev, "gnn_tc_pna_postf_fwd", 8,
+                       x, A, scal, rec.Vx, conv.post_nns[0][0].weight, tower_stride_post,
+                       conv.post_nns[0][0].bias, bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O, mm)
         else:
             _post_fwd(mm, x, A, scal, conv.post_nns[0][0].weight, tower_stride_post, conv.post_nns[0][0].bias,
                bias_stride_post, n, F, Fo, T, 1 if pp.post_layers > 1 else 0, O,
@@ -808,7 +881,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
             for t in range(T):
                 lin = conv.post_nns[t][2 * k]
                 _lin_fwd(mm, O[:, t * Fo:], H, lin.weight, Fo, lin.bias, n, Fo, Fo, 0 if last else 1,
-                   O2[:, t * Fo:], H, plan, ("postk", l, k, t))
+                   O2[:, t * Fo:], H, plan, ("postk", l, k, t), pa)
             os_.append(O2)
             O = O2
         rec.os = os_
@@ -819,7 +892,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
             x = fused
         else:
             y = torch.empty(n, H, **f32)
-            _lin_fwd(mm, O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H, plan, ("lin_plain", l))
+            _lin_fwd(mm, O, H, conv.lin.weight, H, conv.lin.bias, n, H, H, 0, y, H, plan, ("lin_plain", l), pa)
             rec.y = y
             x, rec.stats, rec.bn_batch = _bn_forward(y, bn, training, rec.x_in if pp.skip_connections else None, True,
                                                      valid_nodes)
@@ -848,7 +921,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         rec.inp, rec.lin, rec.bn = hcur, lin, bn
         z = torch.empty(hcur.shape[0], lin.out_features, **f32)
         _lin_fwd(mm, hcur, lin.in_features, lin.weight, lin.in_features, lin.bias, hcur.shape[0],
-           lin.out_features, lin.in_features, 0, z, lin.out_features, plan, hkey)
+           lin.out_features, lin.in_features, 0, z, lin.out_features, plan, hkey, pa)
         rec.z = z
         if bn is not None:
             hcur, rec.stats, rec.bn_batch = _bn_forward(z, bn, training, None, True, valid_graphs)
@@ -872,6 +945,7 @@ def _forward_impl(model: PNAPCSAFT, x_idx, edge_index, edge_attr, batch, num_gra
         sv.layer_stride, sv.tower_stride_pre = layer_stride, tower_stride_pre
         sv.training, sv.mm, sv.fold = training, mm, fold
         sv.compact, sv.valid_nodes, sv.valid_graphs = compact, valid_nodes, valid_graphs
+        sv.pa = pa
     return out, sv
 
 
@@ -928,6 +1002,10 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
     n, g = sv.n, sv.g
     f32 = dict(dtype=torch.float32, device=dev)
     arena = model._arena
+    # pack-ahead continues on the forward's second stream when forward and backward are in the same capture
+    pa = getattr(sv, "pa", None)
+    if pa is not None and pa.capturing != torch.cuda.is_current_stream_capturing():
+        pa = None
 
     def gview(p: torch.Tensor) -> torch.Tensor:
         off = model._offset_of(p)
@@ -953,7 +1031,7 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
            lin.in_features, gview(lin.weight), lin.in_features, gview(lin.bias))
         dprev = torch.empty(rows, lin.in_features, **f32)
         _lin_dgrad(mm, d, lin.out_features, lin.weight, lin.in_features, rows, lin.out_features,
-           lin.in_features, 0, dprev, lin.in_features)
+           lin.in_features, 0, dprev, lin.in_features, pa, ("head_dgrad", id(lin)))
         d = dprev
     # ---- pool
     dx = torch.empty(n, H, **f32)
@@ -972,7 +1050,7 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
         O_last = rec.os[-1]
         _lin_wgrad(mm, dy, H, O_last, H, n, H, H, gview(conv.lin.weight), H, gview(conv.lin.bias))
         dO = torch.empty(n, H, **f32)
-        _lin_dgrad(mm, dy, H, conv.lin.weight, H, n, H, H, 0, dO, H)
+        _lin_dgrad(mm, dy, H, conv.lin.weight, H, n, H, H, 0, dO, H, pa, ("lin_dgrad", l))
         # extra post layers
         for k in reversed(range(1, pp.post_layers)):
             O_in = rec.os[k - 1]
@@ -981,18 +1059,20 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
                 lin = conv.post_nns[t][2 * k]
                 _lin_wgrad(mm, dO[:, t * Fo:], H, O_in[:, t * Fo:], H, n, Fo, Fo, gview(lin.weight), Fo,
                    gview(lin.bias))
-                _lin_dgrad(mm, dO[:, t * Fo:], H, lin.weight, Fo, n, Fo, Fo, 0, dprev[:, t * Fo:], H)
+                _lin_dgrad(mm, dO[:, t * Fo:], H, lin.weight, Fo, n, Fo, Fo, 0, dprev[:, t * Fo:], H, pa,
+                           ("postk_dgrad", l, k, t))
             _c("gnn_relu_bwd", dprev, O_in, n * H)
             dO = dprev
         ts_post, bs_post = rec.post_strides
         w0, b0 = conv.post_nns[0][0].weight, conv.post_nns[0][0].bias
         if sv.fold:
-            _backward_layer_folded(model, sv, rec, l, dO, dx, dtab, gview)
+            _backward_layer_folded(model, sv, rec, l, dO, dx, dtab, gview, pa)
             continue
         _post_wgrad(mm, dO, x_in, rec.A, rec.scal, n, F, Fo, T, gview(w0), ts_post, gview(b0), bs_post)
         gA = torch.empty(n, T * 4 * F, **f32)
         fused_dx = mm >= 0        # tensor-core path: every node-feature gradient of the layer in ONE GEMM (below)
-        _post_dgrad(mm, dO, rec.scal, w0, ts_post, n, F, Fo, T, None if fused_dx else dx, gA)
+        _post_dgrad(mm, dO, rec.scal, w0, ts_post, n, F, Fo, T, None if fused_dx else dx, gA, pa=pa,
+                    key=("post_dgrad", l))
         # aggregation + message
         dP = torch.empty(n, 2 * C, **f32)
         if pp.pre_layers == 1:
@@ -1026,8 +1106,8 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
             pre0 = conv.pre_nns[0][0]
             ts_pre, bs_pre = rec.pre_strides
             _c("gnn_tc_pna_proj_wgrad", dP, x_in, n, F, T, gview(pre0.weight), ts_pre, gview(pre0.bias), bs_pre, mm)
-            ws = _pack_ws(dev)
-            _c("gnn_tc_pna_dx_dgrad", dP, dO, pre0.weight, ts_pre, w0, ts_post, n, F, Fo, T, 1, dx, mm, ws, ws.numel())
+            _gemm_site(None, pa, ("dx_dgrad", l), F, 2 * C + T * Fo, dev, "gnn_tc_pna_dx_dgrad", 6,
+                       dP, dO, pre0.weight, ts_pre, w0, ts_post, n, F, Fo, T, 1, dx, mm)
         else:
             for t in range(T):
                 lin = conv.pre_nns[t][0]
@@ -1056,7 +1136,7 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
     del arena
 
 
-def _backward_layer_folded(model, sv, rec, l, dO, dx, dtab, gview):
+def _backward_layer_folded(model, sv, rec, l, dO, dx, dtab, gview, pa=None):
     """Message / aggregate / post_nns[.][0] part of one conv layer's backward with the destination projection
     folded into the post weights (csrc/fold.cu): accumulates into dx and the parameter gradients."""
     conv = model.convs[l]
@@ -1074,7 +1154,7 @@ def _backward_layer_folded(model, sv, rec, l, dO, dx, dtab, gview):
     _c("gnn_tc_pna_postf_wgrad", dO, rec.x_in, rec.A, rec.scal, n, F, Fo, T, gview(w0), ts_post, gview(b0), bs_post,
        dVx, mm)
     gA = torch.empty(n, T * 4 * F, **f32)
-    _post_dgrad(mm, dO, rec.scal, w0, ts_post, n, F, Fo, T, None, gA)
+    _post_dgrad(mm, dO, rec.scal, w0, ts_post, n, F, Fo, T, None, gA, pa=pa, key=("post_dgrad", l))
     dPs = torch.empty(n, C, **f32)
     dq = torch.empty(max(g.ep, 1), C, **f32) if DETERMINISTIC_SCATTER else None
     nb = _lib.query("gnn_pna_aggregate_bwd_workspace_bytes", T, F)
@@ -1084,8 +1164,8 @@ def _backward_layer_folded(model, sv, rec, l, dO, dx, dtab, gview):
     if dq is not None:
         _c("gnn_slot_sum_by_source", dq, g.srcptr, g.src_slot, n, C, dPs, C)
     _c("gnn_tc_pna_projsrc_wgrad", dPs, rec.x_in, n, F, T, gview(pre0.weight), ts_pre, gview(pre0.bias), bs_pre, mm)
-    ws = _pack_ws(dev)
-    _c("gnn_tc_pna_dxf_dgrad", dPs, dO, rec.scal, pre0.weight, ts_pre, rec.Vx, n, F, Fo, T, 1, dx, mm, ws, ws.numel())
+    _gemm_site(None, pa, ("dxf_dgrad", l), F, C + 3 * T * Fo, dev, "gnn_tc_pna_dxf_dgrad", 6,
+               dPs, dO, rec.scal, pre0.weight, ts_pre, rec.Vx, n, F, Fo, T, 1, dx, mm)
 
 
 class _PNAFunction(torch.autograd.Function):

@@ -289,7 +289,10 @@ int gnn_pna_post_wgrad(const float* dO, const float* x, const float* A, const fl
  * wide one (hidden 256) needs 8 MiB for its post GEMM (the host passes 32 MiB).  Too small -> unpacked (slower) path.
  * pack_ws_bytes < 0 (inference with constant weights): pack_ws (|pack_ws_bytes| bytes) already holds the image that an
  * earlier call of the same entry point with the same weights and shapes packed there - the pack kernel is skipped;
- * GNN_ERR_WORKSPACE if the image cannot have fitted. */
+ * GNN_ERR_WORKSPACE if the image cannot have fitted.
+ * Row count 0 with pack_ws_bytes > 0: only the weight image is packed (no activation pointer is read; NULL is fine),
+ * for the same call with the real row count and -pack_ws_bytes later.  The host issues these packs of a captured
+ * training step on a second stream, where they depend on the weights only and leave the step's critical path. */
 int gnn_tc_linear_fwd(const float* X, int64_t ldx, const float* W, int64_t ldw, const float* bias,
                       int64_t M, int N, int K, int act, float* Y, int64_t ldy, int precision,
                       void* pack_ws, int64_t pack_ws_bytes, void* stream);
