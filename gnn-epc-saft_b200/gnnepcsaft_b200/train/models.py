@@ -166,6 +166,18 @@ def _c(name, *args):
         _lib.call(name, *args, _lib.stream_ptr())
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev: torch.device, i: int = 0) -> "torch.cuda.Stream":
+    """Extra streams per device for small jobs that only have to finish before the end of the backward pass."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), i)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
 # dense-stage dispatch: which kernel family runs the Linear layers
 MATMUL_MODES = {"simt": -1, "tf32x3": 0, "bf16": 2}
 
@@ -1117,22 +1129,44 @@ def _backward_impl(model: PNAPCSAFT, sv, dout: torch.Tensor, grad_arena: torch.T
                 _lin_dgrad(mm, dP[:, t * F:], 2 * C, lin.weight, 3 * F, n, F, F, 1, dx, H)
                 _lin_dgrad(mm, dP[:, C + t * F:], 2 * C, lin.weight[:, F:], 3 * F, n, F, F, 1, dx, H)
 
-    # ---- encoders
-    atom_tab = model.node_embed.atom_embedding_list[0].weight
-    _c("gnn_atom_embed_u8_bwd" if sv.compact else "gnn_atom_embed_bwd", sv.x_idx, n, dx, model._consts(dev),
-       sum(ATOM_FEATURE_DIMS), H, gview(atom_tab))
+    # ---- encoders: three small, latency-bound jobs that write disjoint gradient regions (atom tables | post weights +
+    # destination third of the pre weights | bond tables, edge encoders, bond third of the pre weights).  None of them
+    # fills the GPU, so the last two run on side streams beside the AtomEncoder backward (parallel branches of a
+    # captured step); with per-call timing on they stay in line.
+    tails = []
     if L > 0:
         conv0 = model.convs[0]
         if sv.fold:     # dVx of all layers -> post_nns / pre_nns (destination third) weight gradients, one launch
             w0, wp0 = conv0.post_nns[0][0].weight, conv0.pre_nns[0][0].weight
             tsp = model._offset_of(conv0.post_nns[1][0].weight) - model._offset_of(w0)
-            _c("gnn_pna_fold_bwd", sv.dVx, w0, tsp, wp0, sv.tower_stride_pre, sv.layer_stride, L, F, Fo, T, gview(w0),
-               gview(wp0))
+            tails.append(lambda: _c("gnn_pna_fold_bwd", sv.dVx, w0, tsp, wp0, sv.tower_stride_pre, sv.layer_stride, L, F,
+                                    Fo, T, gview(w0), gview(wp0)))
         denc = torch.empty(L, NUM_BOND_CODES, F, **f32)
-        _c("gnn_bond_table_bwd", dtab, model.edge_embed.bond_embedding_list[0].weight, conv0.edge_encoder.weight,
-           conv0.pre_nns[0][0].weight, sv.tower_stride_pre, sv.layer_stride, L, sv.enc, H, T, denc,
-           gview(model.edge_embed.bond_embedding_list[0].weight), gview(conv0.edge_encoder.weight),
-           gview(conv0.edge_encoder.bias), gview(conv0.pre_nns[0][0].weight))
+        tails.append(lambda: _c(
+            "gnn_bond_table_bwd", dtab, model.edge_embed.bond_embedding_list[0].weight, conv0.edge_encoder.weight,
+            conv0.pre_nns[0][0].weight, sv.tower_stride_pre, sv.layer_stride, L, sv.enc, H, T, denc,
+            gview(model.edge_embed.bond_embedding_list[0].weight), gview(conv0.edge_encoder.weight),
+            gview(conv0.edge_encoder.bias), gview(conv0.pre_nns[0][0].weight)))
+    joins = []
+    if dev.type == "cuda" and _PROFILER is None and tails:
+        fork = torch.cuda.Event()
+        fork.record()
+        for i, job in enumerate(tails):
+            st = _side_stream(dev, i)
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                job()
+                ev = torch.cuda.Event()
+                ev.record()
+            joins.append(ev)
+        tails = []
+    atom_tab = model.node_embed.atom_embedding_list[0].weight
+    _c("gnn_atom_embed_u8_bwd" if sv.compact else "gnn_atom_embed_bwd", sv.x_idx, n, dx, model._consts(dev),
+       sum(ATOM_FEATURE_DIMS), H, gview(atom_tab))
+    for job in tails:
+        job()
+    for ev in joins:
+        torch.cuda.current_stream().wait_event(ev)
     del arena
 
 
