@@ -330,11 +330,11 @@ class _PackAhead:
     def __init__(self, model, dev, capturing):
         self.dev = dev
         self.capturing = capturing
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
         if not hasattr(model, "_train_sites"):
             model._train_sites = {}
-        self.sites = model._train_sites
+        self.sites = model._train_sites.setdefault(key, {})      # per device: the model may be moved
         if capturing:
-            key = dev.index if dev.index is not None else torch.cuda.current_device()
             if key not in _PackAhead._streams:
                 _PackAhead._streams[key] = torch.cuda.Stream(device=dev)
             self.side = _PackAhead._streams[key]
